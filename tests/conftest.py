@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
+
+
+@pytest.fixture(scope="session")
+def params_base(tmp_path_factory):
+    """A $PHYLOCSF_BASE-like directory re-emitted from tests/golden (reference file formats)."""
+    from tools import golden_params
+
+    d = str(tmp_path_factory.mktemp("phylocsf_base"))
+    golden_params.materialize(d)
+    golden_params.write_examples(d)
+    return d

@@ -1,0 +1,159 @@
+"""Pins the CPU oracle (oracle/) against every known answer the reference's own tests hold for the
+scoring path:
+  lib/CamlPaml/test.ml:8-54   2-state tree (A,(B,C)), 8 leaf patterns, eps 1e-3
+  lib/CamlPaml/test.ml:56-99  JC69 BEAGLE tiny test, lnL = -1574.63623 +- 1e-3
+  src/test.ml:27-59           four end-to-end runs on PhyloCSF_Examples (score windows + coordinates)
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+from tools import golden_params as gp
+
+
+# ---------------------------------------------------------------- lib/CamlPaml/test.ml:8-54
+@pytest.mark.parametrize("lvs", [(a, b, c) for a in (0, 1) for b in (0, 1) for c in (0, 1)])
+def test_two_state_pruning(lvs):
+    t = o.Tree.of_newick(o.newick_parse("(A,(B,C))"))
+    assert t.children[3] == (1, 2) and t.children[4] == (0, 3)
+    sm0 = np.array([[0.8, 0.2], [0.25, 0.75]])
+    sm1 = np.array([[0.9, 0.1], [0.85, 0.15]])
+    prior = np.array([0.6, 0.4])
+
+    class M:  # a PhyloModel with hand-set pms, as PhyloLik.prepare t sms prior (test.ml:31)
+        tree = t
+        pms = np.ascontiguousarray(np.stack([sm0, sm1, sm1, sm1]))
+
+        @staticmethod
+        def prior():
+            return prior
+
+    a = [np.array([1.0 if lvs[i] == s else 0.0 for s in (0, 1)]) for i in range(3)]
+    a3 = (sm1 @ a[1]) * (sm1 @ a[2])
+    a4 = (sm0 @ a[0]) * (sm1 @ a3)
+    z = float(prior @ a4)
+    z_o, alpha = o.likelihood_column(M, list(lvs))
+    assert abs(z_o - z) < 1e-3 and abs(z_o - z) < 1e-15
+    post_root = alpha[1] * prior / z_o  # PhyloLik.ml:137-138 at the root
+    np.testing.assert_allclose(post_root, prior * a4 / z, atol=1e-3)
+    np.testing.assert_allclose(alpha[0], a3, atol=1e-15)
+
+
+# ---------------------------------------------------------------- lib/CamlPaml/test.ml:56-99
+_BEAGLE = None
+
+
+def _beagle():
+    global _BEAGLE
+    if _BEAGLE is None:
+        import json
+
+        with open(os.path.join(os.path.dirname(__file__), "golden", "beagle_tiny.json")) as f:
+            _BEAGLE = json.load(f)
+    return _BEAGLE
+
+
+def test_beagle_tiny_jc69():
+    d = _beagle()
+    t = o.Tree.of_newick(o.newick_parse(d["newick"]))
+    q = o.QDiag(np.array([[-3.0, 1, 1, 1], [1, -3.0, 1, 1], [1, 1, -3.0, 1], [1, 1, 1, -3.0]])).scaled(1.0 / 3.0)
+    np.testing.assert_allclose(q.equilibrium(), [0.25] * 4, atol=1e-12)
+    m = o.PhyloModel(t, q, t.branches)
+    idx = {"A": 0, "C": 1, "G": 2, "T": 3}
+    seqs = [d["human"], d["chimp"], d["gorilla"]]
+    codes = np.array([[idx.get(s[i], 4) for s in seqs] for i in range(len(seqs[0]))], dtype=np.uint8)
+    ll = o.lpr_columns(m, codes)[0]
+    assert abs(ll - (-1574.63623)) < 1e-3
+
+
+# ---------------------------------------------------------------- src/test.ml:27-59
+def _run(params_base, pset, fn, **kw):
+    opts = o.Options(**kw)
+    ps = o.load_paramset(os.path.join(params_base, "PhyloCSF_Parameters", pset), opts)
+    lines = o.process_alignment(ps, opts, fn, gp.example_lines(fn))
+    return lines[-1].split("\t")
+
+
+def test_tal_AA(params_base):
+    ans = _run(params_base, "12flies", "tal-AA.fa", anc_comp=True)
+    assert ans[1] == "score(decibans)"
+    assert 297.62 < float(ans[2]) < 297.63
+    assert 48.25 < float(ans[3]) < 48.26
+
+
+def test_aldh2_ex5_out(params_base):
+    ans = _run(params_base, "29mammals", "ALDH2.exon5.fa", anc_comp=True)
+    assert ans[1] == "score(decibans)"
+    assert -178.93 < float(ans[2]) < -178.92
+    assert -38.29 < float(ans[3]) < -38.28
+
+
+def test_aldh2_ex5_in(params_base):
+    ans = _run(params_base, "29mammals", "ALDH2.exon5.fa", frames=6)
+    assert ans[1] == "max_score(decibans)"
+    assert 218.26 < float(ans[2]) < 218.27
+    assert int(ans[3]) == 1 and int(ans[4]) == 111 and ans[5] == "+"
+
+
+@pytest.mark.slow
+def test_aldh2_mRNA(params_base):
+    ans = _run(params_base, "29mammals", "Aldh2.mRNA.fa", orf="ATGStop", frames=3, remove_ref_gaps=True, aa=True)
+    assert ans[1] == "max_score(decibans)"
+    assert 2013.92 < float(ans[2]) < 2013.93
+    assert int(ans[3]) == 343 and int(ans[4]) == 1899
+    assert ans[5].startswith("MLRAALTTVRRGPRLSRLLSAAA")
+
+
+def test_tal_AA_fixed_restatement_value(params_base):
+    """BASELINE.json configs[0]; no reference-published value, 361.6876 is restatement-derived."""
+    ans = _run(params_base, "12flies", "tal-AA.fa", anc_comp=True, strategy="fixed")
+    assert abs(float(ans[2]) - 361.6876) < 1e-4 and abs(float(ans[3]) - 48.0241) < 1e-4
+
+
+# ---------------------------------------------------------------- P(t) semantics, Q.ml:211-249
+def test_pt_fixups_and_prior(params_base):
+    s, pi = o.read_ecm(os.path.join(params_base, "PhyloCSF_Parameters", "23flies_coding.ECM"))
+    assert abs(pi.sum() - 1.0) > 5e-7  # the file prior is not normalised
+    q = o.QDiag(o.ecm_q(s, pi))
+    eq = q.equilibrium()
+    assert abs(eq.sum() - 1.0) < 1e-12
+    np.testing.assert_allclose(eq, pi / pi.sum(), rtol=1e-8)
+    for t in (0.0, 1e-3, 0.1, 1.0, 10.0):
+        P = q.to_Pt(t)
+        assert (P >= 0).all()
+        np.testing.assert_allclose(P.sum(axis=1), 1.0, atol=1e-12)
+        if t == 0.0:
+            np.testing.assert_allclose(P, np.eye(64), atol=1e-9)
+    with pytest.raises(o.OracleFailure):
+        q.to_Pt(-1.0)
+
+
+def test_tree_numbering_58mammals(params_base):
+    t = o.Tree.of_newick(o.newick_parse(open(os.path.join(params_base, "PhyloCSF_Parameters", "58mammals.nh")).read()))
+    assert t.n_leaves == 58 and t.size == 115 and t.root == 114
+    assert t.labels[0] == "Human" and t.labels[1] == "Chimp"
+    assert t.children[58] == (0, 1)  # first cherry is the first internal node (post-order)
+    for i in range(58, 115):
+        lc, rc = t.children[i]
+        assert lc < i and rc < i
+
+
+def test_ocaml_random_is_deterministic():
+    a = [o.OCamlRandom(0).rawfloat() for _ in range(3)]
+    assert a[0] == a[1] == a[2] and 0.0 <= a[0] < 1.0
+
+
+def test_find_orfs_modes():
+    # hand-traced against src/PhyloCSF.ml:134-196
+    assert o.find_orfs("CCATGAAACCCGGGTTTTAGCCATGCCCAAATGAGGG", 2, "ATGStop", 2) == [(2, 16)]
+    # nested ATGs share the stop; the later start is reported first (starts is a LIFO list)
+    assert o.find_orfs("ATGAAAATGCCCTAAGG", 0, "ATGStop", 2) == [(6, 11), (0, 11)]
+    assert o.find_orfs("ATGAAAATGCCCTAAGG", 0, "ATGStop", 3) == [(0, 11)]
+    # StopStop: first ORF runs from the frame start to the codon before the stop; the tail ORF
+    # runs off the end of the alignment
+    assert o.find_orfs("CCCAAATAGGGGTTTCC", 0, "StopStop", 1) == [(0, 5), (9, 14)]
+    assert o.find_orfs("CCCAAATAGGGGTTTCC", 0, "ToFirstStop", 1) == [(0, 5)]
+    assert o.find_orfs("CCCAAATAGGGGTTTCC", 0, "FromLastStop", 1) == [(9, 14)]
