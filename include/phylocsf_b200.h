@@ -1,0 +1,153 @@
+/*
+ * phylocsf_b200.h — C ABI of the B200-native PhyloCSF scoring path.
+ *
+ * The reference (mlin/PhyloCSF, OCaml + GSL) has no FFI of its own; the seam this library replaces
+ * is the pair of closures
+ *     PhyloCSFModel.lpr_leaves : instance -> leaf array array -> float -> {lpr_leaves; elpr_anc; inst}
+ *                                                          (src/PhyloCSFModel.ml:67-82)
+ *     OmegaModel.lpr_leaves    : instance -> leaf array array -> float   (src/OmegaModel.ml:137-144)
+ * together with the CamlPaml calls underneath them: PhyloModel.make's P(t) loop
+ * (lib/CamlPaml/PhyloModel.ml:12-25 -> Q.Diag.real_to_Pt, lib/CamlPaml/Q.ml:211-249) and the
+ * pruning pass PhyloLik.prepare / likelihood / node_posterior (lib/CamlPaml/PhyloLik.ml:46-138).
+ * INTEGRATION.md shows the OCaml C stubs a maintainer would add to bind these entry points.
+ *
+ * Conventions: every array argument is a caller-owned HOST pointer (pinned or pageable); matrices
+ * are FP64 row-major; all entry points return PCSF_OK (0) or a negative PCSF_ERR_* code, with a
+ * message available from pcsf_last_error(). One context per GPU; a context is not re-entrant.
+ * There is no CPU fallback: pcsf_create fails if no CUDA device is usable.
+ */
+#ifndef PHYLOCSF_B200_H
+#define PHYLOCSF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCSF_K 64                 /* Codon64.dim, lib/CamlPaml/Code.ml:135 */
+#define PCSF_CODE_MARGINALIZE 64  /* `Marginalize (lib/CamlPaml/PhyloLik.ml:9); codes 0..63 = `Certain i */
+
+/* Return codes. The reference raises OCaml exceptions at the same points. */
+#define PCSF_OK 0
+#define PCSF_ERR_INVALID_ARG (-1) /* Invalid_argument (PhyloLik.ml:51-58, PhyloModel.ml:14-23, Q.ml:212) */
+#define PCSF_ERR_CUDA (-2)        /* CUDA runtime / driver error, or no device */
+#define PCSF_ERR_STATE (-3)       /* call order violated (e.g. lpr before tree_set / batch_upload) */
+#define PCSF_ERR_NUMERIC (-4)     /* a Failure of the numeric path; see the status arrays */
+#define PCSF_ERR_NOMEM (-5)
+
+/* Bits of the per-P-set / per-evaluation status words (0 = fine). */
+#define PCSF_ST_NEG_T 1        /* t < 0                          -> Invalid_argument, Q.ml:212 */
+#define PCSF_ST_NEG_ENTRY 2    /* expm entry < -1e-6             -> Failure, Q.ml:235-236 */
+#define PCSF_ST_ROWSUM 4       /* |row sum - 1| > 1e-6           -> Failure, Q.ml:243-244 */
+#define PCSF_ST_DIAG_ASSERT 8  /* not (0 < new diagonal <= 1)    -> Assert_failure, Q.ml:245 */
+#define PCSF_ST_NOT_FINITE 16  /* lpr is -inf/nan (z underflowed to 0; the reference prints -inf/nan) */
+#define PCSF_ST_BRACKET 32     /* Brent: endpoints do not enclose a minimum -> Gsl_exn via Fit.ml:13 */
+#define PCSF_ST_RANDOM_INIT 64 /* Fit.find_init took its random branch (Fit.ml:33-41); informational */
+
+typedef struct pcsf_ctx pcsf_ctx;
+
+const char *pcsf_version(void);
+int pcsf_device_count(void);
+
+/* Context = one GPU: stream, resident P tables, staged batch.  (No reference analogue.) */
+int pcsf_create(int device_id, pcsf_ctx **out);
+void pcsf_destroy(pcsf_ctx *ctx);
+const char *pcsf_last_error(const pcsf_ctx *ctx);
+/* Run all work of this context on an existing cudaStream_t (so a caller can bracket calls with its
+ * own CUDA events). NULL restores the context's own stream. */
+int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
+
+/*
+ * Tree shape = T.t (lib/CamlPaml/T.mli:3, T.ml:57-112): leaves are nodes 0..n_leaves-1 in
+ * left-to-right order, internal nodes follow in post-order, root = 2*n_leaves-2.
+ *   children[2*(i-n_leaves)+{0,1}] = (left,right) child of internal node i; both < i.
+ *   branch_len[i], i < 2*n_leaves-2 = length of the branch above node i (T.branch), >= 0.
+ */
+int pcsf_tree_set(pcsf_ctx *ctx, int n_leaves, const int32_t *children, const double *branch_len);
+
+/*
+ * A diagonalised rate matrix = Q.Diag.t, real path (Q.ml:96-141): Q = S * diag(lambda) * Sinv, plus
+ * the root prior the caller wants (PhyloModel.prior: the Q equilibrium when prior=None,
+ * PhyloModel.ml:30-32 / Q.ml:153-177). model_id is a small non-negative slot number chosen by the
+ * caller (e.g. 0 = coding ECM, 1 = noncoding ECM); setting a slot again replaces it.
+ */
+int pcsf_model_set(pcsf_ctx *ctx, int model_id, const double *S, const double *Sinv, const double *lambda,
+                   const double *prior);
+
+/*
+ * K1. P(t) for every branch and every tree scale: P[scale][br] = real_to_Pt(Q, scales[scale] *
+ * branch_len[br]) (PhyloModel.ml:17 looping Q.ml:211-249, with the clamp / row-sum / diagonal
+ * fix-ups and tol = 1e-6). status[scale] (optional) receives PCSF_ST_* bits. Returns
+ * PCSF_ERR_NUMERIC if any status is non-zero (the tables are still usable for the others).
+ * The tables stay resident on the device until the next pt_build of the same model.
+ */
+int pcsf_pt_build(pcsf_ctx *ctx, int model_id, int nscales, const double *scales, int32_t *status);
+
+/* PhyloModel.p (PhyloModel.ml:29): copy one built P(t) back, 64x64 row-major (row = parent state,
+ * column = child state, PhyloLik.mli:17). For tests and diagnostics. */
+int pcsf_pt_get(pcsf_ctx *ctx, int model_id, int scale_idx, int branch, double *P_out);
+
+/*
+ * Stage a batch of regions = many `leaf array array`s (the output of pleaves, src/PhyloCSF.ml:219-246).
+ *   region_off[r] .. region_off[r+1]-1 = codon columns of region r (nregions+1 offsets, region_off[0]=0);
+ *   codes[col * n_leaves + leaf]       = 0..63 (`Certain) or PCSF_CODE_MARGINALIZE.
+ * Empty regions are allowed (their lpr is 0, like an empty Array.iter). Replaces any previous batch.
+ */
+int pcsf_batch_upload(pcsf_ctx *ctx, int64_t nregions, const int64_t *region_off, const uint8_t *codes);
+
+/*
+ * Stage a batch of alignments and let the device do pleaves: one region per requested frame.
+ *   nt[a]: alignment a = n_leaves rows (tree-leaf order; absent species = a row of '-') of aln_len[a]
+ *   bytes each, at nt + aln_off[a]; bytes are the alignment characters after u->t.
+ *   frames = 1, 3 or 6 (AsIs candidate_regions, src/PhyloCSF.ml:198-205). Regions are numbered
+ *   alignment-major, then frame (+0,+1,+2,-0,-1,-2).
+ */
+int pcsf_batch_upload_alignments(pcsf_ctx *ctx, int64_t nalign, const int64_t *aln_off, const int32_t *aln_len,
+                                 const uint8_t *nt, int frames);
+int64_t pcsf_batch_nregions(const pcsf_ctx *ctx);
+int64_t pcsf_batch_ncols(const pcsf_ctx *ctx);
+
+/*
+ * K2-K4. lpr_leaves for every region of the staged batch under each listed (model, scale):
+ *   out_lpr[m*nregions + r]      = sum over columns of log z          (PhyloCSFModel.ml:79)
+ *   out_elpr_anc[m*nregions + r] = sum over columns of post_root . log prior (PhyloCSFModel.ml:80-81)
+ * scale_idx may be NULL (= scale 0 of each model). out_elpr_anc / out_status may be NULL.
+ */
+int pcsf_lpr_all(pcsf_ctx *ctx, int n_models, const int32_t *model_ids, const int32_t *scale_idx,
+                 double *out_lpr, double *out_elpr_anc, int32_t *out_status);
+
+/*
+ * The same for an explicit list of evaluations: evaluation e scores region eval_region[e] under
+ * model eval_model[e] with P tables of scale index eval_scale[e]. This is the shape one round of
+ * batched maximize_lpr candidates has (one candidate rho per (region, model)).
+ */
+int pcsf_lpr(pcsf_ctx *ctx, int64_t n_evals, const int32_t *eval_model, const int32_t *eval_scale,
+             const int64_t *eval_region, double *out_lpr, double *out_elpr_anc, int32_t *out_status);
+
+/* Per-column terms of the most recent pcsf_lpr_all call for its m-th listed model:
+ * col_logz[c] = log z(c), col_anc[c] = post_root(c) . log prior (either may be NULL). */
+int pcsf_column_terms(pcsf_ctx *ctx, int m, double *col_logz, double *col_anc);
+
+/*
+ * Batched PhyloCSFModel.maximize_lpr (src/PhyloCSFModel.ml:84-99): for every region of the batch,
+ * Fit.find_init (lib/CamlPaml/Fit.ml:27-48) then GSL Brent on -lpr(rho) until (ub-lb)/x <= accuracy,
+ * then the final re-evaluation f(x). Each round builds P(t) for all live candidates (K1) and scores
+ * them (K2-K4) in one launch sequence. out_* have nregions entries; out_nevals (optional) counts
+ * likelihood evaluations per region.
+ */
+int pcsf_maximize_lpr(pcsf_ctx *ctx, int model_id, double init, double lo, double hi, double accuracy,
+                      double *out_rho, double *out_lpr, double *out_elpr_anc, int32_t *out_status,
+                      int32_t *out_nevals);
+
+/* Timing of the most recent call, measured with CUDA events on the context's stream:
+ * which = 0 pruning kernel (K2+K3 fused), 1 region reduction (K4), 2 P(t) build (K1),
+ * 3 H2D copies, 4 D2H copies. Returns milliseconds, or a negative value if not recorded. */
+double pcsf_last_ms(const pcsf_ctx *ctx, int which);
+/* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
+int64_t pcsf_launch_count(const pcsf_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLOCSF_B200_H */

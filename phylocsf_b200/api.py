@@ -1,0 +1,136 @@
+"""Thin Python face of the C ABI (include/phylocsf_b200.h): numpy in, numpy out. Used by the parity
+tests and bench.py; the drop-in host (C++ CLI) links the same library directly."""
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+
+
+class PcsfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pcsf error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One GPU. Mirrors the call order of the reference seam: tree (T.t) -> models (Q.Diag.t + prior)
+    -> P(t) tables (PhyloModel.make) -> leaves (pleaves) -> lpr_leaves / maximize_lpr."""
+
+    def __init__(self, device=0):
+        self._L = N.load()
+        h = ctypes.c_void_p()
+        rc = self._L.pcsf_create(device, ctypes.byref(h))
+        if rc != N.PCSF_OK:
+            raise PcsfError(rc, "pcsf_create(device=%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
+        self._h = h
+        self.n_leaves = 0
+        self.nregions = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pcsf_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, ok_numeric=False):
+        if rc == N.PCSF_OK or (ok_numeric and rc == -4):
+            return rc
+        raise PcsfError(rc, self._L.pcsf_last_error(self._h).decode())
+
+    def stream_set(self, cuda_stream_ptr):
+        self._check(self._L.pcsf_stream_set(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def tree_set(self, n_leaves, children, branch_len):
+        ch = np.ascontiguousarray(children, dtype=np.int32).ravel()
+        bl = _f64(branch_len)[: 2 * n_leaves - 2]
+        assert ch.size == 2 * (n_leaves - 1) and bl.size == 2 * n_leaves - 2
+        self._check(self._L.pcsf_tree_set(self._h, n_leaves, N.ptr(ch), N.ptr(np.ascontiguousarray(bl))))
+        self.n_leaves = n_leaves
+
+    def model_set(self, model_id, S, Sinv, lam, prior):
+        S, Sinv, lam, prior = _f64(S), _f64(Sinv), _f64(lam), _f64(prior)
+        assert S.shape == (64, 64) and Sinv.shape == (64, 64) and lam.shape == (64,) and prior.shape == (64,)
+        self._check(self._L.pcsf_model_set(self._h, model_id, N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior)))
+
+    def pt_build(self, model_id, scales, check=True):
+        sc = _f64(np.atleast_1d(scales))
+        st = np.zeros(sc.size, dtype=np.int32)
+        self._check(self._L.pcsf_pt_build(self._h, model_id, sc.size, N.ptr(sc), N.ptr(st)), ok_numeric=not check)
+        return st
+
+    def pt_get(self, model_id, scale_idx, branch):
+        P = np.empty((64, 64))
+        self._check(self._L.pcsf_pt_get(self._h, model_id, scale_idx, branch, N.ptr(P)))
+        return P
+
+    def batch_upload(self, region_off, codes):
+        """region_off: int64 [nregions+1]; codes: uint8 [total_cols, n_leaves] (numpy) or a raw host
+        address (int) of such a buffer, e.g. pinned memory."""
+        ro = np.ascontiguousarray(region_off, dtype=np.int64)
+        if isinstance(codes, np.ndarray):
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            assert codes.size == int(ro[-1]) * self.n_leaves, "codes must be [total_cols, n_leaves]"
+        self._check(self._L.pcsf_batch_upload(self._h, ro.size - 1, N.ptr(ro), N.ptr(codes)))
+        self.nregions = ro.size - 1
+
+    def batch_upload_alignments(self, aln_off, aln_len, nt, frames):
+        ao = np.ascontiguousarray(aln_off, dtype=np.int64)
+        al = np.ascontiguousarray(aln_len, dtype=np.int32)
+        if isinstance(nt, np.ndarray):
+            nt = np.ascontiguousarray(nt, dtype=np.uint8)
+        self._check(self._L.pcsf_batch_upload_alignments(self._h, ao.size, N.ptr(ao), N.ptr(al), N.ptr(nt), frames))
+        self.nregions = int(self._L.pcsf_batch_nregions(self._h))
+
+    @property
+    def ncols(self):
+        return int(self._L.pcsf_batch_ncols(self._h))
+
+    def lpr_all(self, model_ids, scale_idx=None, out=None):
+        mids = np.ascontiguousarray(model_ids, dtype=np.int32)
+        sidx = None if scale_idx is None else np.ascontiguousarray(scale_idx, dtype=np.int32)
+        m, R = mids.size, self.nregions
+        if out is None:
+            lpr, elpr = np.empty((m, R)), np.empty((m, R))
+        else:
+            lpr, elpr = out
+        st = np.zeros((m, R), dtype=np.int32)
+        self._check(self._L.pcsf_lpr_all(self._h, m, N.ptr(mids), N.ptr(sidx), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
+        return lpr, elpr, st
+
+    def lpr(self, eval_model, eval_scale, eval_region):
+        em = np.ascontiguousarray(eval_model, dtype=np.int32)
+        es = np.ascontiguousarray(eval_scale, dtype=np.int32)
+        er = np.ascontiguousarray(eval_region, dtype=np.int64)
+        n = em.size
+        lpr, elpr, st = np.empty(n), np.empty(n), np.zeros(n, dtype=np.int32)
+        self._check(self._L.pcsf_lpr(self._h, n, N.ptr(em), N.ptr(es), N.ptr(er), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
+        return lpr, elpr, st
+
+    def column_terms(self, m):
+        n = self.ncols
+        a, b = np.empty(n), np.empty(n)
+        self._check(self._L.pcsf_column_terms(self._h, m, N.ptr(a), N.ptr(b)))
+        return a, b
+
+    def maximize_lpr(self, model_id, init=1.0, lo=1e-2, hi=10.0, accuracy=0.01, check=True):
+        R = self.nregions
+        rho, lpr, elpr = np.empty(R), np.empty(R), np.empty(R)
+        st, ne = np.zeros(R, dtype=np.int32), np.zeros(R, dtype=np.int32)
+        self._check(self._L.pcsf_maximize_lpr(self._h, model_id, init, lo, hi, accuracy, N.ptr(rho), N.ptr(lpr),
+                                              N.ptr(elpr), N.ptr(st), N.ptr(ne)), ok_numeric=not check)
+        return rho, lpr, elpr, st, ne
+
+    def last_ms(self, which):
+        return float(self._L.pcsf_last_ms(self._h, which))
+
+    @property
+    def launch_count(self):
+        return int(self._L.pcsf_launch_count(self._h))

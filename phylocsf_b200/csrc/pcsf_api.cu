@@ -1,0 +1,762 @@
+// pcsf_api.cu — the C ABI declared in include/phylocsf_b200.h: context, resident tables, batch
+// staging, launch sequencing, and the batched Brent driver. No torch types; plain CUDA runtime.
+#include "../../include/phylocsf_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pcsf_brent.hpp"
+#include "pcsf_kernels.cuh"
+
+using namespace pcsf;
+
+#define PCSF_VERSION_STRING "phylocsf_b200 0.1 (sm_100a)"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Model {
+    bool set = false;
+    double* d_params = nullptr;  // S | Sinv | lambda | prior | logprior  (64*64*2 + 3*64 doubles)
+    DevBuf tables;               // [nscales][n_branches][PT_SLOT]
+    DevBuf d_scales, d_status;
+    int nscales = 0;
+    std::vector<int32_t> status;
+    const double* S() const { return d_params; }
+    const double* Sinv() const { return d_params + 4096; }
+    const double* lambda() const { return d_params + 8192; }
+    const double* prior() const { return d_params + 8192 + 64; }
+    const double* logprior() const { return d_params + 8192 + 128; }
+};
+
+}  // namespace
+
+struct pcsf_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    // tree
+    int n_leaves = 0, n_branches = 0;
+    std::vector<int32_t> children;
+    std::vector<double> branch_len;
+    double* d_branch_len = nullptr;
+    Op* d_ops = nullptr;
+    std::vector<Op> ops;
+    int n_gemm = 0, max_levels = 0;
+    // models
+    std::vector<Model> models;
+    // batch
+    int64_t nregions = -1, total_cols = 0;
+    std::vector<int64_t> region_off;
+    DevBuf d_region_off, d_codes, d_nt, d_aln_off, d_aln_len;
+    // work + outputs
+    DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
+    int last_all_models = 0;
+    // timing
+    cudaEvent_t ev[10];
+    double ms[5] = {-1, -1, -1, -1, -1};
+    int64_t launches = 0;
+    int prune_smem_optin = 0;
+};
+
+namespace {
+
+int fail(pcsf_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, PCSF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+int reserve(pcsf_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return PCSF_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, PCSF_ERR_NOMEM, "cudaMalloc of " + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return PCSF_OK;
+}
+#define TRY(x)                    \
+    do {                          \
+        int r_ = (x);             \
+        if (r_ != PCSF_OK) return r_; \
+    } while (0)
+
+// ---- tree program ------------------------------------------------------------------------------
+// Post-order schedule that keeps the partial of the current subtree in registers. At a node with two
+// internal children the child needing more live partials goes first (Sethi-Ullman), its message is
+// parked on the stack while the other subtree is evaluated.
+struct ProgramBuilder {
+    int nl;
+    const std::vector<int32_t>& ch;
+    std::vector<Op> ops;
+    std::vector<int> need;
+    int height = 0, max_height = 0, n_gemm = 0;
+    ProgramBuilder(int n_leaves, const std::vector<int32_t>& children) : nl(n_leaves), ch(children), need(2 * n_leaves - 1, 0) {}
+    int lc(int i) const { return ch[2 * (i - nl)]; }
+    int rc(int i) const { return ch[2 * (i - nl) + 1]; }
+    void compute_need() {
+        for (int i = nl; i < 2 * nl - 1; i++) {  // children precede parents in T numbering
+            const int l = lc(i), r = rc(i);
+            const bool li = l >= nl, ri = r >= nl;
+            if (!li && !ri) need[i] = 1;
+            else if (li && ri) {
+                const int a = std::max(need[l], need[r]), b = std::min(need[l], need[r]);
+                need[i] = std::max(a, b + 1);
+            } else need[i] = need[li ? l : r];
+        }
+    }
+    void emit(int i) {
+        // iterative post-order would also do; depth is bounded by the tree height (<= n_leaves)
+        const int l = lc(i), r = rc(i);
+        const bool li = l >= nl, ri = r >= nl;
+        if (!li && !ri) {
+            ops.push_back({OP_CHERRY, l, r, 0});
+        } else if (li && ri) {
+            const int first = need[l] >= need[r] ? l : r, second = first == l ? r : l;
+            emit(first);
+            ops.push_back({OP_GEMM_PUSH, first, 0, height});
+            n_gemm++;
+            height++;
+            max_height = std::max(max_height, height);
+            emit(second);
+            height--;
+            ops.push_back({OP_GEMM_POP, second, 0, height});
+            n_gemm++;
+        } else {
+            const int inner = li ? l : r, leaf = li ? r : l;
+            emit(inner);
+            ops.push_back({OP_GEMM_LEAF, inner, leaf, 0});
+            n_gemm++;
+        }
+    }
+};
+
+int prune_fixed_smem(const pcsf_ctx* c) {
+    const int ops_bytes = ((int)(c->ops.size() * sizeof(Op)) + 15) & ~15;
+    const int codes_bytes = (TILE_COLS * c->n_leaves + 15) & ~15;
+    return 2 * FRAG_BYTES + 64 + ops_bytes + codes_bytes;
+}
+
+// Launch K2+K3 over `spans`, then K4 over the given segments. Outputs land in ctx->d_lpr/d_elpr.
+int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vector<PSet>& psets, int64_t out_cols) {
+    std::vector<Span> spans = spans_in;
+    int64_t tiles = 0;
+    for (auto& s : spans) {
+        s.tile0 = tiles;
+        tiles += (s.ncols + TILE_COLS - 1) / TILE_COLS;
+    }
+    // spans with zero columns would break the tile0 search (duplicate tile0): drop them
+    spans.erase(std::remove_if(spans.begin(), spans.end(), [](const Span& s) { return s.ncols == 0; }), spans.end());
+    TRY(reserve(ctx, ctx->d_out_logz, sizeof(double) * std::max<int64_t>(out_cols, 1)));
+    TRY(reserve(ctx, ctx->d_out_anc, sizeof(double) * std::max<int64_t>(out_cols, 1)));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (tiles > 0) {
+        TRY(reserve(ctx, ctx->d_spans, sizeof(Span) * spans.size()));
+        TRY(reserve(ctx, ctx->d_psets, sizeof(PSet) * psets.size()));
+        CU(cudaMemcpyAsync(ctx->d_spans.p, spans.data(), sizeof(Span) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_psets.p, psets.data(), sizeof(PSet) * psets.size(), cudaMemcpyHostToDevice, ctx->stream));
+        const int fixed = prune_fixed_smem(ctx);
+        int smem_levels = std::max(0, std::min(ctx->max_levels, (ctx->prune_smem_optin - fixed) / STACK_LEVEL_BYTES));
+        const int global_levels = ctx->max_levels - smem_levels;
+        const int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
+        if (global_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * global_levels * STACK_LEVEL_BYTES));
+        PruneParams p;
+        p.ops = ctx->d_ops;
+        p.n_ops = (int)ctx->ops.size();
+        p.n_leaves = ctx->n_leaves;
+        p.n_gemm = ctx->n_gemm;
+        p.spans = (const Span*)ctx->d_spans.p;
+        p.n_spans = (int)spans.size();
+        p.n_tiles = tiles;
+        p.psets = (const PSet*)ctx->d_psets.p;
+        p.codes = (const uint8_t*)ctx->d_codes.p;
+        p.out_logz = (double*)ctx->d_out_logz.p;
+        p.out_anc = (double*)ctx->d_out_anc.p;
+        p.smem_levels = smem_levels;
+        p.global_stack = (uint8_t*)ctx->d_gstack.p;
+        p.global_levels = global_levels;
+        p.codes_smem_bytes = (TILE_COLS * ctx->n_leaves + 15) & ~15;
+        const int smem = fixed + smem_levels * STACK_LEVEL_BYTES;
+        if (smem > ctx->prune_smem_optin)
+            return fail(ctx, PCSF_ERR_INVALID_ARG, "tree too large for the pruning kernel's shared memory (" + std::to_string(smem) + " bytes)");
+        CU(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        prune_kernel<<<grid, PRUNE_THREADS, smem, ctx->stream>>>(p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    return PCSF_OK;
+}
+
+int run_reduce(pcsf_ctx* ctx, int64_t n_segs) {
+    TRY(reserve(ctx, ctx->d_lpr, sizeof(double) * std::max<int64_t>(n_segs, 1)));
+    TRY(reserve(ctx, ctx->d_elpr, sizeof(double) * std::max<int64_t>(n_segs, 1)));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (n_segs > 0) {
+        const int threads = 256;
+        const int64_t blocks = (n_segs * 32 + threads - 1) / threads;
+        region_reduce_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+            (const double*)ctx->d_out_logz.p, (const double*)ctx->d_out_anc.p, (const int64_t*)ctx->d_seg_begin.p,
+            (const int64_t*)ctx->d_seg_end.p, n_segs, (double*)ctx->d_lpr.p, (double*)ctx->d_elpr.p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    return PCSF_OK;
+}
+
+int finish_timing(pcsf_ctx* ctx) {
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+    ctx->ms[0] = t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]));
+    ctx->ms[1] = t;
+    return PCSF_OK;
+}
+
+int check_ready(pcsf_ctx* ctx, bool need_batch) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (ctx->n_leaves == 0) return fail(ctx, PCSF_ERR_STATE, "pcsf_tree_set has not been called");
+    if (need_batch && ctx->nregions < 0) return fail(ctx, PCSF_ERR_STATE, "no batch staged (pcsf_batch_upload)");
+    return PCSF_OK;
+}
+
+int check_model(pcsf_ctx* ctx, int model_id, int scale) {
+    if (model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set)
+        return fail(ctx, PCSF_ERR_STATE, "model " + std::to_string(model_id) + " has not been set (pcsf_model_set)");
+    const Model& m = ctx->models[model_id];
+    if (scale < 0 || scale >= m.nscales)
+        return fail(ctx, PCSF_ERR_STATE, "model " + std::to_string(model_id) + " has no P tables for scale index " + std::to_string(scale) + " (pcsf_pt_build)");
+    return PCSF_OK;
+}
+
+PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
+    const Model& m = ctx->models[model_id];
+    PSet ps;
+    ps.tables = (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT;
+    ps.prior = m.prior();
+    ps.logprior = m.logprior();
+    return ps;
+}
+
+int pt_build_device(pcsf_ctx* ctx, Model& m, int nscales, const double* scales) {
+    TRY(reserve(ctx, m.tables, sizeof(double) * (size_t)nscales * ctx->n_branches * PT_SLOT));
+    TRY(reserve(ctx, m.d_scales, sizeof(double) * nscales));
+    TRY(reserve(ctx, m.d_status, sizeof(int32_t) * nscales));
+    CU(cudaMemcpyAsync(m.d_scales.p, scales, sizeof(double) * nscales, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(m.d_status.p, 0, sizeof(int32_t) * nscales, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    // gridDim.y is limited to 65535: slice the scales
+    for (int s0 = 0; s0 < nscales; s0 += 32768) {
+        const int ns = std::min(32768, nscales - s0);
+        dim3 grid(ctx->n_branches, ns);
+        pt_build_kernel<<<grid, 256, 0, ctx->stream>>>(m.S(), m.Sinv(), m.lambda(), ctx->d_branch_len,
+                                                       (const double*)m.d_scales.p + s0, ctx->n_leaves,
+                                                       (double*)m.tables.p + (size_t)s0 * ctx->n_branches * PT_SLOT,
+                                                       (int32_t*)m.d_status.p + s0, 1e-6);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+    m.nscales = nscales;
+    m.status.assign(nscales, 0);
+    CU(cudaMemcpyAsync(m.status.data(), m.d_status.p, sizeof(int32_t) * nscales, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
+    ctx->ms[2] = t;
+    return PCSF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* pcsf_version(void) { return PCSF_VERSION_STRING; }
+
+int pcsf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pcsf_create(int device_id, pcsf_ctx** out) {
+    if (!out) return PCSF_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device_id < 0 || device_id >= n) {
+        cudaGetLastError();
+        return PCSF_ERR_CUDA;  // no CPU fallback by design
+    }
+    pcsf_ctx* ctx = new pcsf_ctx();
+    ctx->device = device_id;
+    auto bail = [&](cudaError_t er) {
+        (void)er;
+        delete ctx;
+        return PCSF_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return bail(e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail(e);
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->prune_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    ctx->stream = ctx->own_stream;
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e);
+    *out = ctx;
+    return PCSF_OK;
+}
+
+void pcsf_destroy(pcsf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    auto fr = [](DevBuf& b) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+    };
+    for (auto& m : ctx->models) {
+        if (m.d_params) cudaFree(m.d_params);
+        fr(m.tables);
+        fr(m.d_scales);
+        fr(m.d_status);
+    }
+    DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
+                      &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
+                      &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack};
+    for (auto* b : bufs) fr(*b);
+    if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
+    if (ctx->d_ops) cudaFree(ctx->d_ops);
+    for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* pcsf_last_error(const pcsf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pcsf_stream_set(pcsf_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PCSF_OK;
+}
+
+int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const double* branch_len) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (n_leaves < 2 || !children || !branch_len) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: need n_leaves >= 2");
+    CU(cudaSetDevice(ctx->device));
+    const int n = 2 * n_leaves - 1;
+    std::vector<int> seen(n, 0);
+    for (int i = n_leaves; i < n; i++)
+        for (int k = 0; k < 2; k++) {
+            const int c = children[2 * (i - n_leaves) + k];
+            if (c < 0 || c >= i || seen[c]++) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: children do not follow the T numbering (child < parent, each node one parent)");
+        }
+    for (int i = 0; i < n - 1; i++) {
+        if (!seen[i]) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: node without a parent");
+        if (!(branch_len[i] >= 0.0)) return fail(ctx, PCSF_ERR_INVALID_ARG, "CamlPaml.PhyloModel.make: negative or NaN branch length");  // PhyloModel.ml:16
+    }
+    if ((TILE_COLS * n_leaves + 15) / 16 * 16 + 2 * FRAG_BYTES + 4096 > ctx->prune_smem_optin)
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: too many leaves for the shared-memory code tile");
+    ctx->n_leaves = n_leaves;
+    ctx->n_branches = n - 1;
+    ctx->children.assign(children, children + 2 * (n_leaves - 1));
+    ctx->branch_len.assign(branch_len, branch_len + (n - 1));
+    ProgramBuilder pb(n_leaves, ctx->children);
+    pb.compute_need();
+    pb.emit(n - 1);
+    pb.ops.push_back({OP_ROOT, 0, 0, 0});
+    ctx->ops = pb.ops;
+    ctx->n_gemm = pb.n_gemm;
+    ctx->max_levels = pb.max_height;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_branch_len) CU(cudaFree(ctx->d_branch_len));
+    if (ctx->d_ops) CU(cudaFree(ctx->d_ops));
+    CU(cudaMalloc(&ctx->d_branch_len, sizeof(double) * (n - 1)));
+    CU(cudaMalloc(&ctx->d_ops, sizeof(Op) * ctx->ops.size()));
+    CU(cudaMemcpy(ctx->d_branch_len, branch_len, sizeof(double) * (n - 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_ops, ctx->ops.data(), sizeof(Op) * ctx->ops.size(), cudaMemcpyHostToDevice));
+    for (auto& m : ctx->models) m.nscales = 0;  // tables belong to the previous tree
+    return PCSF_OK;
+}
+
+int pcsf_model_set(pcsf_ctx* ctx, int model_id, const double* S, const double* Sinv, const double* lambda,
+                   const double* prior) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (model_id < 0 || model_id > (1 << 20) || !S || !Sinv || !lambda || !prior)
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_model_set: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if ((int)ctx->models.size() <= model_id) ctx->models.resize(model_id + 1);
+    Model& m = ctx->models[model_id];
+    std::vector<double> h(8192 + 192);
+    memcpy(h.data(), S, 4096 * 8);
+    memcpy(h.data() + 4096, Sinv, 4096 * 8);
+    memcpy(h.data() + 8192, lambda, 64 * 8);
+    memcpy(h.data() + 8192 + 64, prior, 64 * 8);
+    for (int i = 0; i < 64; i++) h[8192 + 128 + i] = log(prior[i]);  // anc_lprior, src/PhyloCSFModel.ml:74
+    if (!m.d_params) CU(cudaMalloc(&m.d_params, h.size() * 8));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(m.d_params, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    m.set = true;
+    m.nscales = 0;
+    return PCSF_OK;
+}
+
+int pcsf_pt_build(pcsf_ctx* ctx, int model_id, int nscales, const double* scales, int32_t* status) {
+    TRY(check_ready(ctx, false));
+    if (model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set)
+        return fail(ctx, PCSF_ERR_STATE, "pcsf_pt_build: model not set");
+    if (nscales < 1 || !scales) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_pt_build: need at least one scale");
+    CU(cudaSetDevice(ctx->device));
+    Model& m = ctx->models[model_id];
+    TRY(pt_build_device(ctx, m, nscales, scales));
+    bool bad = false;
+    for (int i = 0; i < nscales; i++) {
+        if (status) status[i] = m.status[i];
+        bad |= m.status[i] != 0;
+    }
+    if (bad) return fail(ctx, PCSF_ERR_NUMERIC, "CamlPaml.Q.real_to_Pt: P(t) failed its checks for at least one scale (see status)");
+    return PCSF_OK;
+}
+
+int pcsf_pt_get(pcsf_ctx* ctx, int model_id, int scale_idx, int branch, double* P_out) {
+    TRY(check_ready(ctx, false));
+    TRY(check_model(ctx, model_id, scale_idx));
+    if (branch < 0 || branch >= ctx->n_branches || !P_out) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_pt_get: bad branch");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<double> slot(PT_SLOT);
+    const double* src = (const double*)ctx->models[model_id].tables.p + ((size_t)scale_idx * ctx->n_branches + branch) * PT_SLOT;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(slot.data(), src, PT_SLOT_BYTES, cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 64; a++)
+        for (int b = 0; b < 64; b++)
+            P_out[a * 64 + b] = branch < ctx->n_leaves ? slot[b * 64 + a] : slot[frag_index(a, b)];
+    return PCSF_OK;
+}
+
+int pcsf_batch_upload(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off, const uint8_t* codes) {
+    TRY(check_ready(ctx, false));
+    if (nregions < 0 || !region_off || region_off[0] != 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload: bad region offsets");
+    for (int64_t r = 0; r < nregions; r++)
+        if (region_off[r + 1] < region_off[r]) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload: region offsets must be non-decreasing");
+    const int64_t total = region_off[nregions];
+    if (total > 0 && !codes) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload: null codes");
+    CU(cudaSetDevice(ctx->device));
+    TRY(reserve(ctx, ctx->d_codes, (size_t)std::max<int64_t>(total, 1) * ctx->n_leaves));
+    TRY(reserve(ctx, ctx->d_region_off, sizeof(int64_t) * (nregions + 1)));
+    CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+    if (total > 0) CU(cudaMemcpyAsync(ctx->d_codes.p, codes, (size_t)total * ctx->n_leaves, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_region_off.p, region_off, sizeof(int64_t) * (nregions + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[7], ctx->stream));
+    ctx->region_off.assign(region_off, region_off + nregions + 1);
+    ctx->nregions = nregions;
+    ctx->total_cols = total;
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+    ctx->ms[3] = t;
+    return PCSF_OK;
+}
+
+int pcsf_batch_upload_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off, const int32_t* aln_len,
+                                 const uint8_t* nt, int frames) {
+    TRY(check_ready(ctx, false));
+    if (nalign < 0 || !aln_off || !aln_len || (frames != 1 && frames != 3 && frames != 6))
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload_alignments: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t nregions = nalign * frames;
+    std::vector<int64_t> roff(nregions + 1, 0);
+    int64_t nt_bytes = 0;
+    for (int64_t a = 0; a < nalign; a++) {
+        if (aln_len[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment length");
+        nt_bytes = std::max<int64_t>(nt_bytes, aln_off[a] + (int64_t)aln_len[a] * ctx->n_leaves);
+        for (int f = 0; f < frames; f++) {
+            const int rem = aln_len[a] - (f % 3);
+            roff[a * frames + f + 1] = roff[a * frames + f] + (rem >= 3 ? rem / 3 : 0);  // pos+2 <= hi, PhyloCSF.ml:226
+        }
+    }
+    const int64_t total = roff[nregions];
+    if (nt_bytes > 0 && !nt) return fail(ctx, PCSF_ERR_INVALID_ARG, "null nucleotide buffer");
+    TRY(reserve(ctx, ctx->d_nt, std::max<int64_t>(nt_bytes, 1)));
+    TRY(reserve(ctx, ctx->d_aln_off, sizeof(int64_t) * std::max<int64_t>(nalign, 1)));
+    TRY(reserve(ctx, ctx->d_aln_len, sizeof(int32_t) * std::max<int64_t>(nalign, 1)));
+    TRY(reserve(ctx, ctx->d_codes, (size_t)std::max<int64_t>(total, 1) * ctx->n_leaves));
+    TRY(reserve(ctx, ctx->d_region_off, sizeof(int64_t) * (nregions + 1)));
+    CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+    if (nt_bytes > 0) CU(cudaMemcpyAsync(ctx->d_nt.p, nt, nt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (nalign > 0) {
+        CU(cudaMemcpyAsync(ctx->d_aln_off.p, aln_off, sizeof(int64_t) * nalign, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_aln_len.p, aln_len, sizeof(int32_t) * nalign, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->d_region_off.p, roff.data(), sizeof(int64_t) * (nregions + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[7], ctx->stream));
+    if (nregions > 0) {
+        frame_codes_kernel<<<(unsigned)nregions, 128, 0, ctx->stream>>>(
+            (const uint8_t*)ctx->d_nt.p, (const int64_t*)ctx->d_aln_off.p, (const int32_t*)ctx->d_aln_len.p,
+            (const int64_t*)ctx->d_region_off.p, nregions, frames, ctx->n_leaves, (uint8_t*)ctx->d_codes.p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    ctx->region_off = roff;
+    ctx->nregions = nregions;
+    ctx->total_cols = total;
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+    ctx->ms[3] = t;
+    return PCSF_OK;
+}
+
+int64_t pcsf_batch_nregions(const pcsf_ctx* ctx) { return ctx ? ctx->nregions : -1; }
+int64_t pcsf_batch_ncols(const pcsf_ctx* ctx) { return ctx ? ctx->total_cols : -1; }
+
+int pcsf_lpr_all(pcsf_ctx* ctx, int n_models, const int32_t* model_ids, const int32_t* scale_idx, double* out_lpr,
+                 double* out_elpr_anc, int32_t* out_status) {
+    TRY(check_ready(ctx, true));
+    if (n_models < 1 || !model_ids || !out_lpr) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_lpr_all: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<Span> spans;
+    std::vector<PSet> psets;
+    for (int m = 0; m < n_models; m++) {
+        const int sc = scale_idx ? scale_idx[m] : 0;
+        TRY(check_model(ctx, model_ids[m], sc));
+        psets.push_back(make_pset(ctx, model_ids[m], sc));
+        spans.push_back(Span{0, (int64_t)m * ctx->total_cols, 0, (int32_t)0, m});
+        spans.back().ncols = (int32_t)ctx->total_cols;
+    }
+    if (ctx->total_cols > 0x7fffffffLL) return fail(ctx, PCSF_ERR_INVALID_ARG, "batch too large: more than 2^31-1 codon columns");
+    const int64_t n_segs = ctx->nregions * n_models;
+    TRY(run_prune(ctx, spans, psets, ctx->total_cols * n_models));
+    TRY(reserve(ctx, ctx->d_seg_begin, sizeof(int64_t) * std::max<int64_t>(n_segs, 1)));
+    TRY(reserve(ctx, ctx->d_seg_end, sizeof(int64_t) * std::max<int64_t>(n_segs, 1)));
+    if (n_segs > 0) {
+        make_segments_kernel<<<(unsigned)((n_segs + 255) / 256), 256, 0, ctx->stream>>>(
+            (const int64_t*)ctx->d_region_off.p, ctx->nregions, n_models, ctx->total_cols, (int64_t*)ctx->d_seg_begin.p,
+            (int64_t*)ctx->d_seg_end.p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    TRY(run_reduce(ctx, n_segs));
+    CU(cudaEventRecord(ctx->ev[8], ctx->stream));
+    if (n_segs > 0) {
+        CU(cudaMemcpyAsync(out_lpr, ctx->d_lpr.p, sizeof(double) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_elpr_anc) CU(cudaMemcpyAsync(out_elpr_anc, ctx->d_elpr.p, sizeof(double) * n_segs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaEventRecord(ctx->ev[9], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    TRY(finish_timing(ctx));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]));
+    ctx->ms[4] = t;
+    ctx->last_all_models = n_models;
+    if (out_status)
+        for (int m = 0; m < n_models; m++) {
+            const int st = ctx->models[model_ids[m]].status[scale_idx ? scale_idx[m] : 0];
+            for (int64_t r = 0; r < ctx->nregions; r++)
+                out_status[m * ctx->nregions + r] = st | (std::isfinite(out_lpr[m * ctx->nregions + r]) ? 0 : PCSF_ST_NOT_FINITE);
+        }
+    return PCSF_OK;
+}
+
+int pcsf_lpr(pcsf_ctx* ctx, int64_t n_evals, const int32_t* eval_model, const int32_t* eval_scale,
+             const int64_t* eval_region, double* out_lpr, double* out_elpr_anc, int32_t* out_status) {
+    TRY(check_ready(ctx, true));
+    if (n_evals < 0 || !eval_model || !eval_region || !out_lpr) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_lpr: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<Span> spans;
+    std::vector<PSet> psets;
+    std::vector<int64_t> seg_b(n_evals), seg_e(n_evals);
+    spans.reserve(n_evals);
+    psets.reserve(n_evals);
+    int64_t out = 0;
+    int prev_model = -1, prev_scale = -1;
+    for (int64_t e = 0; e < n_evals; e++) {
+        const int sc = eval_scale ? eval_scale[e] : 0;
+        const int64_t r = eval_region[e];
+        if (r < 0 || r >= ctx->nregions) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_lpr: region index out of range");
+        if (eval_model[e] != prev_model || sc != prev_scale) {
+            TRY(check_model(ctx, eval_model[e], sc));
+            psets.push_back(make_pset(ctx, eval_model[e], sc));
+            prev_model = eval_model[e];
+            prev_scale = sc;
+        }
+        const int64_t c0 = ctx->region_off[r], nc = ctx->region_off[r + 1] - c0;
+        seg_b[e] = out;
+        seg_e[e] = out + nc;
+        // merge with the previous span when it continues the same columns under the same P set
+        if (!spans.empty() && spans.back().pset == (int32_t)psets.size() - 1 &&
+            spans.back().col0 + spans.back().ncols == c0 && spans.back().out0 + spans.back().ncols == out &&
+            (int64_t)spans.back().ncols + nc < 0x7fffffffLL) {
+            spans.back().ncols += (int32_t)nc;
+        } else {
+            Span s{c0, out, 0, (int32_t)nc, (int32_t)psets.size() - 1};
+            spans.push_back(s);
+        }
+        out += nc;
+    }
+    TRY(run_prune(ctx, spans, psets, out));
+    TRY(reserve(ctx, ctx->d_seg_begin, sizeof(int64_t) * std::max<int64_t>(n_evals, 1)));
+    TRY(reserve(ctx, ctx->d_seg_end, sizeof(int64_t) * std::max<int64_t>(n_evals, 1)));
+    if (n_evals > 0) {
+        CU(cudaMemcpyAsync(ctx->d_seg_begin.p, seg_b.data(), sizeof(int64_t) * n_evals, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_seg_end.p, seg_e.data(), sizeof(int64_t) * n_evals, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TRY(run_reduce(ctx, n_evals));
+    if (n_evals > 0) {
+        CU(cudaMemcpyAsync(out_lpr, ctx->d_lpr.p, sizeof(double) * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_elpr_anc) CU(cudaMemcpyAsync(out_elpr_anc, ctx->d_elpr.p, sizeof(double) * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    TRY(finish_timing(ctx));
+    ctx->last_all_models = 0;
+    if (out_status)
+        for (int64_t e = 0; e < n_evals; e++)
+            out_status[e] = ctx->models[eval_model[e]].status[eval_scale ? eval_scale[e] : 0] |
+                            (std::isfinite(out_lpr[e]) ? 0 : PCSF_ST_NOT_FINITE);
+    return PCSF_OK;
+}
+
+int pcsf_column_terms(pcsf_ctx* ctx, int m, double* col_logz, double* col_anc) {
+    TRY(check_ready(ctx, true));
+    if (m < 0 || m >= ctx->last_all_models) return fail(ctx, PCSF_ERR_STATE, "pcsf_column_terms: no matching pcsf_lpr_all result");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t off = (size_t)m * ctx->total_cols, n = (size_t)ctx->total_cols;
+    if (col_logz && n) CU(cudaMemcpy(col_logz, (const double*)ctx->d_out_logz.p + off, n * 8, cudaMemcpyDeviceToHost));
+    if (col_anc && n) CU(cudaMemcpy(col_anc, (const double*)ctx->d_out_anc.p + off, n * 8, cudaMemcpyDeviceToHost));
+    return PCSF_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Batched maximize_lpr. Every region runs the reference's find_init + GSL Brent state machine
+// (pcsf_brent.hpp); each round gathers one candidate rho per live region, builds their P tables and
+// scores them in one K1 + K2/K3 + K4 sequence. Candidates that are the same for every region
+// (lo, hi, init, Brent's first golden-section point, find_init's fixed random stream) share one
+// P set and run as a single span over the whole batch.
+// -------------------------------------------------------------------------------------------------
+int pcsf_maximize_lpr(pcsf_ctx* ctx, int model_id, double init, double lo, double hi, double accuracy,
+                      double* out_rho, double* out_lpr, double* out_elpr_anc, int32_t* out_status,
+                      int32_t* out_nevals) {
+    TRY(check_ready(ctx, true));
+    if (model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set)
+        return fail(ctx, PCSF_ERR_STATE, "pcsf_maximize_lpr: model not set");
+    if (!out_rho || !out_lpr) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_maximize_lpr: null output");
+    if (lo >= hi || lo <= 0.0) return fail(ctx, PCSF_ERR_INVALID_ARG, "CamlPaml.Fit.find_init");  // Fit.ml:28
+    CU(cudaSetDevice(ctx->device));
+    const int64_t R = ctx->nregions;
+    Model& m = ctx->models[model_id];
+    std::vector<MaximizeLpr> st((size_t)R, MaximizeLpr(init, lo, hi, accuracy));
+    std::vector<double> lpr(R), elpr(R);
+    std::vector<int32_t> status(R);
+    // candidates of a round
+    std::vector<int64_t> live;
+    std::vector<double> xs;
+    std::vector<double> uniq;
+    std::vector<int32_t> e_model, e_scale;
+    std::vector<int64_t> e_region;
+    std::vector<double> r_lpr, r_elpr;
+    std::vector<int32_t> r_status;
+    // bound the P tables of one launch to ~16 GiB
+    const size_t pset_bytes = (size_t)ctx->n_branches * PT_SLOT_BYTES;
+    const int64_t max_sets = std::max<int64_t>(1, (int64_t)((16ull << 30) / pset_bytes));
+    double ms_prune = 0, ms_reduce = 0, ms_pt = 0;
+    for (;;) {
+        live.clear();
+        xs.clear();
+        for (int64_t r = 0; r < R; r++)
+            if (!st[r].done()) {
+                live.push_back(r);
+                xs.push_back(st[r].candidate());
+            }
+        if (live.empty()) break;
+        for (size_t c0 = 0; c0 < live.size(); c0 += (size_t)max_sets) {
+            const size_t c1 = std::min(live.size(), c0 + (size_t)max_sets);
+            // unique scales of this chunk, in first-appearance order (keeps common candidates in one span)
+            uniq.clear();
+            e_model.clear();
+            e_scale.clear();
+            e_region.clear();
+            {
+                std::vector<std::pair<double, int>> seen;  // small when candidates are common
+                double last_x = std::nan("");
+                int last_i = -1;
+                for (size_t i = c0; i < c1; i++) {
+                    const double x = xs[i];
+                    int idx;
+                    if (x == last_x) idx = last_i;
+                    else {
+                        idx = (int)uniq.size();
+                        uniq.push_back(x);
+                    }
+                    last_x = x;
+                    last_i = idx;
+                    e_model.push_back(model_id);
+                    e_scale.push_back(idx);
+                    e_region.push_back(live[i]);
+                }
+            }
+            TRY(pt_build_device(ctx, m, (int)uniq.size(), uniq.data()));
+            ms_pt += ctx->ms[2];
+            const int64_t ne = (int64_t)e_region.size();
+            r_lpr.resize(ne);
+            r_elpr.resize(ne);
+            r_status.resize(ne);
+            TRY(pcsf_lpr(ctx, ne, e_model.data(), e_scale.data(), e_region.data(), r_lpr.data(), r_elpr.data(), r_status.data()));
+            ms_prune += ctx->ms[0];
+            ms_reduce += ctx->ms[1];
+            for (int64_t i = 0; i < ne; i++) st[live[c0 + i]].feed(r_lpr[i], r_elpr[i], r_status[i]);
+        }
+    }
+    bool bad = false;
+    for (int64_t r = 0; r < R; r++) {
+        out_rho[r] = st[r].result_x;
+        out_lpr[r] = st[r].result_f;
+        if (out_elpr_anc) out_elpr_anc[r] = st[r].result_elpr;
+        if (out_status) out_status[r] = st[r].status;
+        if (out_nevals) out_nevals[r] = st[r].nevals;
+        bad |= (st[r].status & ~PCSF_ST_RANDOM_INIT) != 0;
+    }
+    ctx->ms[0] = ms_prune;
+    ctx->ms[1] = ms_reduce;
+    ctx->ms[2] = ms_pt;
+    m.nscales = 0;  // the candidate tables are scratch
+    if (bad) return fail(ctx, PCSF_ERR_NUMERIC, "maximize_lpr failed for at least one region (see status)");
+    return PCSF_OK;
+}
+
+double pcsf_last_ms(const pcsf_ctx* ctx, int which) {
+    if (!ctx || which < 0 || which > 4) return -1.0;
+    return ctx->ms[which];
+}
+
+int64_t pcsf_launch_count(const pcsf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the CPU oracle on the same inputs. Bars: P(t) entries to 2e-13 absolute; region scores to
+|delta| <= 1e-6 decibans (BASELINE.json north_star), asserted at 1e-7 to leave margin."""
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+import pcsf_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_DB = 1e-7
+
+
+@pytest.fixture(scope="module")
+def flies(params_base):
+    return H.oracle_paramset(params_base, "12flies")
+
+
+@pytest.fixture(scope="module")
+def mammals58(params_base):
+    return H.oracle_paramset(params_base, "58mammals")
+
+
+@pytest.mark.parametrize("pset", ["12flies", "58mammals", "20flies"])
+def test_pt_build_matches_oracle(params_base, pset):
+    ps = H.oracle_paramset(params_base, pset)
+    ctx = H.make_context(ps)
+    scales = np.array([1.0, 0.01, 0.37, 10.0])
+    for mid, inst in enumerate((ps.model.coding_model, ps.model.noncoding_model)):
+        st = ctx.pt_build(mid, scales)
+        assert (st == 0).all()
+        for si, rho in enumerate(scales):
+            for br in range(ps.tree.root):
+                P = ctx.pt_get(mid, si, br)
+                Po = inst.q.to_Pt(rho * ps.tree.branches[br])
+                assert np.abs(P - Po).max() < 2e-13, (pset, mid, rho, br)
+                assert (P >= 0).all()
+    ctx.close()
+
+
+def test_pt_build_negative_scale_flags(flies):
+    ctx = H.make_context(flies)
+    st = ctx.pt_build(0, [1.0, -1.0], check=False)
+    assert st[0] == 0 and (st[1] & 1)
+    ctx.close()
+
+
+def test_fixed_tal_AA(flies):
+    regs, _ = H.example_codes(flies, "tal-AA.fa")
+    ctx = H.make_context(flies)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    lpr, elpr, st = ctx.lpr_all([0, 1])
+    lo, eo = H.oracle_fixed(flies, regs)
+    assert (st == 0).all()
+    score = H.DB * (lpr[0] - lpr[1])
+    assert abs(score[0] - 361.6876) < 1e-4  # BASELINE.json configs[0] (restatement-derived value)
+    assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB
+    assert np.abs(H.DB * (elpr - eo)).max() < TOL_DB
+    # per-column terms against the oracle's
+    clz, can = ctx.column_terms(0)
+    _, _, oz, oa = o.lpr_columns(flies.model.coding_model.model(1.0), regs[0])
+    np.testing.assert_allclose(clz, oz, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(can, oa, rtol=0, atol=1e-12)
+    ctx.close()
+
+
+def test_fixed_simulated_58mammals_ragged(mammals58):
+    ps = mammals58
+    rng = np.random.default_rng(42)
+    mc, mn = ps.model.coding_model.model(1.0), ps.model.noncoding_model.model(1.0)
+    regs = []
+    for i, n in enumerate([100, 99, 99, 1, 0, 7, 128, 129, 300, 16, 15, 17, 0, 64]):
+        c = o.simulate_columns(mc if i % 2 == 0 else mn, n, rng) if n else np.zeros((0, 58), dtype=np.uint8)
+        regs.append(c)
+    # gaps / missing species / whole-column marginalisation
+    regs[0][:, 5] = 64
+    regs[1][3, :] = 64
+    regs[2][10:20, 30:] = 64
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    lpr, elpr, st = ctx.lpr_all([0, 1])
+    lo, eo = H.oracle_fixed(ps, regs)
+    assert (st == 0).all()
+    assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB
+    assert np.abs(H.DB * (elpr - eo)).max() < TOL_DB
+    assert lpr[0, 4] == 0.0 and elpr[1, 12] == 0.0  # empty regions
+    # the explicit-evaluation entry point gives bit-identical numbers
+    em = np.repeat([0, 1], len(regs))
+    er = np.tile(np.arange(len(regs)), 2)
+    l2, e2, _ = ctx.lpr(em, np.zeros_like(em), er)
+    assert (l2.reshape(2, -1) == lpr).all() and (e2.reshape(2, -1) == elpr).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("pset", ["120mammals", "100vertebrates", "29mammals", "7yeast"])
+def test_fixed_other_trees(params_base, pset):
+    ps = H.oracle_paramset(params_base, pset)
+    rng = np.random.default_rng(7)
+    mc, mn = ps.model.coding_model.model(1.0), ps.model.noncoding_model.model(1.0)
+    regs = [o.simulate_columns(mc, 40, rng), o.simulate_columns(mn, 33, rng)]
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    lpr, elpr, st = ctx.lpr_all([0, 1])
+    lo, eo = H.oracle_fixed(ps, regs)
+    assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB
+    assert np.abs(H.DB * (elpr - eo)).max() < TOL_DB
+    ctx.close()
+
+
+def test_underflow_matches_reference_semantics(params_base):
+    """The reference does not rescale partials (PhyloLik.ml:87-92): uniform-random columns on the
+    120-leaf tree underflow to z = 0 => log z = -inf, posterior zeros (PhyloLik.ml:131-132)."""
+    ps = H.oracle_paramset(params_base, "120mammals")
+    rng = np.random.default_rng(3)
+    regs = [rng.integers(0, 64, size=(5, 120)).astype(np.uint8)]
+    lo, eo = H.oracle_fixed(ps, regs)
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    lpr, elpr, st = ctx.lpr_all([0, 1])
+    assert np.isneginf(lo).all() and np.isneginf(lpr).all()
+    assert (st & 16).all()
+    assert (elpr == eo).all()
+    ctx.close()
+
+
+def test_device_pleaves_frames(params_base):
+    """pcsf_batch_upload_alignments (on-device pleaves, 6 frames) against the oracle's pleaves."""
+    ps = H.oracle_paramset(params_base, "29mammals")
+    regs, (aln, leaf_ord) = H.example_codes(ps, "ALDH2.exon5.fa", frames=6)
+    n, L = ps.tree.n_leaves, len(aln[0])
+    nt = np.full((n, L), ord("-"), dtype=np.uint8)
+    for l, r in enumerate(leaf_ord):
+        if r is not None:
+            nt[l] = np.frombuffer(aln[r].encode(), dtype=np.uint8)
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    ctx.batch_upload_alignments([0], [L], nt, 6)
+    assert ctx.nregions == 6 and ctx.ncols == sum(r.shape[0] for r in regs)
+    lpr, elpr, st = ctx.lpr_all([0, 1])
+    lo, eo = H.oracle_fixed(ps, regs)
+    assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB
+    assert np.abs(H.DB * (elpr - eo)).max() < TOL_DB
+    score = H.DB * (lpr[0] - lpr[1])
+    assert int(np.argmax(score)) == 1  # frame +1 wins (src/test.ml:41-49 under mle; same frame under fixed)
+    ctx.close()
+
+
+def _oracle_mle(ps, regs):
+    out = []
+    for c in regs:
+        row = []
+        for inst in (ps.model.coding_model, ps.model.noncoding_model):
+            tr = {}
+            x, (lp, el) = o.maximize_lpr(lambda r: o.lpr_leaves(inst, c, r), lambda r: r[0], init=1.0, trace=tr)
+            row.append((x, lp, el, tr.get("iterations", 0), tr.get("random_tries", 0)))
+        out.append(row)
+    return out
+
+
+def test_mle_examples(params_base):
+    """maximize_lpr (find_init + GSL Brent) batched on the device vs the oracle: same iterate
+    count, rho to 1e-9, scores to 1e-6 dB; and the reference's golden windows (src/test.ml:27-39)."""
+    for pset, fn, window, anc_window in (("12flies", "tal-AA.fa", (297.62, 297.63), (48.25, 48.26)),
+                                         ("29mammals", "ALDH2.exon5.fa", (-178.93, -178.92), (-38.29, -38.28))):
+        ps = H.oracle_paramset(params_base, pset)
+        regs, _ = H.example_codes(ps, fn, frames=3)
+        ctx = H.make_context(ps)
+        off, codes = H.regions_to_batch(regs)
+        ctx.batch_upload(off, codes)
+        res = [ctx.maximize_lpr(m) for m in (0, 1)]
+        ora = _oracle_mle(ps, regs)
+        for r in range(len(regs)):
+            for m in (0, 1):
+                rho, lpr, elpr, st, ne = (a[r] for a in res[m])
+                ox, olp, oel, oit, otries = ora[r][m]
+                assert (st & ~64) == 0
+                assert abs(rho - ox) < 1e-9 * max(1.0, ox), (pset, r, m, rho, ox)
+                assert abs(H.DB * (lpr - olp)) < 1e-6 and abs(H.DB * (elpr - oel)) < 1e-6
+                assert ne == 3 + otries + 3 + 1 + oit + 1
+        score0 = H.DB * (res[0][1][0] - res[1][1][0])
+        anc0 = H.DB * (res[0][2][0] - res[1][2][0])
+        assert window[0] < score0 < window[1] and anc_window[0] < anc0 < anc_window[1]
+        ctx.close()
