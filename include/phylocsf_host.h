@@ -1,0 +1,52 @@
+/*
+ * phylocsf_host.h — C ABI of the host-side half of the drop-in (C++ in phylocsf_b200/csrc/host):
+ * parameter loading, tree numbering and rate-matrix diagonalisation, i.e. what the reference's OCaml
+ * host does in PhyloCSF.initialize_strategy (src/PhyloCSF.ml:406-467), PhyloCSFModel.make
+ * (src/PhyloCSFModel.ml:107-110) and Q.Diag.of_Q / equilibrium (lib/CamlPaml/Q.ml:124-177) before
+ * any likelihood is evaluated. The OCaml toolchain is absent from this image, so this layer is C++
+ * (DESIGN.md "Host language"); with OCaml present, the reference's own modules would call the
+ * compute ABI in phylocsf_b200.h directly.
+ */
+#ifndef PHYLOCSF_HOST_H
+#define PHYLOCSF_HOST_H
+
+#include <stdint.h>
+
+#include "phylocsf_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcsf_paramset pcsf_paramset;
+
+/*
+ * Load <prefix>.nh, <prefix>_coding.ECM, <prefix>_noncoding.ECM (src/PhyloCSF.ml:423-445).
+ * species_csv: optional "--species" list (comma separated) -> Newick.subtree pruning (:425-433).
+ * with_ecm = 0 loads only the tree (omega strategy). On failure returns a negative PCSF_ERR_* and
+ * writes the reference-style exception text into err (if errlen > 0).
+ */
+int pcsf_paramset_load(const char *prefix, const char *species_csv, int with_ecm, pcsf_paramset **out, char *err,
+                       int errlen);
+void pcsf_paramset_free(pcsf_paramset *ps);
+int pcsf_paramset_n_leaves(const pcsf_paramset *ps);
+const char *pcsf_paramset_leaf_label(const pcsf_paramset *ps, int leaf);
+/* children[2*(n_leaves-1)], branch_len[2*n_leaves-2] in the pcsf_tree_set layout */
+int pcsf_paramset_tree(const pcsf_paramset *ps, int32_t *children, double *branch_len);
+/* which: 0 = coding ECM, 1 = noncoding ECM. Any output may be NULL. Q is the scaled rate matrix. */
+int pcsf_paramset_qdiag(const pcsf_paramset *ps, int which, double *Q, double *S, double *Sinv, double *lambda,
+                        double *prior);
+/* sets the tree and both models (slot 0 = coding, slot 1 = noncoding) on a compute context */
+int pcsf_paramset_install(pcsf_ctx *ctx, const pcsf_paramset *ps);
+
+/* Diagonalise an arbitrary reversible 64x64 rate matrix with stationary weights w (Q.Diag.of_Q +
+ * equilibrium for callers that assemble their own Q, e.g. the omega model). */
+int pcsf_qdiag_reversible(const double *Q, const double *w, double *S, double *Sinv, double *lambda, double *prior,
+                          char *err, int errlen);
+/* OmegaModel rate matrix at settings v[12] = kappa, omega, sigma, 9 x F3x4 (src/OmegaModel.ml:21-80) */
+int pcsf_omega_q(const double *v, double *Q, double *pi, char *err, int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,146 @@
+// pcsf_host_api.cu — C ABI of include/phylocsf_host.h over the C++ host layer (csrc/host).
+#include "../../include/phylocsf_host.h"
+
+#include <cstring>
+#include <set>
+#include <sstream>
+
+#include "host/codon_model.hpp"
+#include "host/newick_tree.hpp"
+
+using namespace pcsf::host;
+
+struct pcsf_paramset {
+    NewickPtr nt;  // after --species pruning
+    Tree tree;
+    bool have_ecm = false;
+    ECM ecm[2];
+    QDiag qd[2];
+};
+
+namespace {
+void put_err(char* err, int errlen, const std::string& m) {
+    if (err && errlen > 0) {
+        std::strncpy(err, m.c_str(), (size_t)errlen - 1);
+        err[errlen - 1] = 0;
+    }
+}
+std::string slurp(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw failure("could not find required parameter file " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+}  // namespace
+
+extern "C" {
+
+int pcsf_paramset_load(const char* prefix, const char* species_csv, int with_ecm, pcsf_paramset** out, char* err,
+                       int errlen) {
+    if (!prefix || !out) return PCSF_ERR_INVALID_ARG;
+    *out = nullptr;
+    try {
+        auto ps = new pcsf_paramset();
+        std::unique_ptr<pcsf_paramset> guard(ps);
+        const std::string pre(prefix);
+        NewickPtr nt = newick_parse(slurp(pre + ".nh"));
+        if (species_csv && *species_csv) {
+            std::set<std::string> want;
+            std::stringstream ss(species_csv);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) want.insert(tok);
+            NewickPtr snt = newick_subtree([&](const std::string& s) { return want.count(s) > 0; }, nt);
+            if (!snt || newick_leaves(*snt) <= 1) throw failure("specify at least two available --species");
+            nt = snt;
+        }
+        ps->nt = nt;
+        ps->tree = Tree::of_newick(*nt);
+        if (with_ecm) {
+            ps->ecm[0] = read_ecm(pre + "_coding.ECM");
+            ps->ecm[1] = read_ecm(pre + "_noncoding.ECM");
+            for (int w = 0; w < 2; w++) ps->qd[w] = QDiag::of_reversible_Q(ecm_q(ps->ecm[w]), ps->ecm[w].pi);
+            ps->have_ecm = true;
+        }
+        *out = guard.release();
+        return PCSF_OK;
+    } catch (const std::exception& e) {
+        put_err(err, errlen, e.what());
+        return PCSF_ERR_INVALID_ARG;
+    }
+}
+
+void pcsf_paramset_free(pcsf_paramset* ps) { delete ps; }
+int pcsf_paramset_n_leaves(const pcsf_paramset* ps) { return ps ? ps->tree.n_leaves : 0; }
+const char* pcsf_paramset_leaf_label(const pcsf_paramset* ps, int leaf) {
+    if (!ps || leaf < 0 || leaf >= ps->tree.n_leaves) return "";
+    return ps->tree.labels[leaf].c_str();
+}
+
+int pcsf_paramset_tree(const pcsf_paramset* ps, int32_t* children, double* branch_len) {
+    if (!ps) return PCSF_ERR_INVALID_ARG;
+    const auto ch = ps->tree.children_array();
+    if (children) std::memcpy(children, ch.data(), ch.size() * sizeof(int32_t));
+    if (branch_len)
+        for (int i = 0; i < ps->tree.root(); i++) branch_len[i] = ps->tree.branches[i];
+    return PCSF_OK;
+}
+
+int pcsf_paramset_qdiag(const pcsf_paramset* ps, int which, double* Q, double* S, double* Sinv, double* lambda,
+                        double* prior) {
+    if (!ps || !ps->have_ecm || which < 0 || which > 1) return PCSF_ERR_INVALID_ARG;
+    const QDiag& d = ps->qd[which];
+    if (Q) std::memcpy(Q, d.q.data(), 4096 * 8);
+    if (S) std::memcpy(S, d.S.data(), 4096 * 8);
+    if (Sinv) std::memcpy(Sinv, d.Sinv.data(), 4096 * 8);
+    if (lambda) std::memcpy(lambda, d.lam.data(), 64 * 8);
+    if (prior) std::memcpy(prior, d.pi_eq.data(), 64 * 8);
+    return PCSF_OK;
+}
+
+int pcsf_paramset_install(pcsf_ctx* ctx, const pcsf_paramset* ps) {
+    if (!ctx || !ps) return PCSF_ERR_INVALID_ARG;
+    const auto ch = ps->tree.children_array();
+    std::vector<double> bl(ps->tree.branches.begin(), ps->tree.branches.begin() + ps->tree.root());
+    int rc = pcsf_tree_set(ctx, ps->tree.n_leaves, ch.data(), bl.data());
+    if (rc != PCSF_OK) return rc;
+    if (ps->have_ecm)
+        for (int w = 0; w < 2; w++) {
+            const QDiag& d = ps->qd[w];
+            rc = pcsf_model_set(ctx, w, d.S.data(), d.Sinv.data(), d.lam.data(), d.pi_eq.data());
+            if (rc != PCSF_OK) return rc;
+        }
+    return PCSF_OK;
+}
+
+int pcsf_qdiag_reversible(const double* Q, const double* w, double* S, double* Sinv, double* lambda, double* prior,
+                          char* err, int errlen) {
+    if (!Q || !w) return PCSF_ERR_INVALID_ARG;
+    try {
+        QDiag d = QDiag::of_reversible_Q(std::vector<double>(Q, Q + 4096), std::vector<double>(w, w + 64));
+        if (S) std::memcpy(S, d.S.data(), 4096 * 8);
+        if (Sinv) std::memcpy(Sinv, d.Sinv.data(), 4096 * 8);
+        if (lambda) std::memcpy(lambda, d.lam.data(), 64 * 8);
+        if (prior) std::memcpy(prior, d.pi_eq.data(), 64 * 8);
+        return PCSF_OK;
+    } catch (const std::exception& e) {
+        put_err(err, errlen, e.what());
+        return PCSF_ERR_NUMERIC;
+    }
+}
+
+int pcsf_omega_q(const double* v, double* Q, double* pi, char* err, int errlen) {
+    if (!v || !Q) return PCSF_ERR_INVALID_ARG;
+    try {
+        std::vector<double> p;
+        std::vector<double> q = omega_q(v, &p);
+        std::memcpy(Q, q.data(), 4096 * 8);
+        if (pi) std::memcpy(pi, p.data(), 64 * 8);
+        return PCSF_OK;
+    } catch (const std::exception& e) {
+        put_err(err, errlen, e.what());
+        return PCSF_ERR_NUMERIC;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+"""ctypes face of the C++ host layer (include/phylocsf_host.h): parameter sets, tree numbering and
+rate-matrix diagonalisation — the product's own restatement of the reference's host setup
+(src/PhyloCSF.ml:406-467, src/PhyloCSFModel.ml:107-110, lib/CamlPaml/Q.ml:124-177)."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native as N
+
+HOST_SYMBOLS = [
+    "pcsf_paramset_load", "pcsf_paramset_free", "pcsf_paramset_n_leaves", "pcsf_paramset_leaf_label",
+    "pcsf_paramset_tree", "pcsf_paramset_qdiag", "pcsf_paramset_install", "pcsf_qdiag_reversible", "pcsf_omega_q",
+]
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _lib():
+    L = N.load()
+    if not getattr(L, "_host_ready", False):
+        vp = ctypes.c_void_p
+        L.pcsf_paramset_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int]
+        L.pcsf_paramset_free.argtypes = [vp]
+        L.pcsf_paramset_free.restype = None
+        L.pcsf_paramset_n_leaves.argtypes = [vp]
+        L.pcsf_paramset_leaf_label.argtypes = [vp, ctypes.c_int]
+        L.pcsf_paramset_leaf_label.restype = ctypes.c_char_p
+        L.pcsf_paramset_tree.argtypes = [vp, vp, vp]
+        L.pcsf_paramset_qdiag.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
+        L.pcsf_paramset_install.argtypes = [vp, vp]
+        L.pcsf_qdiag_reversible.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_char_p, ctypes.c_int]
+        L.pcsf_omega_q.argtypes = [vp, vp, vp, ctypes.c_char_p, ctypes.c_int]
+        L._host_ready = True
+    return L
+
+
+class ParamSet:
+    """<base>/PhyloCSF_Parameters/<name>.nh + ECMs, optionally pruned to `species`."""
+
+    def __init__(self, prefix, species=None, with_ecm=True):
+        L = _lib()
+        h = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(512)
+        sp = ",".join(species).encode() if species else None
+        rc = L.pcsf_paramset_load(os.fspath(prefix).encode(), sp, 1 if with_ecm else 0, ctypes.byref(h), err, 512)
+        if rc != 0:
+            raise HostError(err.value.decode())
+        self._L, self._h = L, h
+        self.n_leaves = L.pcsf_paramset_n_leaves(h)
+        self.leaf_labels = [L.pcsf_paramset_leaf_label(h, i).decode() for i in range(self.n_leaves)]
+        self.children = np.zeros(2 * (self.n_leaves - 1), dtype=np.int32)
+        self.branch_len = np.zeros(2 * self.n_leaves - 2)
+        L.pcsf_paramset_tree(h, N.ptr(self.children), N.ptr(self.branch_len))
+        self.with_ecm = with_ecm
+
+    def qdiag(self, which):
+        Q, S, Sinv = np.empty((64, 64)), np.empty((64, 64)), np.empty((64, 64))
+        lam, prior = np.empty(64), np.empty(64)
+        rc = self._L.pcsf_paramset_qdiag(self._h, which, N.ptr(Q), N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior))
+        if rc != 0:
+            raise HostError("pcsf_paramset_qdiag failed (%d)" % rc)
+        return {"Q": Q, "S": S, "Sinv": Sinv, "lam": lam, "prior": prior}
+
+    def install(self, ctx):
+        rc = self._L.pcsf_paramset_install(ctx._h, self._h)
+        ctx._check(rc)
+        ctx.n_leaves = self.n_leaves
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pcsf_paramset_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def qdiag_reversible(Q, w):
+    L = _lib()
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    S, Sinv, lam, prior = np.empty((64, 64)), np.empty((64, 64)), np.empty(64), np.empty(64)
+    err = ctypes.create_string_buffer(512)
+    rc = L.pcsf_qdiag_reversible(N.ptr(Q), N.ptr(w), N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior), err, 512)
+    if rc != 0:
+        raise HostError(err.value.decode())
+    return {"Q": Q, "S": S, "Sinv": Sinv, "lam": lam, "prior": prior}
+
+
+def omega_q(v):
+    L = _lib()
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    assert v.size == 12
+    Q, pi = np.empty((64, 64)), np.empty(64)
+    err = ctypes.create_string_buffer(512)
+    rc = L.pcsf_omega_q(N.ptr(v), N.ptr(Q), N.ptr(pi), err, 512)
+    if rc != 0:
+        raise HostError(err.value.decode())
+    return Q, pi
