@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libphylocsf_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "-shared",
-]
+] + os.environ.get("PCSF_NVCC_EXTRA", "").split()
 
 
 def sources():

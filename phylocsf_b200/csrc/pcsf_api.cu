@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -50,7 +51,9 @@ struct pcsf_ctx {
     std::vector<double> branch_len;
     double* d_branch_len = nullptr;
     Op* d_ops = nullptr;
+    Item* d_items = nullptr;
     std::vector<Op> ops;
+    std::vector<Item> items;          // what the producer warpgroup stages per tile, in program order
     int n_gemm = 0, max_levels = 0;
     // models
     std::vector<Model> models;
@@ -66,6 +69,9 @@ struct pcsf_ctx {
     double ms[5] = {-1, -1, -1, -1, -1};
     int64_t launches = 0;
     int prune_smem_optin = 0;
+    int skew_ns = 1500;
+    void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
+    int timeline_cap = 0;
 };
 
 namespace {
@@ -152,10 +158,10 @@ struct ProgramBuilder {
     }
 };
 
-int prune_fixed_smem(const pcsf_ctx* c) {
-    const int ops_bytes = ((int)(c->ops.size() * sizeof(Op)) + 15) & ~15;
-    const int codes_bytes = (TILE_COLS * c->n_leaves + 15) & ~15;
-    return 2 * FRAG_BYTES + 64 + ops_bytes + codes_bytes;
+int r16(int x) { return (x + 15) & ~15; }
+int prune_smem_for(int n_ops, int n_items, int n_leaves) {
+    return P_STAGES * FRAG_BYTES + M_STAGES * STACK_LEVEL_BYTES + PRUNE_BAR_BYTES + r16(n_ops * (int)sizeof(Op)) +
+           r16(n_items * (int)sizeof(Item)) + r16(TILE_COLS * n_leaves);
 }
 
 // Launch K2+K3 over `spans`, then K4 over the given segments. Outputs land in ctx->d_lpr/d_elpr.
@@ -176,16 +182,15 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         TRY(reserve(ctx, ctx->d_psets, sizeof(PSet) * psets.size()));
         CU(cudaMemcpyAsync(ctx->d_spans.p, spans.data(), sizeof(Span) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_psets.p, psets.data(), sizeof(PSet) * psets.size(), cudaMemcpyHostToDevice, ctx->stream));
-        const int fixed = prune_fixed_smem(ctx);
-        int smem_levels = std::max(0, std::min(ctx->max_levels, (ctx->prune_smem_optin - fixed) / STACK_LEVEL_BYTES));
-        const int global_levels = ctx->max_levels - smem_levels;
         const int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
-        if (global_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * global_levels * STACK_LEVEL_BYTES));
+        if (ctx->max_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * ctx->max_levels * STACK_LEVEL_BYTES));
         PruneParams p;
+        memset(&p, 0, sizeof(p));
         p.ops = ctx->d_ops;
         p.n_ops = (int)ctx->ops.size();
+        p.items = ctx->d_items;
+        p.n_items = (int)ctx->items.size();
         p.n_leaves = ctx->n_leaves;
-        p.n_gemm = ctx->n_gemm;
         p.spans = (const Span*)ctx->d_spans.p;
         p.n_spans = (int)spans.size();
         p.n_tiles = tiles;
@@ -193,11 +198,14 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         p.codes = (const uint8_t*)ctx->d_codes.p;
         p.out_logz = (double*)ctx->d_out_logz.p;
         p.out_anc = (double*)ctx->d_out_anc.p;
-        p.smem_levels = smem_levels;
         p.global_stack = (uint8_t*)ctx->d_gstack.p;
-        p.global_levels = global_levels;
-        p.codes_smem_bytes = (TILE_COLS * ctx->n_leaves + 15) & ~15;
-        const int smem = fixed + smem_levels * STACK_LEVEL_BYTES;
+        p.n_levels = ctx->max_levels;
+        p.ops_bytes = r16((int)(ctx->ops.size() * sizeof(Op)));
+        p.items_bytes = r16((int)(ctx->items.size() * sizeof(Item)));
+        p.timeline = (long long*)ctx->timeline;
+        p.timeline_cap = ctx->timeline_cap;
+        p.skew_ns = ctx->skew_ns;
+        const int smem = prune_smem_for(p.n_ops, p.n_items, ctx->n_leaves);
         if (smem > ctx->prune_smem_optin)
             return fail(ctx, PCSF_ERR_INVALID_ARG, "tree too large for the pruning kernel's shared memory (" + std::to_string(smem) + " bytes)");
         CU(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -326,6 +334,7 @@ int pcsf_create(int device_id, pcsf_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return bail(e);
     ctx->num_sms = prop.multiProcessorCount;
     ctx->prune_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* e = getenv("PCSF_SKEW_NS")) ctx->skew_ns = atoi(e);  // tuning knob, see prune_kernel
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->stream = ctx->own_stream;
     for (auto& ev : ctx->ev)
@@ -354,6 +363,7 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     for (auto* b : bufs) fr(*b);
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
+    if (ctx->d_items) cudaFree(ctx->d_items);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -384,8 +394,8 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         if (!seen[i]) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: node without a parent");
         if (!(branch_len[i] >= 0.0)) return fail(ctx, PCSF_ERR_INVALID_ARG, "CamlPaml.PhyloModel.make: negative or NaN branch length");  // PhyloModel.ml:16
     }
-    if ((TILE_COLS * n_leaves + 15) / 16 * 16 + 2 * FRAG_BYTES + 4096 > ctx->prune_smem_optin)
-        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: too many leaves for the shared-memory code tile");
+    if (prune_smem_for(n_leaves + 1, 3 * n_leaves, n_leaves) > ctx->prune_smem_optin)
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: too many leaves for the pruning kernel's shared memory");
     ctx->n_leaves = n_leaves;
     ctx->n_branches = n - 1;
     ctx->children.assign(children, children + 2 * (n_leaves - 1));
@@ -397,11 +407,22 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
     ctx->ops = pb.ops;
     ctx->n_gemm = pb.n_gemm;
     ctx->max_levels = pb.max_height;
+    if (ctx->max_levels > MAX_STACK_LEVELS) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: tree needs more than 16 parked partials");
+    ctx->items.clear();
+    for (const Op& op : ctx->ops) {
+        if (op.kind == OP_CHERRY) { ctx->items.push_back({ITEM_LEAF, op.a}); ctx->items.push_back({ITEM_LEAF, op.b}); }
+        else if (op.kind == OP_GEMM_LEAF) { ctx->items.push_back({ITEM_P, op.a}); ctx->items.push_back({ITEM_LEAF, op.b}); }
+        else if (op.kind == OP_GEMM_PUSH) ctx->items.push_back({ITEM_P, op.a});
+        else if (op.kind == OP_GEMM_POP) { ctx->items.push_back({ITEM_P, op.a}); ctx->items.push_back({ITEM_POP, op.c}); }
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_branch_len) CU(cudaFree(ctx->d_branch_len));
     if (ctx->d_ops) CU(cudaFree(ctx->d_ops));
+    if (ctx->d_items) CU(cudaFree(ctx->d_items));
     CU(cudaMalloc(&ctx->d_branch_len, sizeof(double) * (n - 1)));
     CU(cudaMalloc(&ctx->d_ops, sizeof(Op) * ctx->ops.size()));
+    CU(cudaMalloc(&ctx->d_items, sizeof(Item) * std::max<size_t>(1, ctx->items.size())));
+    CU(cudaMemcpy(ctx->d_items, ctx->items.data(), sizeof(Item) * ctx->items.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_branch_len, branch_len, sizeof(double) * (n - 1), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_ops, ctx->ops.data(), sizeof(Op) * ctx->ops.size(), cudaMemcpyHostToDevice));
     for (auto& m : ctx->models) m.nscales = 0;  // tables belong to the previous tree
@@ -751,6 +772,23 @@ int pcsf_maximize_lpr(pcsf_ctx* ctx, int model_id, double init, double lo, doubl
     if (bad) return fail(ctx, PCSF_ERR_NUMERIC, "maximize_lpr failed for at least one region (see status)");
     return PCSF_OK;
 }
+
+#ifdef PCSF_TIMELINE
+// debug builds only (tools/timeline.py): per-warp (op, clock64) marks of CTA 0
+int pcsf_debug_timeline(pcsf_ctx* ctx, int cap, long long* out) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (!out) {
+        if (ctx->timeline) cudaFree(ctx->timeline);
+        ctx->timeline = nullptr;
+        ctx->timeline_cap = cap;
+        CU(cudaMalloc(&ctx->timeline, (size_t)cap * PRUNE_WARPS * 16));
+        CU(cudaMemset(ctx->timeline, 0xff, (size_t)cap * PRUNE_WARPS * 16));
+        return PCSF_OK;
+    }
+    CU(cudaMemcpy(out, ctx->timeline, (size_t)ctx->timeline_cap * PRUNE_WARPS * 16, cudaMemcpyDeviceToHost));
+    return PCSF_OK;
+}
+#endif
 
 double pcsf_last_ms(const pcsf_ctx* ctx, int which) {
     if (!ctx || which < 0 || which > 4) return -1.0;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 // D(8x8) += A(8x4) * B(4x8), FP64. lane = 4g+t: a = A[g][t], b = B[t][g], c = D[g][2t..2t+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
 }
@@ -190,19 +190,41 @@ __global__ void __launch_bounds__(256) pt_build_kernel(const double* __restrict_
 // =================================================================================================
 // K2+K3: pruning
 // =================================================================================================
-constexpr int PRUNE_WARPS = 8;
-constexpr int PRUNE_T = 2;                                   // 8-column tiles per warp
-constexpr int PRUNE_THREADS = PRUNE_WARPS * 32;
-constexpr int WARP_COLS = 8 * PRUNE_T;                       // 16
+#ifndef PCSF_PRUNE_T
+#define PCSF_PRUNE_T 2
+#endif
+constexpr int PRUNE_T = PCSF_PRUNE_T;                        // 8-column tiles per compute warp
+constexpr int PRUNE_WARPS = 16 / PRUNE_T;                    // compute warps (warpgroups 1..): 16 (T=1) or 8 (T=2)
+constexpr int PROD_THREADS = 128;                            // warpgroup 0: data movement only
+constexpr int PRUNE_THREADS = PROD_THREADS + PRUNE_WARPS * 32;  // 640 / 384
+constexpr int WARP_COLS = 8 * PRUNE_T;                       // 8 / 16
 constexpr int TILE_COLS = PRUNE_WARPS * WARP_COLS;           // 128
-constexpr int STACK_ENTRY_BYTES = PRUNE_T * 8 * 32 * 16;     // per warp per level: 8 KB
-constexpr int STACK_LEVEL_BYTES = PRUNE_WARPS * STACK_ENTRY_BYTES;  // 64 KB per level per CTA
+constexpr int STACK_ENTRY_BYTES = PRUNE_T * 8 * 32 * 16;     // one warp's partial: 8 KB
+constexpr int STACK_LEVEL_BYTES = PRUNE_WARPS * STACK_ENTRY_BYTES;  // one CTA's partial: 64 KB
+constexpr int P_STAGES = 2;                                  // ring of P images, 32 KB each
+constexpr int M_STAGES = 2;                                  // ring of multiplicand buffers, 64 KB each
+constexpr int MAX_STACK_LEVELS = 16;
+constexpr int PRUNE_BAR_BYTES = 256;                         // pfull[2] pempty[2] mfull[2] mempty[2] pushed[16]
+// setmaxnreg targets. Launch allocation is 65536 / threads (96 for 640 threads, 168 for 384).
+constexpr int PROD_REGS = PRUNE_T == 1 ? 32 : 56;  // inc can only take what dec released (CTA pool): (launch-PROD)*128 >= (COMPUTE-launch)*32*PRUNE_WARPS
+constexpr int COMPUTE_REGS = PRUNE_T == 1 ? 112 : 224;
+
+// What the producer warpgroup stages for the compute warps, in program order (built on the host).
+enum ItemKind : int32_t {
+    ITEM_P = 0,     // fragment-ordered P image of internal edge `a`            -> P ring (TMA bulk copy)
+    ITEM_LEAF = 1,  // leaf message of leaf `a`: gathered rows of its P^T table  -> M ring (cp.async gather)
+    ITEM_POP = 2    // parked partial of stack level `a`                         -> M ring (TMA bulk copy)
+};
+struct Item {
+    int32_t kind, a;
+};
 
 struct PruneParams {
     const Op* ops;
     int n_ops;
+    const Item* items;
+    int n_items;
     int n_leaves;
-    int n_gemm;  // GEMM ops per tile
     const Span* spans;
     int n_spans;
     int64_t n_tiles;
@@ -210,99 +232,181 @@ struct PruneParams {
     const uint8_t* codes;  // [total_cols][n_leaves]
     double* out_logz;
     double* out_anc;
-    int smem_levels;         // stack levels kept in shared memory
-    uint8_t* global_stack;   // [gridDim.x][max_levels - smem_levels][STACK_LEVEL_BYTES]
-    int global_levels;
-    int codes_smem_bytes;    // TILE_COLS * n_leaves rounded up to 16
+    uint8_t* global_stack;   // [gridDim.x][n_levels][STACK_LEVEL_BYTES]
+    int n_levels;
+    int ops_bytes;           // n_ops * sizeof(Op) rounded up to 16
+    int items_bytes;         // n_items * sizeof(Item) rounded up to 16
+    int skew_ns;             // start-up offset of the second compute warp of every SM sub-partition
+    long long* timeline;     // PCSF_TIMELINE builds only: [warp][event][2] = (code, clock64) of CTA 0
+    int timeline_cap;
 };
 
-// shared memory map: [P buf 0 | P buf 1 | barriers(64 B) | ops | codes | stack levels]
-__device__ __forceinline__ void load_leaf_mul(double (&cur)[PRUNE_T][8][2], const double* __restrict__ tab,
-                                              const uint8_t* codes_s, int n_leaves, int leaf, int wcol, int g, int t,
-                                              bool init) {
-#pragma unroll
-    for (int T = 0; T < PRUNE_T; T++) {
-        int code = codes_s[(wcol + 8 * T + g) * n_leaves + leaf];
-        code = code > 64 ? 64 : code;
-        const double2* src = reinterpret_cast<const double2*>(tab + code * 64 + 2 * t);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double2 v = __ldg(src + 4 * j);
-            if (init) {
-                cur[T][j][0] = v.x;
-                cur[T][j][1] = v.y;
-            } else {
-                cur[T][j][0] *= v.x;
-                cur[T][j][1] *= v.y;
-            }
-        }
+#ifdef PCSF_TIMELINE
+#define TL_MARK(code)                                                                        \
+    do {                                                                                     \
+        if (p.timeline && blockIdx.x == 0 && lane == 0 && tl_n < p.timeline_cap) {            \
+            p.timeline[((size_t)cw * p.timeline_cap + tl_n) * 2] = (long long)(code);         \
+            p.timeline[((size_t)cw * p.timeline_cap + tl_n) * 2 + 1] = clock64();             \
+            tl_n++;                                                                          \
+        }                                                                                    \
+    } while (0)
+#else
+#define TL_MARK(code) do { } while (0)
+#endif
+
+__device__ __forceinline__ int find_span(const Span* __restrict__ spans, int n_spans, int64_t tile) {
+    int lo = 0, hi = n_spans - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (spans[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
     }
+    return lo;
 }
 
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+// arrive on `bar` once all cp.async of this thread issued so far have landed (counts as a normal arrival)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// One CTA per SM, warp-specialised:
+//   warpgroup 0 (128 threads, registers trimmed to 56) moves data only. In program order it stages
+//     - the P image of every internal edge into a 2 x 32 KB ring (TMA bulk copy, one thread),
+//     - every multiplicand an epilogue needs into a 2 x 64 KB ring, already in the register layout
+//       of the compute warps: leaf messages as a cp.async gather of P^T rows selected by the leaf
+//       codes (K2), parked partials as a TMA bulk copy back from the L2-resident stack,
+//     running up to one tree edge ahead of the compute warps, across tile boundaries.
+//   warpgroups 1-2 (8 warps, registers raised to 224) each own 16 codon columns of the 128-column
+//     tile and walk the tree with the partials in registers: DMMA contraction against the staged P
+//     image (K3), then one pass of LDS.128 + DMUL over the staged multiplicand.
+// All hand-offs are mbarriers; there is no CTA-wide barrier after start-up.
+// shared memory map: [P ring | M ring | barriers | ops | items | tile codes]
 __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PruneParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    double* Pbuf0 = reinterpret_cast<double*>(smem);
-    double* Pbuf1 = reinterpret_cast<double*>(smem + FRAG_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * FRAG_BYTES);  // [2]
-    uint64_t* empty = full + 2;                                           // [2]
-    Op* ops_s = reinterpret_cast<Op*>(smem + 2 * FRAG_BYTES + 64);
-    const int ops_bytes = ((p.n_ops * (int)sizeof(Op)) + 15) & ~15;
-    uint8_t* codes_s = smem + 2 * FRAG_BYTES + 64 + ops_bytes;
-    uint8_t* stack_s = codes_s + p.codes_smem_bytes;
+    uint8_t* Pring = smem;
+    uint8_t* Mring = smem + P_STAGES * FRAG_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Mring + M_STAGES * STACK_LEVEL_BYTES);
+    uint64_t* pfull = bars;
+    uint64_t* pempty = bars + 2;
+    uint64_t* mfull = bars + 4;
+    uint64_t* mempty = bars + 6;
+    uint64_t* pushed = bars + 8;  // [MAX_STACK_LEVELS]
+    Op* ops_s = reinterpret_cast<Op*>(reinterpret_cast<uint8_t*>(bars) + PRUNE_BAR_BYTES);
+    Item* items_s = reinterpret_cast<Item*>(reinterpret_cast<uint8_t*>(ops_s) + p.ops_bytes);
+    uint8_t* codes_s = reinterpret_cast<uint8_t*>(items_s) + p.items_bytes;
 
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int wcol = w * WARP_COLS;
-
+    const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], PRUNE_WARPS);
-        mbar_init(&empty[1], PRUNE_WARPS);
+        for (int i = 0; i < P_STAGES; i++) {
+            mbar_init(&pfull[i], 1);
+            mbar_init(&pempty[i], PRUNE_WARPS);
+        }
+        for (int i = 0; i < M_STAGES; i++) {
+            mbar_init(&mfull[i], PROD_THREADS);
+            mbar_init(&mempty[i], PRUNE_WARPS);
+        }
+        for (int i = 0; i < MAX_STACK_LEVELS; i++) mbar_init(&pushed[i], PRUNE_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     for (int i = tid; i < p.n_ops; i += PRUNE_THREADS) ops_s[i] = p.ops[i];
+    for (int i = tid; i < p.n_items; i += PRUNE_THREADS) items_s[i] = p.items[i];
     __syncthreads();
 
-    uint32_t gq = 0;  // running count of GEMMs this CTA has gone through (selects buffer and parity)
-    uint8_t* gstack = p.global_stack + (size_t)blockIdx.x * p.global_levels * STACK_LEVEL_BYTES;
+    uint8_t* gstack = p.global_stack + (size_t)blockIdx.x * p.n_levels * STACK_LEVEL_BYTES;
+
+    if (tid < PROD_THREADS) {
+        // ====================================== producer warpgroup ======================================
+        reg_dealloc<PROD_REGS>();
+        uint32_t pq = 0, mq = 0;  // P images / multiplicands staged so far
+        uint32_t pops = 0;        // bit l = parity of the next pop of stack level l
+        // element e = tid + 128 i of a multiplicand: compute warp e/512, column tile (e/256)%2, state
+        // block (e/32)%8, lane e%32 -> 16 bytes at offset 16 e of the stage
+        for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const Span sp = p.spans[find_span(p.spans, p.n_spans, tile)];
+            const double* tables = p.psets[sp.pset].tables;
+            const int64_t tcol0 = (tile - sp.tile0) * TILE_COLS;
+            const int ncols = (int)min((int64_t)TILE_COLS, (int64_t)sp.ncols - tcol0);
+            {   // leaf codes of the tile (columns past the end of the span marginalise)
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // every gather of the previous tile has been issued
+                const uint8_t* src = p.codes + (size_t)(sp.col0 + tcol0) * p.n_leaves;
+                const int nbytes = ncols * p.n_leaves, total = TILE_COLS * p.n_leaves;
+                for (int i = tid; i < total; i += PROD_THREADS) codes_s[i] = (i < nbytes) ? src[i] : (uint8_t)64;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            for (int ii = 0; ii < p.n_items; ii++) {
+                const Item it = items_s[ii];
+                if (it.kind == ITEM_P) {
+                    if (tid == 0) {
+                        const uint32_t st = pq % P_STAGES, u = pq / P_STAGES;
+                        if (u >= 1) mbar_wait(&pempty[st], (u - 1) & 1);
+                        mbar_expect_tx(&pfull[st], FRAG_BYTES);
+                        tma_bulk_g2s(Pring + st * FRAG_BYTES, tables + (size_t)it.a * PT_SLOT, FRAG_BYTES, &pfull[st]);
+                    }
+                    pq++;
+                    continue;
+                }
+                const uint32_t st = mq % M_STAGES, u = mq / M_STAGES;
+                if (u >= 1) mbar_wait(&mempty[st], (u - 1) & 1);
+                uint8_t* dst = Mring + st * STACK_LEVEL_BYTES;
+                if (it.kind == ITEM_LEAF) {
+                    const double* tab = tables + (size_t)it.a * PT_SLOT;
+                    const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll 4
+                    for (int i = 0; i < 32; i++) {
+                        const int e = tid + PROD_THREADS * i;  // 16-byte element of the stage
+                        // e = ((warp * T + tile) * 8 + j) * 32 + lane, so (e >> 8) = warp * T + tile = column / 8
+                        const int j = (e >> 5) & 7, col = ((e >> 8) << 3) + g;
+                        int code = codes_s[col * p.n_leaves + it.a];
+                        code = code > 64 ? 64 : code;
+                        cp_async_16(dst + 16 * e, tab + code * 64 + 8 * j + 2 * t);
+                    }
+                    cp_async_arrive(&mfull[st]);
+                } else {  // ITEM_POP: the compute warps' stores to this level must be visible first
+                    mbar_wait(&pushed[it.a], (pops >> it.a) & 1);
+                    pops ^= 1u << it.a;
+                    if (tid == 0) {
+                        mbar_expect_tx(&mfull[st], STACK_LEVEL_BYTES);
+                        tma_bulk_g2s(dst, gstack + (size_t)it.a * STACK_LEVEL_BYTES, STACK_LEVEL_BYTES, &mfull[st]);
+                    } else {
+                        mbar_arrive(&mfull[st]);
+                    }
+                }
+                mq++;
+            }
+        }
+        return;
+    }
+
+    // ========================================= compute warps =========================================
+    reg_alloc<COMPUTE_REGS>();
+    const int ctid = tid - PROD_THREADS, lane = ctid & 31, cw = ctid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wcol = cw * WARP_COLS;
+    uint32_t pq = 0, mq = 0;
+    // The two compute warps of an SM sub-partition start half an edge apart so that one is in its
+    // epilogue while the other keeps the DMMA pipe busy; nothing re-synchronises them afterwards.
+    bool skew_pending = cw >= PRUNE_WARPS / 2 && p.skew_ns > 0;  // applied once the first data has arrived
+#ifdef PCSF_TIMELINE
+    int tl_n = 0;
+#endif
 
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        // ---- locate the span of this tile (binary search over tile0) ----
-        int lo = 0, hi = p.n_spans - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (p.spans[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
-        }
-        const Span sp = p.spans[lo];
+        const Span sp = p.spans[find_span(p.spans, p.n_spans, tile)];
         const PSet ps = p.psets[sp.pset];
         const int64_t tcol0 = (tile - sp.tile0) * TILE_COLS;  // first column of the tile within the span
         const int ncols = (int)min((int64_t)TILE_COLS, (int64_t)sp.ncols - tcol0);
         const bool warp_active = wcol < ncols;
-
-        __syncthreads();  // previous tile fully retired: codes_s and both P buffers are free
-
-        // ---- producer: first P image of the tile ----
-        int gemm_seen = 0;  // GEMM ops met so far in this tile (uniform across the CTA)
-        // branch ids of GEMM ops are found by scanning ops_s; next_gemm_op = index of the next GEMM op to prefetch
-        int next_gemm_op = 0;
-        while (next_gemm_op < p.n_ops && (ops_s[next_gemm_op].kind == OP_CHERRY || ops_s[next_gemm_op].kind == OP_ROOT))
-            next_gemm_op++;
-        if (tid == 0 && next_gemm_op < p.n_ops) {
-            const uint32_t q = gq, b = q & 1, u = q >> 1;
-            if (u >= 1) mbar_wait(&empty[b], (u - 1) & 1);
-            mbar_expect_tx(&full[b], FRAG_BYTES);
-            tma_bulk_g2s(b ? Pbuf1 : Pbuf0, ps.tables + (size_t)ops_s[next_gemm_op].a * PT_SLOT, FRAG_BYTES, &full[b]);
-        }
-        // ---- codes of the tile -> shared ----
-        {
-            const uint8_t* src = p.codes + (size_t)(sp.col0 + tcol0) * p.n_leaves;
-            const int nbytes = ncols * p.n_leaves;
-            const int total = TILE_COLS * p.n_leaves;
-            for (int i = tid; i < total; i += PRUNE_THREADS) codes_s[i] = (i < nbytes) ? src[i] : (uint8_t)64;
-        }
-        __syncthreads();
 
         double cur[PRUNE_T][8][2];
 #pragma unroll
@@ -313,9 +417,24 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
         for (int oi = 0; oi < p.n_ops; oi++) {
             const Op op = ops_s[oi];
             if (op.kind == OP_CHERRY) {
-                if (warp_active) {
-                    load_leaf_mul(cur, ps.tables + (size_t)op.a * PT_SLOT, codes_s, p.n_leaves, op.a, wcol, g, t, true);
-                    load_leaf_mul(cur, ps.tables + (size_t)op.b * PT_SLOT, codes_s, p.n_leaves, op.b, wcol, g, t, false);
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const uint32_t st = mq % M_STAGES;
+                    mbar_wait(&mfull[st], (mq / M_STAGES) & 1);
+                    if (warp_active) {
+                        const double2* m = reinterpret_cast<const double2*>(Mring + st * STACK_LEVEL_BYTES + cw * STACK_ENTRY_BYTES) + lane;
+#pragma unroll
+                        for (int T = 0; T < PRUNE_T; T++)
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const double2 v = m[(T * 8 + j) * 32];
+                                cur[T][j][0] = k ? cur[T][j][0] * v.x : v.x;
+                                cur[T][j][1] = k ? cur[T][j][1] * v.y : v.y;
+                            }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&mempty[st]);
+                    mq++;
                 }
                 continue;
             }
@@ -356,24 +475,18 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 }
                 continue;
             }
-            // ------------------------------ GEMM ops ------------------------------
-            const uint32_t q = gq + gemm_seen, b = q & 1, u = q >> 1;
-            // producer: prefetch the P image of the next GEMM op of this tile into the other buffer
-            {
-                int nxt = oi + 1;
-                while (nxt < p.n_ops && (ops_s[nxt].kind == OP_CHERRY || ops_s[nxt].kind == OP_ROOT)) nxt++;
-                if (tid == 0 && nxt < p.n_ops) {
-                    const uint32_t q1 = q + 1, b1 = q1 & 1, u1 = q1 >> 1;
-                    if (u1 >= 1) mbar_wait(&empty[b1], (u1 - 1) & 1);
-                    mbar_expect_tx(&full[b1], FRAG_BYTES);
-                    tma_bulk_g2s(b1 ? Pbuf1 : Pbuf0, ps.tables + (size_t)ops_s[nxt].a * PT_SLOT, FRAG_BYTES, &full[b1]);
-                }
-                __syncwarp();
+            // ------------------------------ K3: contraction over one internal edge ------------------------------
+            TL_MARK(oi * 8 + 0);
+            const uint32_t pst = pq % P_STAGES;
+            mbar_wait(&pfull[pst], (pq / P_STAGES) & 1);
+            if (skew_pending) {
+                __nanosleep(p.skew_ns);
+                skew_pending = false;
             }
-            mbar_wait(&full[b], u & 1);
+            TL_MARK(oi * 8 + 1);
             double acc[PRUNE_T][8][2];
             if (warp_active) {
-                const double* Pb = (b ? Pbuf1 : Pbuf0) + lane;
+                const double* Pb = reinterpret_cast<const double*>(Pring + pst * FRAG_BYTES) + lane;
 #pragma unroll
                 for (int T = 0; T < PRUNE_T; T++)
 #pragma unroll
@@ -389,42 +502,46 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[b]);
-            gemm_seen++;
-            if (!warp_active) continue;
-            // ------------------------------ epilogues ------------------------------
-            if (op.kind == OP_GEMM_LEAF) {
-#pragma unroll
-                for (int T = 0; T < PRUNE_T; T++)
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        cur[T][j][0] = acc[T][j][0];
-                        cur[T][j][1] = acc[T][j][1];
-                    }
-                load_leaf_mul(cur, ps.tables + (size_t)op.b * PT_SLOT, codes_s, p.n_leaves, op.b, wcol, g, t, false);
-            } else {
-                uint8_t* base = (op.c < p.smem_levels)
-                                    ? stack_s + (size_t)op.c * STACK_LEVEL_BYTES
-                                    : gstack + (size_t)(op.c - p.smem_levels) * STACK_LEVEL_BYTES;
-                double2* slot = reinterpret_cast<double2*>(base + (size_t)w * STACK_ENTRY_BYTES) + lane;
-                if (op.kind == OP_GEMM_PUSH) {
+            if (lane == 0) mbar_arrive(&pempty[pst]);
+            pq++;
+            TL_MARK(oi * 8 + 2);
+            // ------------------------------ epilogue ------------------------------
+            if (op.kind == OP_GEMM_PUSH) {
+                if (warp_active) {
+                    double2* slot = reinterpret_cast<double2*>(gstack + (size_t)op.c * STACK_LEVEL_BYTES + cw * STACK_ENTRY_BYTES) + lane;
 #pragma unroll
                     for (int T = 0; T < PRUNE_T; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) slot[(T * 8 + j) * 32] = make_double2(acc[T][j][0], acc[T][j][1]);
-                } else {  // OP_GEMM_POP
+                    // The producer reads the level back with a TMA bulk copy (async proxy). Writer-side
+                    // ordering: CTA-scope fence (writer and reader share the SM), generic->async proxy fence,
+                    // then the release-arrive on pushed[] that the producer acquires before issuing the copy.
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pushed[op.c]);
+            } else {  // OP_GEMM_LEAF / OP_GEMM_POP: multiply by the staged leaf message / parked partial
+                const uint32_t st = mq % M_STAGES;
+                mbar_wait(&mfull[st], (mq / M_STAGES) & 1);
+                TL_MARK(oi * 8 + 3);
+                if (warp_active) {
+                    const double2* m = reinterpret_cast<const double2*>(Mring + st * STACK_LEVEL_BYTES + cw * STACK_ENTRY_BYTES) + lane;
 #pragma unroll
                     for (int T = 0; T < PRUNE_T; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const double2 v = slot[(T * 8 + j) * 32];
+                            const double2 v = m[(T * 8 + j) * 32];
                             cur[T][j][0] = acc[T][j][0] * v.x;
                             cur[T][j][1] = acc[T][j][1] * v.y;
                         }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&mempty[st]);
+                mq++;
             }
+            TL_MARK(oi * 8 + 4);
         }
-        gq += (uint32_t)gemm_seen;
     }
 }
 
