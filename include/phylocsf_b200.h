@@ -125,6 +125,21 @@ int pcsf_lpr_all(pcsf_ctx *ctx, int n_models, const int32_t *model_ids, const in
 int pcsf_lpr(pcsf_ctx *ctx, int64_t n_evals, const int32_t *eval_model, const int32_t *eval_scale,
              const int64_t *eval_region, double *out_lpr, double *out_elpr_anc, int32_t *out_status);
 
+/*
+ * Many models at once (the omega strategy has one rate matrix per region and per kappa candidate,
+ * src/OmegaModel.ml:166-170). pcsf_models_set fills slots first_id .. first_id+n-1 from arrays of n
+ * consecutive S, Sinv (64x64), lambda, prior (64) blocks; the block lives until the next
+ * pcsf_models_set call, which unsets those slots. pcsf_pt_build_pairs builds one P set per
+ * (model, scale) pair in one K1 launch sequence (replacing the previous pairs); pcsf_lpr_pairs scores
+ * evaluation e = region eval_region[e] under pair eval_pair[e].
+ */
+int pcsf_models_set(pcsf_ctx *ctx, int first_id, int n, const double *S, const double *Sinv, const double *lambda,
+                    const double *prior);
+int pcsf_pt_build_pairs(pcsf_ctx *ctx, int64_t npairs, const int32_t *pair_model, const double *pair_scale,
+                        int32_t *status);
+int pcsf_lpr_pairs(pcsf_ctx *ctx, int64_t n_evals, const int64_t *eval_pair, const int64_t *eval_region,
+                   double *out_lpr, double *out_elpr_anc, int32_t *out_status);
+
 /* Per-column terms of the most recent pcsf_lpr_all call for its m-th listed model:
  * col_logz[c] = log z(c), col_anc[c] = post_root(c) . log prior (either may be NULL). */
 int pcsf_column_terms(pcsf_ctx *ctx, int m, double *col_logz, double *col_anc);

@@ -9,7 +9,9 @@ It restates the reference's OCaml host logic in numpy and calls oracle/liboracle
 file:line it follows (paths relative to /root/reference). It is written independently of the
 C++/CUDA product: eigendecomposition here is LAPACK's general non-symmetric solver
 (numpy.linalg.eig, like GSL's gsl_eigen_nonsymmv at lib/CamlPaml/Q.ml:126) and the inverse is an LU
-inverse (Q.ml:83-93), whereas the product symmetrises Q and runs its own Jacobi solver.
+inverse (Q.ml:83-93), whereas the product symmetrises Q and runs its own Jacobi solver. (When LAPACK
+splits a degenerate real eigenvalue of a reversible Q into a complex pair - the omega model's Q does
+that - the oracle falls back to LAPACK's symmetric solver on the symmetrised matrix, QDiag._symmetric_path.)
 
 Third-party pieces restated because they are not in /root/reference (GSL, version unpinned by the
 reference; OCaml stdlib Random): gsl_min_fminimizer_brent + gsl_min_fminimizer_set (GSL min/brent.c,
@@ -370,7 +372,15 @@ class QDiag:
         self.q = np.ascontiguousarray(qm, dtype=np.float64)
         self.tol = tol
         lam, s = np.linalg.eig(self.q)  # general non-symmetric, like gsl_eigen_nonsymmv (Q.ml:126)
-        sinv = np.linalg.inv(s)  # LU inverse, like zinvm (Q.ml:83-93)
+        if np.iscomplexobj(lam) and np.any(lam.imag != 0.0):
+            # LAPACK split a (near-)degenerate real eigenvalue of a reversible Q into a conjugate pair whose
+            # eigenvectors are genuinely complex; the reference's real_of_complex would reject them. For a
+            # reversible Q the spectrum is real: redo it on the symmetrised matrix with LAPACK's symmetric
+            # solver (dsyevd - still independent of the product's Jacobi code). The omega model's Q has such
+            # degeneracies; the ECMs do not.
+            lam, s, sinv = self._symmetric_path()
+        else:
+            sinv = np.linalg.inv(s)  # LU inverse, like zinvm (Q.ml:83-93)
         if not all(_check_real(complex(z), tol) for z in lam):
             raise OracleFailure("oracle: non-reversible model (complex eigenvalues) is out of scope")
         for m in (s, sinv):
@@ -381,6 +391,18 @@ class QDiag:
         self.lam = np.ascontiguousarray(np.real(lam), dtype=np.float64)
         self._pi = None
         self._memo = {}
+
+    def _symmetric_path(self):
+        k = self.q.shape[0]
+        u_, sv, vt = np.linalg.svd(self.q.T)  # stationary weights = null vector of Q^T
+        w = np.abs(vt[-1])
+        w = w / w.sum()
+        sw = np.sqrt(w)
+        a = sw[:, None] * self.q / sw[None, :]
+        if np.abs(a - a.T).max() > 1e-9 * max(1.0, np.abs(a).max()):
+            raise OracleFailure("oracle: non-reversible model (complex eigenvalues) is out of scope")
+        lam, u = np.linalg.eigh(0.5 * (a + a.T))
+        return lam, u / sw[:, None], u.T * sw[None, :]
 
     def scaled(self, x: float) -> "QDiag":  # Q.ml:193-209
         if x <= 0.0:

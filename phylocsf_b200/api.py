@@ -114,6 +114,27 @@ class Context:
         self._check(self._L.pcsf_lpr(self._h, n, N.ptr(em), N.ptr(es), N.ptr(er), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
         return lpr, elpr, st
 
+    def models_set(self, first_id, S, Sinv, lam, prior):
+        S, Sinv, lam, prior = _f64(S), _f64(Sinv), _f64(lam), _f64(prior)
+        n = S.shape[0]
+        assert S.shape == (n, 64, 64) and Sinv.shape == (n, 64, 64) and lam.shape == (n, 64) and prior.shape == (n, 64)
+        self._check(self._L.pcsf_models_set(self._h, first_id, n, N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior)))
+
+    def pt_build_pairs(self, pair_model, pair_scale, check=True):
+        pm = np.ascontiguousarray(pair_model, dtype=np.int32)
+        sc = _f64(pair_scale)
+        st = np.zeros(pm.size, dtype=np.int32)
+        self._check(self._L.pcsf_pt_build_pairs(self._h, pm.size, N.ptr(pm), N.ptr(sc), N.ptr(st)), ok_numeric=not check)
+        return st
+
+    def lpr_pairs(self, eval_pair, eval_region):
+        ep = np.ascontiguousarray(eval_pair, dtype=np.int64)
+        er = np.ascontiguousarray(eval_region, dtype=np.int64)
+        n = ep.size
+        lpr, elpr, st = np.empty(n), np.empty(n), np.zeros(n, dtype=np.int32)
+        self._check(self._L.pcsf_lpr_pairs(self._h, n, N.ptr(ep), N.ptr(er), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
+        return lpr, elpr, st
+
     def column_terms(self, m):
         n = self.ncols
         a, b = np.empty(n), np.empty(n)

@@ -11,6 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphylocsf_b200.so")
+CLI = os.path.join(HERE, "bin", "PhyloCSF")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2", "-shared",
@@ -29,9 +30,9 @@ def deps():
 
 
 def stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(CLI))
     return any(os.path.getmtime(d) > t for d in deps())
 
 
@@ -43,6 +44,11 @@ def build(force=False, verbose=False):
         nvcc = "nvcc"
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     subprocess.check_call(cmd)
+    # the drop-in command line: C++ host over the C ABI, finds the library next to itself
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-o", CLI, os.path.join(CSRC, "host", "cli_main.cpp"),
+                           "-L" + HERE, "-lphylocsf_b200", "-Wl,-rpath,$ORIGIN/.."])
     return LIB
 
 

@@ -1,0 +1,431 @@
+// driver.hpp — the drop-in PhyloCSF driver over the C ABI: option surface, batching of regions from
+// many alignments onto the GPU, the three scoring strategies, region selection and the report lines.
+//   options / main loop      <- src/PhyloCSF.ml:17-49,469-491
+//   process_alignment        <- src/PhyloCSF.ml:280-389 (three-tier error policy, report format)
+//   PhyloCSFModel.score      <- src/PhyloCSFModel.ml:113-146 (fixed / mle)
+//   OmegaModel.score, kr_map <- src/OmegaModel.ml:102-219
+// The reference evaluates one region at a time; here the regions of many alignments are staged as
+// one batch (pcsf_batch_upload) and every strategy advances all of them together.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/phylocsf_b200.h"
+#include "../pcsf_brent.hpp"
+#include "alignment.hpp"
+#include "paramset.hpp"
+
+namespace pcsf {
+namespace host {
+
+enum Strategy { STRAT_MLE, STRAT_FIXED, STRAT_OMEGA, STRAT_NOP };
+
+struct Options {
+    Strategy strategy = STRAT_MLE;
+    bool filenames = false, remove_ref_gaps = false, allow_ref_gaps = false;
+    std::string species;  // csv, empty = all
+    int frames = 1;
+    OrfMode orf = AsIs;
+    int min_codons = 25;
+    bool all_scores = false;
+    int procs = 1;
+    bool bls = false, anc_comp = false, dna = false, aa = false, debug = false;
+    double omega_H1 = 0.2, sigma_H1 = 0.01;
+    // not in the reference: how many codon columns to stage per GPU batch
+    int64_t batch_cols = 4000000;
+    int device = 0;
+};
+
+struct ScoreRecord {
+    double score = 0.0, anc_comp = 0.0;
+    std::vector<std::pair<std::string, std::string>> diag;
+    std::string exn;  // non-empty: this region raised (Printexc text)
+};
+
+inline double db(double x) { return 10.0 * x / std::log(10.0); }
+inline std::string sf2(double x) {
+    char b[64];
+    snprintf(b, sizeof b, "%.2f", x);
+    return b;
+}
+
+struct AlnJob {
+    std::string name;
+    std::vector<std::string> aln, rc_aln;
+    std::map<std::string, int> which_row;
+    std::vector<Region> regions;
+    int64_t first_region = 0;
+    std::string failure;  // per-alignment failure text (no ORFs)
+};
+
+inline std::string status_exn(int32_t st) {
+    if (st & PCSF_ST_NEG_T) return "Invalid_argument(\"CamlPaml.Q.to_Pt\")";
+    if (st & (PCSF_ST_NEG_ENTRY | PCSF_ST_ROWSUM)) return "Failure(\"CamlPaml.Q.substitution matrix: expm(t*Q) failed its checks\")";
+    if (st & PCSF_ST_DIAG_ASSERT) return "Assert_failure(\"lib/CamlPaml/Q.ml\", 245, 3)";
+    if (st & PCSF_ST_BRACKET) return "Gsl.Error.Gsl_exn(Gsl.Error.EINVAL, \"endpoints do not enclose a minimum\")";
+    if (st & PCSF_ST_NOT_FINITE) return "Gsl.Error.Gsl_exn(Gsl.Error.EBADFUNC, \"computed function value is infinite or NaN\")";
+    return "";
+}
+
+class Driver {
+  public:
+    Driver(const Options& o, const std::string& paramset_prefix) : opt(o) {
+        ps = load_paramset(paramset_prefix, o.species, o.strategy == STRAT_MLE || o.strategy == STRAT_FIXED);
+        n_leaves = ps.tree.n_leaves;
+        leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
+        if (o.strategy != STRAT_NOP) {
+            if (pcsf_create(o.device, &ctx) != PCSF_OK)
+                throw failure("phylocsf_b200: no usable CUDA device (there is no CPU fallback)");
+            const auto ch = ps.tree.children_array();
+            std::vector<double> bl(ps.tree.branches.begin(), ps.tree.branches.begin() + ps.tree.root());
+            check(pcsf_tree_set(ctx, n_leaves, ch.data(), bl.data()));
+            if (ps.have_ecm)
+                for (int w = 0; w < 2; w++)
+                    check(pcsf_model_set(ctx, w, ps.qd[w].S.data(), ps.qd[w].Sinv.data(), ps.qd[w].lam.data(), ps.qd[w].pi_eq.data()));
+            if (o.strategy == STRAT_FIXED) {
+                const double one = 1.0;
+                check(pcsf_pt_build(ctx, 0, 1, &one, nullptr));
+                check(pcsf_pt_build(ctx, 1, 1, &one, nullptr));
+            }
+        }
+    }
+    ~Driver() {
+        if (ctx) pcsf_destroy(ctx);
+    }
+
+    // Returns false when the run must stop (an alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
+    bool add_alignment(const std::string& name, const std::vector<std::string>& lines, std::ostream& out) {
+        AlnJob job;
+        job.name = name;
+        try {
+            Alignment a = input_mfa(lines);
+            if (opt.remove_ref_gaps) remove_ref_gaps(a.seqs);
+            for (auto& s : a.seqs)
+                for (auto& c : s) c = c == 'u' ? 't' : (c == 'U' ? 'T' : c);
+            if (!opt.allow_ref_gaps && a.seqs[0].find('-') != std::string::npos)
+                throw failure("the reference sequence (first alignment row) must be ungapped");
+            job.aln = a.seqs;
+            for (auto& s : a.seqs) job.rc_aln.push_back(revcomp(s));
+            std::set<std::string> tsp(leaf_labels.begin(), leaf_labels.end()), wtf;
+            for (auto& sp : a.species)
+                if (!tsp.count(sp)) wtf.insert(sp);
+            if (!wtf.empty()) {
+                std::string m = "parameters not available for species:";
+                for (auto& s : wtf) m += " " + s;
+                throw failure(m);
+            }
+            for (size_t i = 0; i < a.species.size(); i++) job.which_row[a.species[i]] = (int)i;
+            job.regions = candidate_regions(job.aln[0], opt.orf, opt.frames, opt.min_codons);
+            if (job.regions.empty()) job.failure = "Failure(\"no sufficiently long ORFs found\")";
+        } catch (const HostError& e) {
+            flush(out);
+            out << name << "\tabort\t" << e.what() << "\n";
+            out.flush();
+            return false;
+        }
+        std::vector<int> leaf_ord(n_leaves, -1);
+        for (int l = 0; l < n_leaves; l++) {
+            auto it = job.which_row.find(leaf_labels[l]);
+            if (it != job.which_row.end()) leaf_ord[l] = it->second;
+        }
+        job.first_region = (int64_t)region_off.size() - 1;
+        for (const Region& r : job.regions) {
+            const int nc = pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, codes);
+            region_off.push_back(region_off.back() + nc);
+        }
+        jobs.push_back(std::move(job));
+        if (region_off.back() >= opt.batch_cols) flush(out);
+        return true;
+    }
+
+    void flush(std::ostream& out) {
+        if (jobs.empty()) return;
+        const int64_t R = (int64_t)region_off.size() - 1;
+        std::vector<ScoreRecord> rec(R);
+        if (R > 0) {
+            if (opt.strategy != STRAT_NOP) check(pcsf_batch_upload(ctx, R, region_off.data(), codes.data()));
+            switch (opt.strategy) {
+                case STRAT_FIXED: score_fixed(rec); break;
+                case STRAT_MLE: score_mle(rec); break;
+                case STRAT_OMEGA: score_omega(rec); break;
+                case STRAT_NOP: break;
+            }
+        }
+        for (const AlnJob& j : jobs) report(j, rec, out);
+        jobs.clear();
+        codes.clear();
+        region_off.assign(1, 0);
+    }
+
+    int64_t evaluations = 0;  // likelihood evaluations (region x model) issued, for --debug statistics
+
+  private:
+    Options opt;
+    ParamSet ps;
+    pcsf_ctx* ctx = nullptr;
+    int n_leaves = 0;
+    std::vector<std::string> leaf_labels;
+    std::vector<AlnJob> jobs;
+    std::vector<uint8_t> codes;
+    std::vector<int64_t> region_off{0};
+
+    void check(int rc) {
+        if (rc != PCSF_OK && rc != PCSF_ERR_NUMERIC) throw failure(std::string("phylocsf_b200: ") + pcsf_last_error(ctx));
+    }
+
+    // ---- PhyloCSFModel.llr_FixedLik (src/PhyloCSFModel.ml:122-128) ----
+    void score_fixed(std::vector<ScoreRecord>& rec) {
+        const int64_t R = (int64_t)rec.size();
+        std::vector<double> lpr(2 * R), elpr(2 * R);
+        std::vector<int32_t> st(2 * R);
+        const int32_t mids[2] = {0, 1};
+        check(pcsf_lpr_all(ctx, 2, mids, nullptr, lpr.data(), elpr.data(), st.data()));
+        evaluations += 2 * R;
+        for (int64_t r = 0; r < R; r++) {
+            const int32_t bad = (st[r] | st[R + r]) & ~PCSF_ST_NOT_FINITE;  // log 0 = -inf is not an exception here
+            if (bad) { rec[r].exn = status_exn(bad); continue; }
+            rec[r].score = db(lpr[r] - lpr[R + r]);
+            rec[r].anc_comp = db(elpr[r] - elpr[R + r]);
+            rec[r].diag = {{"rho", sf2(1.0)}, {"L(C)", sf2(db(lpr[r]))}, {"L(NC)", sf2(db(lpr[R + r]))}};
+        }
+    }
+
+    // ---- PhyloCSFModel.llr_MaxLik ~init:1. (src/PhyloCSFModel.ml:130-136) ----
+    void score_mle(std::vector<ScoreRecord>& rec) {
+        const int64_t R = (int64_t)rec.size();
+        std::vector<double> rho[2], lpr[2], elpr[2];
+        std::vector<int32_t> st[2], ne[2];
+        for (int m = 0; m < 2; m++) {
+            rho[m].resize(R); lpr[m].resize(R); elpr[m].resize(R); st[m].resize(R); ne[m].resize(R);
+            check(pcsf_maximize_lpr(ctx, m, 1.0, 1e-2, 10.0, 0.01, rho[m].data(), lpr[m].data(), elpr[m].data(), st[m].data(), ne[m].data()));
+            for (int64_t r = 0; r < R; r++) evaluations += ne[m][r];
+        }
+        for (int64_t r = 0; r < R; r++) {
+            const int32_t b0 = st[0][r] & ~PCSF_ST_RANDOM_INIT, b1 = st[1][r] & ~PCSF_ST_RANDOM_INIT;
+            if (b0 || b1) { rec[r].exn = status_exn(b0 ? b0 : b1); continue; }  // coding model is maximised first
+            rec[r].score = db(lpr[0][r] - lpr[1][r]);
+            rec[r].anc_comp = db(elpr[0][r] - elpr[1][r]);
+            rec[r].diag = {{"rho_0", sf2(1.0)}, {"rho_C", sf2(rho[0][r])}, {"rho_N", sf2(rho[1][r])},
+                           {"L(C)", sf2(db(lpr[0][r]))}, {"L(NC)", sf2(db(lpr[1][r]))}};
+        }
+    }
+
+    // ---- OmegaModel (src/OmegaModel.ml) ----
+    struct OmegaInst {
+        double qs[12];
+        double rho;
+    };
+    static double lpr_rho(double x) {  // half_cauchy_lpdf ~mode:1.0 ~scale:0.5, OmegaModel.ml:148-156
+        const double pi = std::acos(-1.0), mode = 1.0, scale = 0.5;
+        const double numer = 1.0 / (pi * scale * (1.0 + std::pow((x - mode) / scale, 2.0)));
+        const double denom = 1.0 - (std::atan((0.0 - mode) / scale) / pi + 0.5);
+        return std::log(numer) - std::log(denom);
+    }
+    static double lpr_kappa(double k) {  // log (gsl_ran_gamma_pdf ~a:7 ~b:0.25 (k - 1 + epsilon_float)), :157
+        const double x = k - 1.0 + 2.220446049250313e-16, a = 7.0, b = 0.25;
+        double p;
+        if (x < 0) p = 0;
+        else if (x == 0) p = 0;
+        else p = std::exp((a - 1) * std::log(x / b) - x / b - std::lgamma(a)) / b;
+        return std::log(p);
+    }
+
+    // Diagonalise Q(qs) for every listed region on host threads and install them as models slot = index.
+    void omega_install_models(const std::vector<OmegaInst>& inst, const std::vector<int64_t>& which, std::vector<std::string>& exn) {
+        const size_t n = which.size();
+        std::vector<double> S(n * 4096), Sinv(n * 4096), lam(n * 64), prior(n * 64);
+        auto work = [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; i++) {
+                try {
+                    std::vector<double> pi;
+                    const std::vector<double> q = omega_q(inst[which[i]].qs, &pi);
+                    QDiag d = QDiag::of_reversible_Q(q, pi);
+                    std::memcpy(&S[i * 4096], d.S.data(), 4096 * 8);
+                    std::memcpy(&Sinv[i * 4096], d.Sinv.data(), 4096 * 8);
+                    std::memcpy(&lam[i * 64], d.lam.data(), 64 * 8);
+                    std::memcpy(&prior[i * 64], d.pi_eq.data(), 64 * 8);
+                } catch (const std::exception& e) {
+                    exn[which[i]] = e.what();
+                    for (int k = 0; k < 64; k++) { prior[i * 64 + k] = 1.0 / 64; S[i * 4096 + 65 * k] = Sinv[i * 4096 + 65 * k] = 1.0; }
+                }
+            }
+        };
+        const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n));
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+        for (auto& t : th) t.join();
+        check(pcsf_models_set(ctx, 0, (int)n, S.data(), Sinv.data(), lam.data(), prior.data()));
+    }
+
+    // One coordinate of kr_map (OmegaModel.ml:171-188) for all regions at once: maximize_lpr over rho
+    // (kappa_phase = false: rate matrices fixed, tree scale varies) or over kappa (new Q per candidate).
+    void omega_maximize(std::vector<OmegaInst>& inst, bool kappa_phase, std::vector<double>& lpr_out, std::vector<std::string>& exn) {
+        const int64_t R = (int64_t)inst.size();
+        std::vector<MaximizeLpr> st;
+        st.reserve(R);
+        for (int64_t r = 0; r < R; r++)
+            st.emplace_back(kappa_phase ? inst[r].qs[0] : inst[r].rho, kappa_phase ? 1.0 : 0.001, 10.0, 0.01);
+        std::vector<int64_t> all(R);
+        for (int64_t r = 0; r < R; r++) all[r] = r;
+        if (!kappa_phase) omega_install_models(inst, all, exn);  // slot r = region r
+        std::vector<int64_t> live, eval_pair;
+        std::vector<int32_t> pair_model, pstat, estat;
+        std::vector<double> pair_scale, lpr, xs;
+        for (;;) {
+            live.clear();
+            xs.clear();
+            for (int64_t r = 0; r < R; r++)
+                if (!st[r].done() && exn[r].empty()) { live.push_back(r); xs.push_back(st[r].candidate()); }
+            if (live.empty()) break;
+            const int64_t n = (int64_t)live.size();
+            pair_model.resize(n);
+            pair_scale.resize(n);
+            eval_pair.resize(n);
+            if (kappa_phase) {
+                std::vector<OmegaInst> cand(inst);
+                for (int64_t i = 0; i < n; i++) cand[live[i]].qs[0] = xs[i];
+                omega_install_models(cand, live, exn);  // slot i = i-th live region
+                for (int64_t i = 0; i < n; i++) { pair_model[i] = (int32_t)i; pair_scale[i] = inst[live[i]].rho; }
+            } else {
+                for (int64_t i = 0; i < n; i++) { pair_model[i] = (int32_t)live[i]; pair_scale[i] = xs[i]; }
+            }
+            for (int64_t i = 0; i < n; i++) eval_pair[i] = i;
+            pstat.assign(n, 0);
+            estat.assign(n, 0);
+            lpr.assign(n, 0.0);
+            check(pcsf_pt_build_pairs(ctx, n, pair_model.data(), pair_scale.data(), pstat.data()));
+            check(pcsf_lpr_pairs(ctx, n, eval_pair.data(), live.data(), lpr.data(), nullptr, estat.data()));
+            evaluations += n;
+            for (int64_t i = 0; i < n; i++) {
+                const int64_t r = live[i];
+                if (!exn[r].empty()) continue;  // diagonalisation failed for this candidate
+                const double prior = kappa_phase ? lpr_kappa(xs[i]) : lpr_rho(xs[i]);
+                st[r].feed(prior + lpr[i], 0.0, estat[i] & ~PCSF_ST_NOT_FINITE);
+            }
+        }
+        for (int64_t r = 0; r < R; r++) {
+            if (!exn[r].empty()) continue;
+            const int32_t bad = st[r].status & ~PCSF_ST_RANDOM_INIT;
+            if (bad) { exn[r] = status_exn(bad); continue; }
+            (kappa_phase ? inst[r].qs[0] : inst[r].rho) = st[r].result_x;
+            lpr_out[r] = st[r].result_f;
+        }
+    }
+
+    void omega_kr_map(std::vector<OmegaInst>& inst, std::vector<double>& lpr, std::vector<std::string>& exn) {
+        for (int round = 0; round < 3; round++) {  // OmegaModel.ml:189-190
+            omega_maximize(inst, false, lpr, exn);
+            omega_maximize(inst, true, lpr, exn);
+        }
+    }
+
+    void score_omega(std::vector<ScoreRecord>& rec) {
+        const int64_t R = (int64_t)rec.size();
+        std::vector<OmegaInst> inst(R);
+        std::vector<std::string> exn(R);
+        for (int64_t r = 0; r < R; r++) {  // new_instance ~kappa:2.5 + update_f3x4 (OmegaModel.ml:95-134,197)
+            OmegaInst& in = inst[r];
+            in.qs[0] = 2.5; in.qs[1] = 1.0; in.qs[2] = 1.0;
+            in.rho = 1.0;
+            long counts[3][4];
+            for (auto& row : counts) for (auto& c : row) c = 1;
+            for (int64_t i = region_off[r] * n_leaves; i < region_off[r + 1] * n_leaves; i++) {
+                const int c = codes[i];
+                if (c < 64) { counts[0][c / 16]++; counts[1][(c / 4) % 4]++; counts[2][c % 4]++; }
+            }
+            for (int p = 0; p < 3; p++)
+                for (int n = 0; n < 3; n++) in.qs[3 + 3 * p + n] = (double)counts[p][n] / (double)counts[p][3];
+        }
+        std::vector<double> lpr0(R, 0.0), lpr1(R, 0.0);
+        omega_kr_map(inst, lpr0, exn);
+        std::vector<OmegaInst> inst0(inst);
+        for (int64_t r = 0; r < R; r++) { inst[r].qs[1] = opt.omega_H1; inst[r].qs[2] = opt.sigma_H1; }
+        omega_kr_map(inst, lpr1, exn);
+        for (int64_t r = 0; r < R; r++) {
+            if (!exn[r].empty()) { rec[r].exn = exn[r]; continue; }
+            rec[r].score = 10.0 * (lpr1[r] - lpr0[r]) / std::log(10.0);
+            rec[r].anc_comp = std::nan("");
+            const OmegaInst &a = inst0[r], &b = inst[r];
+            rec[r].diag = {{"L(H0)", sf2(db(lpr0[r]))}, {"rho_H0", sf2(a.rho)}, {"kappa_H0", sf2(a.qs[0])}, {"omega_H0", sf2(a.qs[1])},
+                           {"sigma_H0", sf2(a.qs[2])}, {"L(H1)", sf2(db(lpr1[r]))}, {"rho_H1", sf2(b.rho)}, {"kappa_H1", sf2(b.qs[0])},
+                           {"omega_H1", sf2(b.qs[1])}, {"sigma_H1", sf2(b.qs[2])}};
+        }
+    }
+
+    // ---- report (src/PhyloCSF.ml:340-380) ----
+    static bool ocaml_ge(const ScoreRecord& a, const Region& ra, const ScoreRecord& b, const Region& rb) {
+        // structural compare of (score record, rc, lo, hi); a NaN makes the comparison false
+        const double ka[2] = {a.score, a.anc_comp}, kb[2] = {b.score, b.anc_comp};
+        for (int i = 0; i < 2; i++) {
+            if (std::isnan(ka[i]) || std::isnan(kb[i])) return false;
+            if (ka[i] > kb[i]) return true;
+            if (ka[i] < kb[i]) return false;
+        }
+        if (a.diag != b.diag) return a.diag > b.diag;
+        if (ra.rc != rb.rc) return ra.rc;
+        if (ra.lo != rb.lo) return ra.lo > rb.lo;
+        return ra.hi >= rb.hi;
+    }
+
+    void report(const AlnJob& j, const std::vector<ScoreRecord>& rec, std::ostream& out) {
+        char buf[64];
+        auto fmt4 = [&](double x) { snprintf(buf, sizeof buf, "%.4f", x); return std::string(buf); };
+        std::string fail = j.failure;
+        std::vector<int> ok;
+        if (fail.empty()) {
+            for (size_t k = 0; k < j.regions.size(); k++) {
+                const ScoreRecord& s = rec[j.first_region + k];
+                const Region& rg = j.regions[k];
+                if (s.exn.empty()) { ok.push_back((int)k); continue; }
+                out << j.name << "\texception\t" << rg.lo << "\t" << rg.hi;
+                if (opt.frames == 6) out << (rg.rc ? "\t-" : "\t+");
+                out << "\t" << s.exn << "\n";
+            }
+            if (ok.empty()) fail = "Failure(\"no regions successfully evaluated\")";
+        }
+        if (!fail.empty()) {
+            out << j.name << "\tfailure\t" << fail << "\n";
+            out.flush();
+            return;
+        }
+        auto line = [&](const char* ty, int k) {
+            const ScoreRecord& s = rec[j.first_region + k];
+            const Region& rg = j.regions[k];
+            const std::vector<std::string>& rows = rg.rc ? j.rc_aln : j.aln;
+            out << j.name << "\t" << ty << "\t" << fmt4(s.score);
+            if (opt.frames != 1 || opt.orf != AsIs) out << "\t" << rg.lo << "\t" << rg.hi;
+            if (opt.frames == 6) out << "\t" << (rg.rc ? '-' : '+');
+            if (opt.bls) out << "\t" << fmt4(bls_score(ps.nt, rows, j.which_row, rg.lo, rg.hi));
+            if (opt.anc_comp) out << "\t" << fmt4(s.anc_comp);
+            const std::string refdna = rows[0].substr(rg.lo, rg.hi - rg.lo + 1);
+            if (opt.dna) out << "\t" << refdna;
+            if (opt.aa) out << "\t" << translate(refdna);
+            if (opt.debug) {
+                out << "\t#";
+                for (auto& kv : s.diag) out << " " << kv.first << "=" << kv.second;
+            }
+            out << "\n";
+        };
+        if (opt.all_scores)
+            for (int k : ok) line("orf_score(decibans)", k);
+        int best = ok[0];
+        for (size_t i = 1; i < ok.size(); i++)
+            if (!ocaml_ge(rec[j.first_region + best], j.regions[best], rec[j.first_region + ok[i]], j.regions[ok[i]])) best = ok[i];
+        line((opt.orf != AsIs || opt.frames != 1) ? "max_score(decibans)" : "score(decibans)", best);
+        out.flush();
+    }
+
+};
+
+}  // namespace host
+}  // namespace pcsf

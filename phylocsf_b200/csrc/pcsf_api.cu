@@ -26,6 +26,7 @@ struct DevBuf {
 
 struct Model {
     bool set = false;
+    bool owns_params = true;     // false: d_params points into the context's batch block (pcsf_models_set)
     double* d_params = nullptr;  // S | Sinv | lambda | prior | logprior  (64*64*2 + 3*64 doubles)
     DevBuf tables;               // [nscales][n_branches][PT_SLOT]
     DevBuf d_scales, d_status;
@@ -63,6 +64,8 @@ struct pcsf_ctx {
     DevBuf d_region_off, d_codes, d_nt, d_aln_off, d_aln_len;
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
+    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status;
+    std::vector<int32_t> pair_model, pair_status;  // P sets built by pcsf_pt_build_pairs
     int last_all_models = 0;
     // timing
     cudaEvent_t ev[10];
@@ -268,32 +271,61 @@ PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
     return ps;
 }
 
-int pt_build_device(pcsf_ctx* ctx, Model& m, int nscales, const double* scales) {
-    TRY(reserve(ctx, m.tables, sizeof(double) * (size_t)nscales * ctx->n_branches * PT_SLOT));
-    TRY(reserve(ctx, m.d_scales, sizeof(double) * nscales));
-    TRY(reserve(ctx, m.d_status, sizeof(int32_t) * nscales));
-    CU(cudaMemcpyAsync(m.d_scales.p, scales, sizeof(double) * nscales, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(m.d_status.p, 0, sizeof(int32_t) * nscales, ctx->stream));
+// K1 over a list of jobs: tables[job][branch][PT_SLOT], status[job]
+int pt_build_jobs(pcsf_ctx* ctx, const std::vector<PtJob>& jobs, DevBuf& tables, DevBuf& d_status, std::vector<int32_t>& status) {
+    const int64_t n = (int64_t)jobs.size();
+    TRY(reserve(ctx, tables, sizeof(double) * (size_t)n * ctx->n_branches * PT_SLOT));
+    TRY(reserve(ctx, ctx->d_jobs, sizeof(PtJob) * n));
+    TRY(reserve(ctx, d_status, sizeof(int32_t) * n));
+    CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(PtJob) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_status.p, 0, sizeof(int32_t) * n, ctx->stream));
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-    // gridDim.y is limited to 65535: slice the scales
-    for (int s0 = 0; s0 < nscales; s0 += 32768) {
-        const int ns = std::min(32768, nscales - s0);
+    for (int64_t s0 = 0; s0 < n; s0 += 32768) {  // gridDim.y limit
+        const int ns = (int)std::min<int64_t>(32768, n - s0);
         dim3 grid(ctx->n_branches, ns);
-        pt_build_kernel<<<grid, 256, 0, ctx->stream>>>(m.S(), m.Sinv(), m.lambda(), ctx->d_branch_len,
-                                                       (const double*)m.d_scales.p + s0, ctx->n_leaves,
-                                                       (double*)m.tables.p + (size_t)s0 * ctx->n_branches * PT_SLOT,
-                                                       (int32_t*)m.d_status.p + s0, 1e-6);
+        pt_build_kernel<<<grid, 256, 0, ctx->stream>>>((const PtJob*)ctx->d_jobs.p + s0, ctx->d_branch_len, ctx->n_leaves,
+                                                       (double*)tables.p + (size_t)s0 * ctx->n_branches * PT_SLOT,
+                                                       (int32_t*)d_status.p + s0, 1e-6);
         CU(cudaGetLastError());
         ctx->launches++;
     }
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-    m.nscales = nscales;
-    m.status.assign(nscales, 0);
-    CU(cudaMemcpyAsync(m.status.data(), m.d_status.p, sizeof(int32_t) * nscales, cudaMemcpyDeviceToHost, ctx->stream));
+    status.assign(n, 0);
+    CU(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
     ctx->ms[2] = t;
+    return PCSF_OK;
+}
+
+int pt_build_device(pcsf_ctx* ctx, Model& m, int nscales, const double* scales) {
+    std::vector<PtJob> jobs(nscales);
+    for (int i = 0; i < nscales; i++) jobs[i] = PtJob{m.d_params, scales[i]};
+    TRY(pt_build_jobs(ctx, jobs, m.tables, m.d_status, m.status));
+    m.nscales = nscales;
+    return PCSF_OK;
+}
+
+// Shared tail of the evaluation entry points: spans + P sets -> K2/K3 -> K4 -> host
+int eval_spans(pcsf_ctx* ctx, const std::vector<Span>& spans, const std::vector<PSet>& psets, int64_t out_cols,
+               const std::vector<int64_t>& seg_b, const std::vector<int64_t>& seg_e, double* out_lpr, double* out_elpr_anc) {
+    const int64_t n_evals = (int64_t)seg_b.size();
+    TRY(run_prune(ctx, spans, psets, out_cols));
+    TRY(reserve(ctx, ctx->d_seg_begin, sizeof(int64_t) * std::max<int64_t>(n_evals, 1)));
+    TRY(reserve(ctx, ctx->d_seg_end, sizeof(int64_t) * std::max<int64_t>(n_evals, 1)));
+    if (n_evals > 0) {
+        CU(cudaMemcpyAsync(ctx->d_seg_begin.p, seg_b.data(), sizeof(int64_t) * n_evals, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_seg_end.p, seg_e.data(), sizeof(int64_t) * n_evals, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TRY(run_reduce(ctx, n_evals));
+    if (n_evals > 0) {
+        CU(cudaMemcpyAsync(out_lpr, ctx->d_lpr.p, sizeof(double) * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_elpr_anc) CU(cudaMemcpyAsync(out_elpr_anc, ctx->d_elpr.p, sizeof(double) * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    TRY(finish_timing(ctx));
+    ctx->last_all_models = 0;
     return PCSF_OK;
 }
 
@@ -352,14 +384,15 @@ void pcsf_destroy(pcsf_ctx* ctx) {
         b.p = nullptr;
     };
     for (auto& m : ctx->models) {
-        if (m.d_params) cudaFree(m.d_params);
+        if (m.d_params && m.owns_params) cudaFree(m.d_params);
         fr(m.tables);
         fr(m.d_scales);
         fr(m.d_status);
     }
     DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
-                      &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack};
+                      &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
+                      &ctx->d_pair_status};
     for (auto* b : bufs) fr(*b);
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
@@ -443,6 +476,7 @@ int pcsf_model_set(pcsf_ctx* ctx, int model_id, const double* S, const double* S
     memcpy(h.data() + 8192, lambda, 64 * 8);
     memcpy(h.data() + 8192 + 64, prior, 64 * 8);
     for (int i = 0; i < 64; i++) h[8192 + 128 + i] = log(prior[i]);  // anc_lprior, src/PhyloCSFModel.ml:74
+    if (!m.owns_params) { m.d_params = nullptr; m.owns_params = true; }
     if (!m.d_params) CU(cudaMalloc(&m.d_params, h.size() * 8));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpy(m.d_params, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
@@ -643,25 +677,112 @@ int pcsf_lpr(pcsf_ctx* ctx, int64_t n_evals, const int32_t* eval_model, const in
         }
         out += nc;
     }
-    TRY(run_prune(ctx, spans, psets, out));
-    TRY(reserve(ctx, ctx->d_seg_begin, sizeof(int64_t) * std::max<int64_t>(n_evals, 1)));
-    TRY(reserve(ctx, ctx->d_seg_end, sizeof(int64_t) * std::max<int64_t>(n_evals, 1)));
-    if (n_evals > 0) {
-        CU(cudaMemcpyAsync(ctx->d_seg_begin.p, seg_b.data(), sizeof(int64_t) * n_evals, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_seg_end.p, seg_e.data(), sizeof(int64_t) * n_evals, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    TRY(run_reduce(ctx, n_evals));
-    if (n_evals > 0) {
-        CU(cudaMemcpyAsync(out_lpr, ctx->d_lpr.p, sizeof(double) * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_elpr_anc) CU(cudaMemcpyAsync(out_elpr_anc, ctx->d_elpr.p, sizeof(double) * n_evals, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CU(cudaStreamSynchronize(ctx->stream));
-    TRY(finish_timing(ctx));
-    ctx->last_all_models = 0;
+    TRY(eval_spans(ctx, spans, psets, out, seg_b, seg_e, out_lpr, out_elpr_anc));
     if (out_status)
         for (int64_t e = 0; e < n_evals; e++)
             out_status[e] = ctx->models[eval_model[e]].status[eval_scale ? eval_scale[e] : 0] |
                             (std::isfinite(out_lpr[e]) ? 0 : PCSF_ST_NOT_FINITE);
+    return PCSF_OK;
+}
+
+int pcsf_models_set(pcsf_ctx* ctx, int first_id, int n, const double* S, const double* Sinv, const double* lambda,
+                    const double* prior) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (first_id < 0 || n < 1 || first_id + n > (1 << 22) || !S || !Sinv || !lambda || !prior)
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_models_set: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t per = 8192 + 192;
+    std::vector<double> h(per * n);
+    for (int i = 0; i < n; i++) {
+        double* d = h.data() + per * i;
+        memcpy(d, S + (size_t)4096 * i, 4096 * 8);
+        memcpy(d + 4096, Sinv + (size_t)4096 * i, 4096 * 8);
+        memcpy(d + 8192, lambda + (size_t)64 * i, 64 * 8);
+        memcpy(d + 8192 + 64, prior + (size_t)64 * i, 64 * 8);
+        for (int k = 0; k < 64; k++) d[8192 + 128 + k] = log(prior[(size_t)64 * i + k]);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    // models of the previous batch block become unset: the block is about to be reused
+    for (auto& m : ctx->models)
+        if (!m.owns_params) { m.set = false; m.d_params = nullptr; m.nscales = 0; }
+    TRY(reserve(ctx, ctx->d_batch_params, h.size() * 8));
+    CU(cudaMemcpy(ctx->d_batch_params.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    if ((int)ctx->models.size() < first_id + n) ctx->models.resize(first_id + n);
+    for (int i = 0; i < n; i++) {
+        Model& m = ctx->models[first_id + i];
+        if (m.d_params && m.owns_params) CU(cudaFree(m.d_params));
+        m.owns_params = false;
+        m.d_params = (double*)ctx->d_batch_params.p + per * i;
+        m.set = true;
+        m.nscales = 0;
+    }
+    ctx->pair_model.clear();
+    return PCSF_OK;
+}
+
+int pcsf_pt_build_pairs(pcsf_ctx* ctx, int64_t npairs, const int32_t* pair_model, const double* pair_scale, int32_t* status) {
+    TRY(check_ready(ctx, false));
+    if (npairs < 1 || !pair_model || !pair_scale) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_pt_build_pairs: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<PtJob> jobs(npairs);
+    for (int64_t i = 0; i < npairs; i++) {
+        const int mid = pair_model[i];
+        if (mid < 0 || mid >= (int)ctx->models.size() || !ctx->models[mid].set)
+            return fail(ctx, PCSF_ERR_STATE, "pcsf_pt_build_pairs: model " + std::to_string(mid) + " not set");
+        jobs[i] = PtJob{ctx->models[mid].d_params, pair_scale[i]};
+    }
+    ctx->pair_model.clear();
+    TRY(pt_build_jobs(ctx, jobs, ctx->d_pair_tables, ctx->d_pair_status, ctx->pair_status));
+    ctx->pair_model.assign(pair_model, pair_model + npairs);
+    bool bad = false;
+    for (int64_t i = 0; i < npairs; i++) {
+        if (status) status[i] = ctx->pair_status[i];
+        bad |= ctx->pair_status[i] != 0;
+    }
+    if (bad) return fail(ctx, PCSF_ERR_NUMERIC, "CamlPaml.Q.real_to_Pt: P(t) failed its checks for at least one pair (see status)");
+    return PCSF_OK;
+}
+
+int pcsf_lpr_pairs(pcsf_ctx* ctx, int64_t n_evals, const int64_t* eval_pair, const int64_t* eval_region, double* out_lpr,
+                   double* out_elpr_anc, int32_t* out_status) {
+    TRY(check_ready(ctx, true));
+    if (n_evals < 0 || !eval_pair || !eval_region || !out_lpr) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_lpr_pairs: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t npairs = (int64_t)ctx->pair_model.size();
+    std::vector<Span> spans;
+    std::vector<PSet> psets;
+    std::vector<int64_t> seg_b(n_evals), seg_e(n_evals);
+    spans.reserve(n_evals);
+    psets.reserve(n_evals);
+    int64_t out = 0, prev_pair = -1;
+    for (int64_t e = 0; e < n_evals; e++) {
+        const int64_t pr = eval_pair[e], r = eval_region[e];
+        if (pr < 0 || pr >= npairs) return fail(ctx, PCSF_ERR_STATE, "pcsf_lpr_pairs: pair index out of range (pcsf_pt_build_pairs)");
+        if (r < 0 || r >= ctx->nregions) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_lpr_pairs: region index out of range");
+        if (pr != prev_pair) {
+            const Model& m = ctx->models[ctx->pair_model[pr]];
+            PSet ps;
+            ps.tables = (const double*)ctx->d_pair_tables.p + (size_t)pr * ctx->n_branches * PT_SLOT;
+            ps.prior = m.prior();
+            ps.logprior = m.logprior();
+            psets.push_back(ps);
+            prev_pair = pr;
+        }
+        const int64_t c0 = ctx->region_off[r], nc = ctx->region_off[r + 1] - c0;
+        seg_b[e] = out;
+        seg_e[e] = out + nc;
+        if (!spans.empty() && spans.back().pset == (int32_t)psets.size() - 1 && spans.back().col0 + spans.back().ncols == c0 &&
+            spans.back().out0 + spans.back().ncols == out && (int64_t)spans.back().ncols + nc < 0x7fffffffLL) {
+            spans.back().ncols += (int32_t)nc;
+        } else {
+            spans.push_back(Span{c0, out, 0, (int32_t)nc, (int32_t)psets.size() - 1});
+        }
+        out += nc;
+    }
+    TRY(eval_spans(ctx, spans, psets, out, seg_b, seg_e, out_lpr, out_elpr_anc));
+    if (out_status)
+        for (int64_t e = 0; e < n_evals; e++)
+            out_status[e] = ctx->pair_status[eval_pair[e]] | (std::isfinite(out_lpr[e]) ? 0 : PCSF_ST_NOT_FINITE);
     return PCSF_OK;
 }
 

@@ -5,18 +5,11 @@
 #include <set>
 #include <sstream>
 
-#include "host/codon_model.hpp"
-#include "host/newick_tree.hpp"
+#include "host/paramset.hpp"
 
 using namespace pcsf::host;
 
-struct pcsf_paramset {
-    NewickPtr nt;  // after --species pruning
-    Tree tree;
-    bool have_ecm = false;
-    ECM ecm[2];
-    QDiag qd[2];
-};
+struct pcsf_paramset : ParamSet {};
 
 namespace {
 void put_err(char* err, int errlen, const std::string& m) {
@@ -24,13 +17,6 @@ void put_err(char* err, int errlen, const std::string& m) {
         std::strncpy(err, m.c_str(), (size_t)errlen - 1);
         err[errlen - 1] = 0;
     }
-}
-std::string slurp(const std::string& path) {
-    std::ifstream f(path);
-    if (!f) throw failure("could not find required parameter file " + path);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    return ss.str();
 }
 }  // namespace
 
@@ -43,25 +29,7 @@ int pcsf_paramset_load(const char* prefix, const char* species_csv, int with_ecm
     try {
         auto ps = new pcsf_paramset();
         std::unique_ptr<pcsf_paramset> guard(ps);
-        const std::string pre(prefix);
-        NewickPtr nt = newick_parse(slurp(pre + ".nh"));
-        if (species_csv && *species_csv) {
-            std::set<std::string> want;
-            std::stringstream ss(species_csv);
-            std::string tok;
-            while (std::getline(ss, tok, ',')) want.insert(tok);
-            NewickPtr snt = newick_subtree([&](const std::string& s) { return want.count(s) > 0; }, nt);
-            if (!snt || newick_leaves(*snt) <= 1) throw failure("specify at least two available --species");
-            nt = snt;
-        }
-        ps->nt = nt;
-        ps->tree = Tree::of_newick(*nt);
-        if (with_ecm) {
-            ps->ecm[0] = read_ecm(pre + "_coding.ECM");
-            ps->ecm[1] = read_ecm(pre + "_noncoding.ECM");
-            for (int w = 0; w < 2; w++) ps->qd[w] = QDiag::of_reversible_Q(ecm_q(ps->ecm[w]), ps->ecm[w].pi);
-            ps->have_ecm = true;
-        }
+        static_cast<ParamSet&>(*ps) = load_paramset(prefix, species_csv ? species_csv : "", with_ecm != 0);
         *out = guard.release();
         return PCSF_OK;
     } catch (const std::exception& e) {

@@ -109,12 +109,18 @@ __host__ __device__ __forceinline__ int frag_index(int a, int b) {
 //   CTA writes the table in the layout the pruning kernel wants: leaves get the transposed gather
 //   table PT[code][a] (+ row 64 = row sums, the `Marginalize message); internal edges get the
 //   fragment-ordered image.
-__global__ void __launch_bounds__(256) pt_build_kernel(const double* __restrict__ S, const double* __restrict__ Sinv,
-                                                       const double* __restrict__ lambda,
-                                                       const double* __restrict__ branch_len,
-                                                       const double* __restrict__ scales, int n_leaves,
+struct PtJob {               // one P set to build: a diagonalised model at one tree scale
+    const double* params;   // S | Sinv | lambda | prior | logprior (pcsf_api.cu: Model)
+    double scale;
+};
+__global__ void __launch_bounds__(256) pt_build_kernel(const PtJob* __restrict__ jobs,
+                                                       const double* __restrict__ branch_len, int n_leaves,
                                                        double* __restrict__ tables, int32_t* __restrict__ status,
                                                        double tol) {
+    const PtJob job = jobs[blockIdx.y];
+    const double* __restrict__ S = job.params;
+    const double* __restrict__ Sinv = job.params + 4096;
+    const double* __restrict__ lambda = job.params + 8192;
     __shared__ double Psm[64][65];
     __shared__ double e_s[64];
     __shared__ double rowsum_s[64];
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(256) pt_build_kernel(const double* __restrict_
     const int n_branches = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const double tt = scales[sc] * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
+    const double tt = job.scale * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
     if (tid < 64) e_s[tid] = exp(tt * lambda[tid]);  // Q.ml:216-217
     __syncthreads();
     double acc[8][2];

@@ -1,0 +1,171 @@
+"""The drop-in command line (phylocsf_b200/bin/PhyloCSF, C++ host over the C ABI) against the oracle's
+restatement of src/PhyloCSF.ml:process_alignment, line for line. --strategy=nop exercises the whole
+host pipeline (MFA reader, species pruning, ORF search, regions, report format, error tiers) without a
+GPU; the gpu-marked tests run fixed / mle / omega and the reference's own golden checks (src/test.ml)."""
+import os
+import subprocess
+
+import pytest
+
+from oracle import oracle as o
+from tools import golden_params as gp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "phylocsf_b200", "bin", "PhyloCSF")
+
+
+def run_cli(params_base, pset, files, *flags, stdin=None, expect_rc=0):
+    env = dict(os.environ, PHYLOCSF_BASE=params_base)
+    r = subprocess.run([CLI, pset] + list(files) + list(flags), env=env, input=stdin, capture_output=True, text=True, timeout=600)
+    assert r.returncode == expect_rc, (r.returncode, r.stdout, r.stderr)
+    return r.stdout.splitlines()
+
+
+def run_oracle(params_base, pset, name, lines, **kw):
+    opts = o.Options(**kw)
+    ps = o.load_paramset(os.path.join(params_base, "PhyloCSF_Parameters", pset), opts)
+    return o.process_alignment(ps, opts, name, lines)
+
+
+def same_lines(a, b, tol=1.5e-4):
+    """Equal up to the last printed digit of floating-point fields."""
+    assert len(a) == len(b), (a, b)
+    for la, lb in zip(a, b):
+        fa, fb = la.split("\t"), lb.split("\t")
+        assert len(fa) == len(fb), (la, lb)
+        for x, y in zip(fa, fb):
+            if x == y:
+                continue
+            try:
+                assert abs(float(x) - float(y)) <= tol, (la, lb)
+            except ValueError:
+                raise AssertionError((la, lb))
+
+
+def ex(params_base, fn):
+    return os.path.join(params_base, "PhyloCSF_Examples", fn)
+
+
+NOP_CASES = [
+    ("12flies", "tal-AA.fa", [], {}),
+    ("12flies", "tal-AA.fa", ["--frames=3", "--allScores", "--dna", "--aa", "--bls"], dict(frames=3, all_scores=True, dna=True, aa=True, bls=True)),
+    ("29mammals", "ALDH2.exon5.fa", ["-f", "6", "--allScores", "--bls", "--ancComp"], dict(frames=6, all_scores=True, bls=True, anc_comp=True)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--orf=ATGStop", "--frames=3", "--removeRefGaps", "--aa", "--allScores"],
+     dict(orf="ATGStop", frames=3, remove_ref_gaps=True, aa=True, all_scores=True)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--orf=StopStop", "--frames=6", "--removeRefGaps", "--allScores", "--minCodons=40", "--bls"],
+     dict(orf="StopStop", frames=6, remove_ref_gaps=True, all_scores=True, min_codons=40, bls=True)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--orf=StopStop3", "--frames=3", "--removeRefGaps", "--allScores"],
+     dict(orf="StopStop3", frames=3, remove_ref_gaps=True, all_scores=True)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--orf=ToFirstStop", "--frames=3", "--removeRefGaps", "--allScores", "--minCodons=1"],
+     dict(orf="ToFirstStop", frames=3, remove_ref_gaps=True, all_scores=True, min_codons=1)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--orf=FromLastStop", "--frames=6", "--removeRefGaps", "--allScores", "--minCodons=1"],
+     dict(orf="FromLastStop", frames=6, remove_ref_gaps=True, all_scores=True, min_codons=1)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--orf=ToOrFromStop", "--frames=6", "--removeRefGaps", "--allScores", "--minCodons=1"],
+     dict(orf="ToOrFromStop", frames=6, remove_ref_gaps=True, all_scores=True, min_codons=1)),
+    ("29mammals", "ALDH2.exon5.fa", ["--species=Human,Mouse,Rat,Dog,Cow,Horse", "--bls", "--frames=3"],
+     dict(species=["Human", "Mouse", "Rat", "Dog", "Cow", "Horse"], bls=True, frames=3)),
+]
+
+
+@pytest.mark.parametrize("pset,fn,flags,kw", NOP_CASES)
+def test_nop_pipeline_matches_oracle(params_base, pset, fn, flags, kw):
+    path = ex(params_base, fn)
+    got = run_cli(params_base, pset, [path], "--strategy=nop", *flags)
+    want = run_oracle(params_base, pset, path, gp.example_lines(fn), strategy="nop", **kw)
+    assert got == want
+
+
+def test_species_pruned_alignment_with_foreign_species_aborts(params_base):
+    path = ex(params_base, "ALDH2.exon5.fa")
+    got = run_cli(params_base, "29mammals", [path], "--strategy=nop", "--species=Human,Mouse", expect_rc=255)
+    want = run_oracle(params_base, "29mammals", path, gp.example_lines("ALDH2.exon5.fa"), strategy="nop", species=["Human", "Mouse"])
+    assert got == want and "\tabort\t" in got[0] and "parameters not available for species" in got[0]
+
+
+def test_error_tiers(params_base, tmp_path):
+    def write(name, text):
+        p = tmp_path / name
+        p.write_text(text)
+        return str(p)
+
+    cases = [
+        write("gapref.fa", ">dmel\nATG---GGG\n>dana\nATGCCCGGG\n"),          # reference gapped -> abort
+        write("badchar.fa", ">dmel\nATGRCCGGG\n>dana\nATGCCCGGG\n"),        # not ACGTNacgtn- -> abort (revcomp)
+        write("ragged.fa", ">dmel\nATGCCCGGG\n>dana\nATGCCC\n"),            # length mismatch -> abort
+        write("nohdr.fa", "ATGCCCGGG\n"),                                   # bad header -> abort
+        write("alien.fa", ">dmel\nATGCCCGGG\n>human\nATGCCCGGG\n"),         # species not in tree -> abort
+    ]
+    for path in cases:
+        got = run_cli(params_base, "12flies", [path], "--strategy=nop", expect_rc=255)
+        want = run_oracle(params_base, "12flies", path, open(path).read().split("\n")[:-1], strategy="nop")
+        assert got == want, (got, want)
+        assert got[0].split("\t")[1] == "abort"
+    # no ORFs -> per-alignment failure, exit code 0, processing continues with the next file
+    short = write("short.fa", ">dmel\nCCCGGGAAATAA\n>dana\nCCCGGGAAATAA\n")
+    ok = write("ok.fa", ">dmel\nATGCCCGGGAAACCC\n>dana\nATGCCCGGGAAACCC\n")
+    got = run_cli(params_base, "12flies", [short, ok], "--strategy=nop", "--orf=ATGStop", "--frames=3", "--minCodons=2")
+    assert got[0] == short + '\tfailure\tFailure("no sufficiently long ORFs found")'
+    assert got[1].startswith(ok + "\tfailure") or got[1].startswith(ok + "\tmax_score")
+    # a missing file aborts after the earlier alignments were reported
+    got = run_cli(params_base, "12flies", [ok, str(tmp_path / "missing.fa")], "--strategy=nop", expect_rc=255)
+    assert got[0].startswith(ok + "\tscore(decibans)\t0.0000") and "\tabort\tSys_error" in got[1]
+    # u -> t, lower case, stdin, --files
+    got = run_cli(params_base, "12flies", [], "--strategy=nop", "--dna", stdin=">dmel\nauggcc\n>dana\nAUGGCC\n")
+    assert got == ["(STDIN)\tscore(decibans)\t0.0000\tatggcc"]
+    lst = write("list.txt", ok + "\n" + ok + "\n")
+    got = run_cli(params_base, "12flies", [lst], "--strategy=nop", "--files")
+    assert len(got) == 2 and all(l.startswith(ok) for l in got)
+
+
+def test_usage_and_missing_base(params_base):
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 255 and "usage" in r.stderr
+    env = {k: v for k, v in os.environ.items() if k != "PHYLOCSF_BASE"}
+    r = subprocess.run([CLI, "12flies", "--strategy=nop"], env=env, input="", capture_output=True, text=True)
+    assert r.returncode == 2 and "PHYLOCSF_BASE" in r.stderr
+    # a path-like parameter set needs no PHYLOCSF_BASE (src/PhyloCSF.ml:409-419)
+    prefix = os.path.join(params_base, "PhyloCSF_Parameters", "12flies")
+    r = subprocess.run([CLI, prefix, "--strategy=nop"], env=env, input=">dmel\nATGGCC\n>dana\nATGGCC\n", capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "(STDIN)\tscore(decibans)\t0.0000\n"
+
+
+# ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_reference_goldens_through_the_cli(params_base):
+    """src/test.ml:27-59, the reference's own end-to-end tests (default strategy mle)."""
+    ans = run_cli(params_base, "12flies", [ex(params_base, "tal-AA.fa")], "--ancComp")[0].split("\t")
+    assert ans[1] == "score(decibans)" and 297.62 < float(ans[2]) < 297.63 and 48.25 < float(ans[3]) < 48.26
+    ans = run_cli(params_base, "29mammals", [ex(params_base, "ALDH2.exon5.fa")], "--ancComp")[0].split("\t")
+    assert ans[1] == "score(decibans)" and -178.93 < float(ans[2]) < -178.92 and -38.29 < float(ans[3]) < -38.28
+    ans = run_cli(params_base, "29mammals", [ex(params_base, "ALDH2.exon5.fa")], "--frames=6", "-p", "8")[0].split("\t")
+    assert ans[1] == "max_score(decibans)" and 218.26 < float(ans[2]) < 218.27 and ans[3:6] == ["1", "111", "+"]
+    ans = run_cli(params_base, "29mammals", [ex(params_base, "Aldh2.mRNA.fa")], "--orf=ATGStop", "--frames=3", "--removeRefGaps", "--aa")[0].split("\t")
+    assert ans[1] == "max_score(decibans)" and 2013.92 < float(ans[2]) < 2013.93 and ans[3:5] == ["343", "1899"]
+    assert ans[5].startswith("MLRAALTTVRRGPRLSRLLSAAA")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pset,fn,flags,kw", [
+    ("12flies", "tal-AA.fa", ["--strategy=fixed", "--ancComp", "--debug"], dict(strategy="fixed", anc_comp=True, debug=True)),
+    ("29mammals", "ALDH2.exon5.fa", ["--strategy=fixed", "--frames=6", "--allScores", "--ancComp", "--bls"],
+     dict(strategy="fixed", frames=6, all_scores=True, anc_comp=True, bls=True)),
+    ("29mammals", "ALDH2.exon5.fa", ["--strategy=mle", "--frames=3", "--allScores", "--ancComp", "--debug"],
+     dict(strategy="mle", frames=3, all_scores=True, anc_comp=True, debug=True)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--strategy=fixed", "--orf=ATGStop", "--frames=3", "--removeRefGaps", "--allScores"],
+     dict(strategy="fixed", orf="ATGStop", frames=3, remove_ref_gaps=True, all_scores=True)),
+    ("12flies", "tal-AA.fa", ["--strategy=omega", "--frames=3", "--allScores", "--debug"], dict(strategy="omega", frames=3, all_scores=True, debug=True)),
+])
+def test_scores_match_oracle_lines(params_base, pset, fn, flags, kw):
+    path = ex(params_base, fn)
+    got = run_cli(params_base, pset, [path], *flags)
+    want = run_oracle(params_base, pset, path, gp.example_lines(fn), **kw)
+    same_lines(got, want)
+
+
+@pytest.mark.gpu
+def test_many_alignments_one_batch_keep_order(params_base, tmp_path):
+    """Several alignments are staged as one GPU batch; output order and values equal one-by-one runs."""
+    files = [ex(params_base, "ALDH2.exon5.fa")] * 3
+    got = run_cli(params_base, "29mammals", files, "--strategy=fixed", "--frames=3")
+    one = run_cli(params_base, "29mammals", files[:1], "--strategy=fixed", "--frames=3")
+    assert got == one * 3
