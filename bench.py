@@ -298,9 +298,9 @@ def main():
         peak, peak_note = dmma_peak_tflops()
         k_ms = float(np.mean(prune_ms))
         achieved = FLOP_PER_COLUMN * total_cols / (k_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = None  # dram__bytes_read+write of one launch: ncu-measured bytes per codon column x columns
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "prune_kernel_traffic.json")))["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "prune_kernel_traffic.json")))["dram_bytes_per_codon_column"] * total_cols
         except Exception:
             pass
         line = {
