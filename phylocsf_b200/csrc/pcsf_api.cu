@@ -280,12 +280,11 @@ int pt_build_jobs(pcsf_ctx* ctx, const std::vector<PtJob>& jobs, DevBuf& tables,
     CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs.data(), sizeof(PtJob) * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(d_status.p, 0, sizeof(int32_t) * n, ctx->stream));
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-    for (int64_t s0 = 0; s0 < n; s0 += 32768) {  // gridDim.y limit
-        const int ns = (int)std::min<int64_t>(32768, n - s0);
-        dim3 grid(ctx->n_branches, ns);
-        pt_build_kernel<<<grid, 256, 0, ctx->stream>>>((const PtJob*)ctx->d_jobs.p + s0, ctx->d_branch_len, ctx->n_leaves,
-                                                       (double*)tables.p + (size_t)s0 * ctx->n_branches * PT_SLOT,
-                                                       (int32_t*)d_status.p + s0, 1e-6);
+    {
+        const long long n_items = (long long)n * ctx->n_branches;
+        const int grid = (int)std::min<long long>(n_items, 2LL * ctx->num_sms);
+        pt_build_kernel<<<grid, 256, 0, ctx->stream>>>((const PtJob*)ctx->d_jobs.p, n_items, ctx->d_branch_len, ctx->n_branches,
+                                                       ctx->n_leaves, (double*)tables.p, (int32_t*)d_status.p, 1e-6);
         CU(cudaGetLastError());
         ctx->launches++;
     }

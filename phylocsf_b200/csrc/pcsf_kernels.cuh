@@ -103,93 +103,105 @@ __host__ __device__ __forceinline__ int frag_index(int a, int b) {
 // =================================================================================================
 // K1: P(t) build
 // =================================================================================================
-// grid = (n_branches, nscales), block = 256. One CTA builds one 64x64 P(t):
-//   warp w computes rows 8w..8w+7 with 128 DMMAs (A = S rows, B = exp(lambda_k t) * Sinv[k][.]),
-//   then 64 threads apply the reference's row fix-ups sequentially (bit-faithful order), then the
-//   CTA writes the table in the layout the pruning kernel wants: leaves get the transposed gather
-//   table PT[code][a] (+ row 64 = row sums, the `Marginalize message); internal edges get the
-//   fragment-ordered image.
+// Persistent CTAs (two per SM), each owning a contiguous run of (job, branch) items; a job = one
+// diagonalised model at one tree scale. Per model the CTA keeps S as register-resident A fragments and
+// S^-1 as a fragment-ordered image in shared memory; per item it
+//   - evaluates e_k = exp(lambda_k * scale * branch_len) (64 threads),
+//   - warp w computes rows 8w..8w+7 of (S diag(e)) S^-1 with 128 DMMAs,
+//   - applies the reference's row fix-ups (lib/CamlPaml/Q.ml:226-247: clamp (-tol,0) to 0, row sum within
+//     tol of 1, diagonal := 1 - sum of the off-diagonal entries) on the accumulators - a row lives in the
+//     four lanes of a quad, so two shuffles finish each sum -,
+//   - stores the slot in the layout the pruning kernel consumes: leaves get the transposed gather table
+//     PT[code][a] (+ row 64 = row sums, the `Marginalize message), internal edges the fragment-ordered image.
+// Versus the reference's evaluation order, diag(e) is folded into S instead of S^-1 and the row sums are
+// tree-shaped; both move entries by ~1e-16 (test bar: 2e-13 absolute).
 struct PtJob {               // one P set to build: a diagonalised model at one tree scale
     const double* params;   // S | Sinv | lambda | prior | logprior (pcsf_api.cu: Model)
     double scale;
 };
-__global__ void __launch_bounds__(256) pt_build_kernel(const PtJob* __restrict__ jobs,
-                                                       const double* __restrict__ branch_len, int n_leaves,
-                                                       double* __restrict__ tables, int32_t* __restrict__ status,
-                                                       double tol) {
-    const PtJob job = jobs[blockIdx.y];
-    const double* __restrict__ S = job.params;
-    const double* __restrict__ Sinv = job.params + 4096;
-    const double* __restrict__ lambda = job.params + 8192;
-    __shared__ double Psm[64][65];
-    __shared__ double e_s[64];
-    __shared__ double rowsum_s[64];
-    const int br = blockIdx.x, sc = blockIdx.y;
-    const int n_branches = gridDim.x;
+__global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restrict__ jobs, long long n_items,
+                                                          const double* __restrict__ branch_len, int n_branches,
+                                                          int n_leaves, double* __restrict__ tables,
+                                                          int32_t* __restrict__ status, double tol) {
+    __shared__ double Sinv_s[4096];  // fragment-ordered: [(j*16+s)*32 + lane] = Sinv[4s+t][8j+g]
+    __shared__ double e_s[2][64];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const double tt = job.scale * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
-    if (tid < 64) e_s[tid] = exp(tt * lambda[tid]);  // Q.ml:216-217
-    __syncthreads();
-    double acc[8][2];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
-#pragma unroll 4
-    for (int s = 0; s < 16; s++) {
-        const int k = 4 * s + t;
-        const double a = S[(8 * w + g) * 64 + k];
-        const double ek = e_s[k];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double b = Sinv[k * 64 + 8 * j + g] * ek;  // diagm: row k of S' scaled, Q.ml:61-64
-            dmma(acc[j][0], acc[j][1], a, b);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        Psm[8 * w + g][8 * j + 2 * t] = acc[j][0];
-        Psm[8 * w + g][8 * j + 2 * t + 1] = acc[j][1];
-    }
-    __syncthreads();
-    if (tid < 64) {  // Q.ml:226-247, one row per thread, j ascending
-        const int i = tid;
-        int st = (tt < 0.0) ? 1 : 0;
-        double tot = 0.0, smii = 1.0;
-        for (int j = 0; j < 64; j++) {
-            double v = Psm[i][j];
-            tot += v;
-            if (v < 0.0) {
-                if (fabs(v) > tol) st |= 2;
-                v = 0.0;
-                Psm[i][j] = 0.0;
+    const long long per = (n_items + gridDim.x - 1) / gridDim.x;
+    const long long lo = per * blockIdx.x, hi = min(n_items, lo + per);
+    const double* cur_params = nullptr;
+    double afrag[16];  // S[8w+g][4s+t]
+    int buf = 0;
+    for (long long item = lo; item < hi; item++, buf ^= 1) {
+        const long long job_i = item / n_branches;
+        const int br = (int)(item - job_i * n_branches);
+        const PtJob job = jobs[job_i];
+        const double tt = job.scale * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
+        if (tid < 64) e_s[buf][tid] = exp(tt * job.params[8192 + tid]);  // Q.ml:216-217
+        if (job.params != cur_params) {  // uniform across the CTA
+            __syncthreads();             // everybody is done reading the previous model's image
+            const double* Sinv = job.params + 4096;
+            for (int idx = tid; idx < 4096; idx += 256) {
+                const int l = idx & 31, s = (idx >> 5) & 15, j = idx >> 9;
+                Sinv_s[idx] = Sinv[(4 * s + (l & 3)) * 64 + 8 * j + (l >> 2)];
             }
-            if (i != j) smii -= v;
+#pragma unroll
+            for (int s = 0; s < 16; s++) afrag[s] = job.params[(8 * w + g) * 64 + 4 * s + t];
+            cur_params = job.params;
         }
+        __syncthreads();  // e_s[buf] (and the image) visible; e_s[buf^1] is free for the next item
+        double acc[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+            const double a = afrag[s] * e_s[buf][4 * s + t];
+#pragma unroll
+            for (int j = 0; j < 8; j++) dmma(acc[j][0], acc[j][1], a, Sinv_s[(j * 16 + s) * 32 + lane]);
+        }
+        // ---- fix-ups on row i = 8w+g, whose 64 entries sit in the quad's accumulators ----
+        const int i = 8 * w + g;
+        int st = (tt < 0.0) ? 1 : 0;
+        double tot = 0.0, off = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                double v = acc[j][e];
+                tot += v;
+                if (v < 0.0) {
+                    if (fabs(v) > tol) st |= 2;
+                    v = 0.0;
+                    acc[j][e] = 0.0;
+                }
+                if (8 * j + 2 * t + e != i) off += v;
+            }
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        off += __shfl_xor_sync(0xffffffffu, off, 1);
+        off += __shfl_xor_sync(0xffffffffu, off, 2);
+        const double smii = 1.0 - off;
         if (fabs(tot - 1.0) > tol) st |= 4;
         if (!(smii <= 1.0 && smii > 0.0)) st |= 8;
-        Psm[i][i] = smii;
-        double rs = 0.0;  // ddot(row, ones): the `Marginalize leaf message, PhyloLik.ml:90 with raw_marg
-        for (int j = 0; j < 64; j++) rs += Psm[i][j];
-        rowsum_s[i] = rs;
-        if (st) atomicOr(&status[sc], st);
-    }
-    __syncthreads();
-    double* out = tables + ((size_t)sc * n_branches + br) * PT_SLOT;
-    if (br < n_leaves) {
-        for (int idx = tid; idx < 64 * 64; idx += 256) {
-            const int b = idx >> 6, a = idx & 63;
-            out[idx] = Psm[a][b];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+                if (8 * j + 2 * t + e == i) acc[j][e] = smii;
+        if (st) atomicOr(&status[job_i], st);
+        double* out = tables + (size_t)item * PT_SLOT;
+        if (br < n_leaves) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) out[(8 * j + 2 * t + e) * 64 + i] = acc[j][e];
+            if (t == 0) out[4096 + i] = off + smii;  // ddot(row, ones): the `Marginalize leaf message
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) out[((w * 16 + 2 * j + e) * 32) + lane] = acc[j][e];
         }
-        if (tid < 64) out[64 * 64 + tid] = rowsum_s[tid];
-    } else {
-        for (int idx = tid; idx < 64 * 64; idx += 256) {
-            // idx = ((j*16+s)*32 + 4g+t)
-            const int l = idx & 31, s = (idx >> 5) & 15, j = idx >> 9;
-            const int gg = l >> 2, tq = l & 3;
-            const int a = 8 * j + gg, b = 8 * (s >> 1) + 2 * tq + (s & 1);
-            out[idx] = Psm[a][b];
-        }
-        if (tid < 64) out[64 * 64 + tid] = rowsum_s[tid];
     }
 }
 
