@@ -169,3 +169,26 @@ def test_many_alignments_one_batch_keep_order(params_base, tmp_path):
     got = run_cli(params_base, "29mammals", files, "--strategy=fixed", "--frames=3")
     one = run_cli(params_base, "29mammals", files[:1], "--strategy=fixed", "--frames=3")
     assert got == one * 3
+
+
+@pytest.mark.gpu
+def test_omega_100vertebrates_species_subset(params_base, tmp_path):
+    """BASELINE.json configs[3] in miniature: omega strategy, --allScores, 3 frames, on a simulated
+    exon under the 100vertebrates tree pruned with --species (keeps the CPU oracle affordable)."""
+    import numpy as np
+
+    sp = ["Human", "Mouse", "Dog", "Cow", "Elephant", "Opossum", "Chicken", "Lizard", "Zebrafish", "Lamprey"]
+    ops = o.load_paramset(os.path.join(params_base, "PhyloCSF_Parameters", "100vertebrates"),
+                                                    o.Options(strategy="fixed", species=sp))
+    labels = ops.tree.labels[: ops.tree.n_leaves]
+    assert len(labels) >= 6, labels
+    rng = np.random.default_rng(3)
+    codes = o.simulate_columns(ops.model.coding_model.model(1.0), 40, rng)
+    rows = o.codes_to_alignment(codes)
+    path = tmp_path / "sim.fa"
+    path.write_text("".join(">%s\n%s\n" % (l, r) for l, r in zip(labels, rows)))
+    flags = ["--strategy=omega", "--frames=3", "--allScores", "--species=" + ",".join(sp)]
+    got = run_cli(params_base, "100vertebrates", [str(path)], *flags)
+    want = run_oracle(params_base, "100vertebrates", str(path), path.read_text().split("\n")[:-1], strategy="omega", frames=3,
+                      all_scores=True, species=sp)
+    same_lines(got, want)

@@ -195,3 +195,74 @@ def test_mle_examples(params_base):
         anc0 = H.DB * (res[0][2][0] - res[1][2][0])
         assert window[0] < score0 < window[1] and anc_window[0] < anc0 < anc_window[1]
         ctx.close()
+
+
+def test_mle_simulated_120mammals(params_base):
+    """BASELINE.json configs[2] in miniature: 120mammals, mle, alignments simulated at different tree
+    scales; batched device Brent vs the oracle's, per region and model."""
+    ps = H.oracle_paramset(params_base, "120mammals")
+    rng = np.random.default_rng(11)
+    regs = []
+    for i, rho in enumerate((0.4, 1.0, 2.2)):
+        inst = ps.model.coding_model if i % 2 == 0 else ps.model.noncoding_model
+        regs.append(o.simulate_columns(inst.model(rho), 24 + 3 * i, rng))
+    ctx = H.make_context(ps)
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    res = [ctx.maximize_lpr(m) for m in (0, 1)]
+    ora = _oracle_mle(ps, regs)
+    for r in range(len(regs)):
+        for m in (0, 1):
+            rho, lpr, elpr, st, ne = (a[r] for a in res[m])
+            ox, olp, oel, oit, otries = ora[r][m]
+            assert (st & ~64) == 0
+            assert abs(rho - ox) < 1e-8 * max(1.0, ox)
+            assert abs(H.DB * (lpr - olp)) < 1e-6 and abs(H.DB * (elpr - oel)) < 1e-6
+            assert ne == 3 + otries + 3 + 1 + oit + 1
+    ctx.close()
+
+
+def test_mle_boundary_and_flat_regions(params_base):
+    """Regions whose likelihood is monotone in rho: identical sequences (best rho -> lower bound) make
+    find_init exhaust its 250 random tries and return the boundary (Fit.ml:42-47); the device driver
+    must take the same path as the oracle (same OCaml Random stream, same number of evaluations)."""
+    ps = H.oracle_paramset(params_base, "12flies")
+    n = ps.tree.n_leaves
+    same = np.tile(np.array([[14], [35], [7], [60], [22], [9]], dtype=np.uint8), (1, n))  # every species identical
+    regs = [same]
+    ctx = H.make_context(ps)
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    res = [ctx.maximize_lpr(m) for m in (0, 1)]
+    ora = _oracle_mle(ps, regs)
+    for m in (0, 1):
+        rho, lpr, elpr, st, ne = (a[0] for a in res[m])
+        ox, olp, oel, oit, otries = ora[0][m]
+        assert otries == 250 and (st & 64) and (st & ~64) == 0
+        assert rho == ox == 0.01
+        assert abs(H.DB * (lpr - olp)) < 1e-6
+        assert ne == 3 + 250 + 1
+    ctx.close()
+
+
+def test_pairs_api_matches_per_model_api(params_base):
+    """pcsf_models_set / pcsf_pt_build_pairs / pcsf_lpr_pairs (the omega strategy's batched form) give
+    bit-identical numbers to pcsf_model_set / pcsf_pt_build / pcsf_lpr."""
+    ps = H.oracle_paramset(params_base, "29mammals")
+    rng = np.random.default_rng(5)
+    regs = [o.simulate_columns(ps.model.coding_model.model(1.0), n, rng) for n in (20, 33, 7)]
+    ctx = H.make_context(ps)
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    scales = [0.5, 1.0, 1.7]
+    ctx.pt_build(0, scales)
+    ctx.pt_build(1, scales)
+    a = ctx.lpr([0, 1, 0], [0, 1, 2], [0, 1, 2])
+    qs = [ps.model.coding_model.q, ps.model.noncoding_model.q]
+    ctx.models_set(4, np.stack([q.S for q in qs]), np.stack([q.Sinv for q in qs]), np.stack([q.lam for q in qs]),
+                   np.stack([q.equilibrium() for q in qs]))
+    st = ctx.pt_build_pairs([4, 5, 4], [0.5, 1.0, 1.7])
+    assert (st == 0).all()
+    b = ctx.lpr_pairs([0, 1, 2], [0, 1, 2])
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    ctx.close()
