@@ -135,6 +135,15 @@ int pcsf_lpr(pcsf_ctx *ctx, int64_t n_evals, const int32_t *eval_model, const in
  */
 int pcsf_models_set(pcsf_ctx *ctx, int first_id, int n, const double *S, const double *Sinv, const double *lambda,
                     const double *prior);
+/*
+ * K5. The omega model's Q assembly and diagonalisation on the device: model first_id+i is built from
+ * q_settings[12*i .. 12*i+11] = kappa, omega, sigma, 9 x F3x4 ratios (src/OmegaModel.ml:21-80, then
+ * Q.Diag.of_Q + equilibrium, lib/CamlPaml/Q.ml:124-177). Same slot/lifetime rules as pcsf_models_set.
+ * status bits: 128 = Q scale non-positive (PhyloModel.ml:99-100), 256 = no zero eigenvalue (Q.ml:168-169).
+ */
+int pcsf_omega_models_set(pcsf_ctx *ctx, int first_id, int n, const double *q_settings, int32_t *status);
+/* Read a model slot back (S, Sinv 64x64; lambda, prior 64); any output may be NULL. For tests. */
+int pcsf_model_get(pcsf_ctx *ctx, int model_id, double *S, double *Sinv, double *lambda, double *prior);
 int pcsf_pt_build_pairs(pcsf_ctx *ctx, int64_t npairs, const int32_t *pair_model, const double *pair_scale,
                         int32_t *status);
 int pcsf_lpr_pairs(pcsf_ctx *ctx, int64_t n_evals, const int64_t *eval_pair, const int64_t *eval_region,

@@ -120,6 +120,17 @@ class Context:
         assert S.shape == (n, 64, 64) and Sinv.shape == (n, 64, 64) and lam.shape == (n, 64) and prior.shape == (n, 64)
         self._check(self._L.pcsf_models_set(self._h, first_id, n, N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior)))
 
+    def omega_models_set(self, first_id, q_settings, check=True):
+        qs = _f64(q_settings).reshape(-1, 12)
+        st = np.zeros(qs.shape[0], dtype=np.int32)
+        self._check(self._L.pcsf_omega_models_set(self._h, first_id, qs.shape[0], N.ptr(qs), N.ptr(st)), ok_numeric=not check)
+        return st
+
+    def model_get(self, model_id):
+        S, Sinv, lam, prior = np.empty((64, 64)), np.empty((64, 64)), np.empty(64), np.empty(64)
+        self._check(self._L.pcsf_model_get(self._h, model_id, N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior)))
+        return {"S": S, "Sinv": Sinv, "lam": lam, "prior": prior}
+
     def pt_build_pairs(self, pair_model, pair_scale, check=True):
         pm = np.ascontiguousarray(pair_model, dtype=np.int32)
         sc = _f64(pair_scale)

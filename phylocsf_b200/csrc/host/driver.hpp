@@ -240,31 +240,17 @@ class Driver {
         return std::log(p);
     }
 
-    // Diagonalise Q(qs) for every listed region on host threads and install them as models slot = index.
+    // Assemble and diagonalise Q(qs) for every listed region on the device (K5) as models slot = index.
     void omega_install_models(const std::vector<OmegaInst>& inst, const std::vector<int64_t>& which, std::vector<std::string>& exn) {
         const size_t n = which.size();
-        std::vector<double> S(n * 4096), Sinv(n * 4096), lam(n * 64), prior(n * 64);
-        auto work = [&](size_t a, size_t b) {
-            for (size_t i = a; i < b; i++) {
-                try {
-                    std::vector<double> pi;
-                    const std::vector<double> q = omega_q(inst[which[i]].qs, &pi);
-                    QDiag d = QDiag::of_reversible_Q(q, pi);
-                    std::memcpy(&S[i * 4096], d.S.data(), 4096 * 8);
-                    std::memcpy(&Sinv[i * 4096], d.Sinv.data(), 4096 * 8);
-                    std::memcpy(&lam[i * 64], d.lam.data(), 64 * 8);
-                    std::memcpy(&prior[i * 64], d.pi_eq.data(), 64 * 8);
-                } catch (const std::exception& e) {
-                    exn[which[i]] = e.what();
-                    for (int k = 0; k < 64; k++) { prior[i * 64 + k] = 1.0 / 64; S[i * 4096 + 65 * k] = Sinv[i * 4096 + 65 * k] = 1.0; }
-                }
-            }
-        };
-        const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)n));
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
-        for (auto& t : th) t.join();
-        check(pcsf_models_set(ctx, 0, (int)n, S.data(), Sinv.data(), lam.data(), prior.data()));
+        std::vector<double> qs(n * 12);
+        for (size_t i = 0; i < n; i++) std::memcpy(&qs[i * 12], inst[which[i]].qs, 12 * sizeof(double));
+        std::vector<int32_t> st(n, 0);
+        check(pcsf_omega_models_set(ctx, 0, (int)n, qs.data(), st.data()));
+        for (size_t i = 0; i < n; i++) {
+            if (st[i] & 128) exn[which[i]] = "Failure(\"CamlPaml.P14n.instantiate_q: Q scale evaluated to a non-positive value\")";
+            else if (st[i]) exn[which[i]] = "Failure(\"CamlPaml.Q.equilibrium: smallest-magnitude eigenvalue is unacceptably large; check rate matrix validity or increase tol\")";
+        }
     }
 
     // One coordinate of kr_map (OmegaModel.ml:171-188) for all regions at once: maximize_lpr over rho

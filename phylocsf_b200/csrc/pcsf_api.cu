@@ -64,7 +64,7 @@ struct pcsf_ctx {
     DevBuf d_region_off, d_codes, d_nt, d_aln_off, d_aln_len;
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
-    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status;
+    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs;
     std::vector<int32_t> pair_model, pair_status;  // P sets built by pcsf_pt_build_pairs
     int last_all_models = 0;
     // timing
@@ -391,7 +391,7 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
                       &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
-                      &ctx->d_pair_status};
+                      &ctx->d_pair_status, &ctx->d_qs};
     for (auto* b : bufs) fr(*b);
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
@@ -716,6 +716,67 @@ int pcsf_models_set(pcsf_ctx* ctx, int first_id, int n, const double* S, const d
         m.nscales = 0;
     }
     ctx->pair_model.clear();
+    return PCSF_OK;
+}
+
+int pcsf_omega_models_set(pcsf_ctx* ctx, int first_id, int n, const double* q_settings, int32_t* status) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (first_id < 0 || n < 1 || first_id + n > (1 << 22) || !q_settings)
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_omega_models_set: bad argument");
+    for (int i = 0; i < n * 12; i++)
+        if (!(q_settings[i] >= 0.0)) return fail(ctx, PCSF_ERR_INVALID_ARG, "CamlPaml.P14n.instantiate_q: domain violation");  // Fit.NonNeg
+    CU(cudaSetDevice(ctx->device));
+    const size_t per = 8192 + 192;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& m : ctx->models)
+        if (!m.owns_params) { m.set = false; m.d_params = nullptr; m.nscales = 0; }
+    TRY(reserve(ctx, ctx->d_batch_params, per * 8 * (size_t)n));
+    TRY(reserve(ctx, ctx->d_qs, sizeof(double) * 12 * (size_t)n));
+    TRY(reserve(ctx, ctx->d_pair_status, sizeof(int32_t) * (size_t)n));
+    CU(cudaMemcpyAsync(ctx->d_qs.p, q_settings, sizeof(double) * 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_pair_status.p, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
+    const int smem = (2 * 64 * 65 + 64 + 64 + 32 + 32) * 8;
+    CU(cudaFuncSetAttribute(omega_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    omega_eig_kernel<<<n, EIG_THREADS, smem, ctx->stream>>>((const double*)ctx->d_qs.p, (double*)ctx->d_batch_params.p,
+                                                            (int32_t*)ctx->d_pair_status.p);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+    std::vector<int32_t> st(n);
+    CU(cudaMemcpyAsync(st.data(), ctx->d_pair_status.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
+    ctx->ms[2] = t;
+    if ((int)ctx->models.size() < first_id + n) ctx->models.resize(first_id + n);
+    bool bad = false;
+    for (int i = 0; i < n; i++) {
+        Model& m = ctx->models[first_id + i];
+        if (m.d_params && m.owns_params) CU(cudaFree(m.d_params));
+        m.owns_params = false;
+        m.d_params = (double*)ctx->d_batch_params.p + per * i;
+        m.set = true;  // a failed model keeps its slot (contents undefined); the caller sees its status
+        m.nscales = 0;
+        if (status) status[i] = st[i];
+        bad |= st[i] != 0;
+    }
+    ctx->pair_model.clear();
+    if (bad) return fail(ctx, PCSF_ERR_NUMERIC, "omega rate matrix could not be scaled or diagonalised for at least one model (see status)");
+    return PCSF_OK;
+}
+
+int pcsf_model_get(pcsf_ctx* ctx, int model_id, double* S, double* Sinv, double* lambda, double* prior) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set)
+        return fail(ctx, PCSF_ERR_STATE, "pcsf_model_get: model not set");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double* d = ctx->models[model_id].d_params;
+    if (S) CU(cudaMemcpy(S, d, 4096 * 8, cudaMemcpyDeviceToHost));
+    if (Sinv) CU(cudaMemcpy(Sinv, d + 4096, 4096 * 8, cudaMemcpyDeviceToHost));
+    if (lambda) CU(cudaMemcpy(lambda, d + 8192, 64 * 8, cudaMemcpyDeviceToHost));
+    if (prior) CU(cudaMemcpy(prior, d + 8192 + 64, 64 * 8, cudaMemcpyDeviceToHost));
     return PCSF_OK;
 }
 

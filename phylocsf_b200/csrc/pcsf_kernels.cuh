@@ -602,6 +602,189 @@ __global__ void make_segments_kernel(const int64_t* __restrict__ region_off, int
 }
 
 // =================================================================================================
+// K5: omega-model rate matrices and their diagonalisation, one CTA per (region, candidate)
+// =================================================================================================
+// Replaces, for the omega strategy, what the reference does on the host for every kappa candidate of
+// every region (src/OmegaModel.ml:166-170 -> PhyloModel.P14n.update ~q_settings -> Q.Diag.of_Q):
+//   1. assemble Q(kappa, omega, sigma, F3x4) in the evaluation order of the reference's Expr trees
+//      (OmegaModel.ml:21-80; __d*_rn intrinsics keep nvcc from contracting into FMAs, so Q is
+//      bit-identical to the host assembly),
+//   2. symmetrise with the codon frequencies (the model is reversible) and run a parallel-ordered
+//      cyclic Jacobi (round-robin pairing, 32 disjoint rotations per round, 63 rounds per sweep),
+//   3. write S | S^-1 | lambda | equilibrium prior | log prior straight into the model block K1 reads.
+__device__ __forceinline__ bool omega_is_stop(int c) { return c == 48 || c == 50 || c == 56; }
+__constant__ char kOmegaAA[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
+
+constexpr int EIG_THREADS = 256;
+__global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __restrict__ qs_all, double* __restrict__ params_all,
+                                                               int32_t* __restrict__ status) {
+    extern __shared__ double esm[];
+    double* A = esm;              // 64 x 65 (padded)
+    double* V = esm + 64 * 65;    // 64 x 65
+    double* pi = V + 64 * 65;     // 64
+    double* sw = pi + 64;         // 64
+    double* rc = sw + 64;         // 32 cosines
+    double* rs = rc + 32;         // 32 sines
+    __shared__ int pp[32], pq[32];
+    __shared__ double red[EIG_THREADS / 32];
+    __shared__ double s_factor, s_off, s_diag;
+    const int tid = threadIdx.x;
+    const double* v = qs_all + (size_t)blockIdx.x * 12;
+    double* out = params_all + (size_t)blockIdx.x * (8192 + 192);
+    const double kappa = v[0], omega = v[1];
+    // ---- codon frequencies, OmegaModel.ml:24-42 ----
+    if (tid < 64) {
+        auto sc = [&](int i1, int i2, int i3) {
+            const double f1 = __ddiv_rn(i1 == 3 ? 1.0 : v[3 + i1], __dadd_rn(v[3], __dadd_rn(v[4], __dadd_rn(v[5], 1.0))));
+            const double f2 = __ddiv_rn(i2 == 3 ? 1.0 : v[6 + i2], __dadd_rn(v[6], __dadd_rn(v[7], __dadd_rn(v[8], 1.0))));
+            const double f3 = __ddiv_rn(i3 == 3 ? 1.0 : v[9 + i3], __dadd_rn(v[9], __dadd_rn(v[10], __dadd_rn(v[11], 1.0))));
+            return __dmul_rn(f1, __dmul_rn(f2, f3));
+        };
+        const double denom = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, v[2]), __dadd_rn(sc(3, 0, 0), __dadd_rn(sc(3, 0, 2), sc(3, 2, 0)))));
+        pi[tid] = __ddiv_rn(sc(tid >> 4, (tid >> 2) & 3, tid & 3), denom);
+    }
+    __syncthreads();
+    // ---- off-diagonal rates, OmegaModel.ml:44-72 ----
+    for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        const int ii[3] = {i >> 4, (i >> 2) & 3, i & 3}, jj[3] = {j >> 4, (j >> 2) & 3, j & 3};
+        int nd = 0, da = 0, dbb = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (ii[k] != jj[k]) { nd++; da = ii[k]; dbb = jj[k]; }
+        double q = 0.0;
+        if (nd == 1) {
+            const bool transition = (da == 0 && dbb == 2) || (da == 2 && dbb == 0) || (da == 1 && dbb == 3) || (da == 3 && dbb == 1);
+            const double kp = transition ? kappa : 1.0;
+            const double op = (!omega_is_stop(i) && !omega_is_stop(j) && kOmegaAA[i] != kOmegaAA[j]) ? omega : 1.0;
+            q = __dmul_rn(pi[j], __dmul_rn(kp, op));
+        }
+        A[i * 65 + j] = q;
+    }
+    __syncthreads();
+    // ---- diagonal and unit-rate scale, PhyloModel.ml:76-84,94-104 / OmegaModel.ml:76-80 ----
+    if (tid < 64) {
+        double tot = 0.0;
+        for (int j = 0; j < 64; j++)
+            if (j != tid) tot = __dadd_rn(A[tid * 65 + j], tot);
+        A[tid * 65 + tid] = __dsub_rn(0.0, tot);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double factor = 0.0;
+        for (int i = 0; i < 64; i++) factor = __dsub_rn(factor, __dmul_rn(pi[i], A[i * 65 + i]));
+        s_factor = factor;
+    }
+    __syncthreads();
+    const double factor = s_factor;
+    int st = 0;
+    if (!(factor > 0.0)) st |= 128;  // "Q scale evaluated to a non-positive value"
+    if (tid < 64) {
+        if (!(pi[tid] > 0.0)) st |= 128;
+        sw[tid] = sqrt(pi[tid]);
+    }
+    __syncthreads();
+    // ---- scaled Q, symmetrised: A = W^1/2 Q W^-1/2 ----
+    for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        V[i * 65 + j] = sw[i] * __ddiv_rn(A[i * 65 + j], factor) / sw[j];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+        const int i = idx >> 6, j = idx & 63;
+        A[i * 65 + j] = (i == j) ? V[i * 65 + i] : 0.5 * (V[i * 65 + j] + V[j * 65 + i]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 4096; idx += EIG_THREADS) V[(idx >> 6) * 65 + (idx & 63)] = ((idx >> 6) == (idx & 63)) ? 1.0 : 0.0;
+    __syncthreads();
+    // ---- parallel cyclic Jacobi ----
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double o2 = 0.0, d2 = 0.0;
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+            const int i = idx >> 6, j = idx & 63;
+            const double a = A[i * 65 + j];
+            if (i == j) d2 += a * a; else o2 += a * a;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) { o2 += __shfl_xor_sync(0xffffffffu, o2, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+        if ((tid & 31) == 0) red[tid >> 5] = o2;
+        __syncthreads();
+        if (tid == 0) { double t = 0; for (int k = 0; k < EIG_THREADS / 32; k++) t += red[k]; s_off = t; }
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = d2;
+        __syncthreads();
+        if (tid == 0) { double t = 0; for (int k = 0; k < EIG_THREADS / 32; k++) t += red[k]; s_diag = t; }
+        __syncthreads();
+        if (s_off <= 1e-34 * s_diag || s_off == 0.0) break;
+        for (int r = 0; r < 63; r++) {
+            if (tid < 32) {  // pairing of round r and its rotations
+                int a = tid == 0 ? 63 : (r + tid) % 63, b = tid == 0 ? r : (r - tid + 63) % 63;
+                const int p_ = a < b ? a : b, q_ = a < b ? b : a;
+                pp[tid] = p_;
+                pq[tid] = q_;
+                const double apq = A[p_ * 65 + q_], app = A[p_ * 65 + p_], aqq = A[q_ * 65 + q_];
+                double c = 1.0, s = 0.0;
+                if (apq != 0.0 && !(sweep > 4 && fabs(apq) <= 1e-20 * fabs(app) && fabs(apq) <= 1e-20 * fabs(aqq))) {
+                    const double theta = (aqq - app) / (2.0 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    c = 1.0 / sqrt(t * t + 1.0);
+                    s = t * c;
+                }
+                rc[tid] = c;
+                rs[tid] = s;
+            }
+            __syncthreads();
+            // columns: A <- A J, V <- V J   (pair k touches columns p,q of every row)
+            for (int idx = tid; idx < 2048; idx += EIG_THREADS) {
+                const int k = idx & 31, row = idx >> 5;
+                const int p_ = pp[k], q_ = pq[k];
+                const double c = rc[k], s = rs[k];
+                const double akp = A[row * 65 + p_], akq = A[row * 65 + q_];
+                A[row * 65 + p_] = c * akp - s * akq;
+                A[row * 65 + q_] = s * akp + c * akq;
+                const double vkp = V[row * 65 + p_], vkq = V[row * 65 + q_];
+                V[row * 65 + p_] = c * vkp - s * vkq;
+                V[row * 65 + q_] = s * vkp + c * vkq;
+            }
+            __syncthreads();
+            // rows: A <- J^T A
+            for (int idx = tid; idx < 2048; idx += EIG_THREADS) {
+                const int col = idx & 63, k = idx >> 6;
+                const int p_ = pp[k], q_ = pq[k];
+                const double c = rc[k], s = rs[k];
+                const double apk = A[p_ * 65 + col], aqk = A[q_ * 65 + col];
+                A[p_ * 65 + col] = c * apk - s * aqk;
+                A[q_ * 65 + col] = s * apk + c * aqk;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- outputs: S = W^-1/2 U, S^-1 = U^T W^1/2, lambda, equilibrium (Q.ml:153-177) ----
+    for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+        const int i = idx >> 6, k = idx & 63;
+        out[i * 64 + k] = V[i * 65 + k] / sw[i];
+        out[4096 + k * 64 + i] = V[i * 65 + k] * sw[i];
+    }
+    if (tid < 64) out[8192 + tid] = A[tid * 65 + tid];
+    __syncthreads();
+    if (tid == 0) {
+        int p_ = 0;
+        double best = INFINITY;
+        for (int i = 0; i < 64; i++)
+            if (fabs(A[i * 65 + i]) < best) { best = fabs(A[i * 65 + i]); p_ = i; }
+        if (best > 1e-6) st |= 256;  // "smallest-magnitude eigenvalue is unacceptably large"
+        double mass = 0.0;
+        for (int i = 0; i < 64; i++) mass += V[i * 65 + p_] * sw[i];
+        for (int i = 0; i < 64; i++) {
+            const double pr = V[i * 65 + p_] * sw[i] / mass;
+            out[8192 + 64 + i] = pr;
+            out[8192 + 128 + i] = log(pr);
+        }
+    }
+    if (st) atomicOr(&status[blockIdx.x], st);
+}
+
+// =================================================================================================
 // K0: pleaves on the device. One thread per (region column, leaf).
 // =================================================================================================
 __device__ __forceinline__ int nt_index(uint8_t c) {

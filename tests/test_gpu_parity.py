@@ -266,3 +266,38 @@ def test_pairs_api_matches_per_model_api(params_base):
     b = ctx.lpr_pairs([0, 1, 2], [0, 1, 2])
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
     ctx.close()
+
+
+def test_device_omega_eigen_matches_host(params_base):
+    """K5 (pcsf_omega_models_set: Q assembly + batched Jacobi on the device) against the host layer and
+    the oracle: S diag(lambda) S^-1 reproduces the oracle's Q, the prior is the equilibrium, and P(t)
+    built from the device model equals the oracle's P(t)."""
+    from phylocsf_b200 import host
+
+    ps = H.oracle_paramset(params_base, "12flies")
+    ctx = H.make_context(ps)
+    rng = np.random.default_rng(2)
+    qs = np.array([[2.5, 1.0, 1.0] + [1.0] * 9,
+                   [1.7, 0.2, 0.01, 1.3, 0.8, 1.1, 0.9, 1.2, 0.7, 1.05, 0.95, 1.4],
+                   [9.9, 3.0, 0.5] + list(rng.uniform(0.3, 3.0, 9))])
+    st = ctx.omega_models_set(3, qs)
+    assert (st == 0).all()
+    for i, v in enumerate(qs):
+        Qo = o.omega_q(list(v))
+        qd = o.QDiag(Qo)
+        d = ctx.model_get(3 + i)
+        np.testing.assert_allclose(d["S"] @ np.diag(d["lam"]) @ d["Sinv"], Qo, atol=5e-13)
+        np.testing.assert_allclose(d["S"] @ d["Sinv"], np.eye(64), atol=1e-12)
+        np.testing.assert_allclose(np.sort(d["lam"]), np.sort(qd.lam), atol=1e-12)
+        np.testing.assert_allclose(d["prior"], qd.equilibrium(), atol=1e-14)
+        hq, hpi = host.omega_q(v)
+        assert (hq == Qo).all()
+    ctx.pt_build_pairs([3, 4, 5], [1.0, 0.4, 2.0])
+    regs, _ = H.example_codes(ps, "tal-AA.fa")
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    lpr, _, st = ctx.lpr_pairs([0, 1, 2], [0, 0, 0])
+    for i, (v, rho) in enumerate(zip(qs, (1.0, 0.4, 2.0))):
+        inst = o.OmegaInstance(ps.tree, list(v), rho)
+        assert abs(H.DB * (lpr[i] - o.omega_lpr_leaves(inst, regs[0]))) < 1e-6
+    ctx.close()
