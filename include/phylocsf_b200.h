@@ -59,6 +59,16 @@ const char *pcsf_last_error(const pcsf_ctx *ctx);
 int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
 
 /*
+ * Options (no reference analogue). PCSF_OPT_RESCALE = 1: rescue per-column partials from underflow by
+ * exact powers of two and add the exponents back into log z. The reference never rescales
+ * (lib/CamlPaml/PhyloLik.ml:87-92) and returns log 0 = -inf for such columns, which is what the default
+ * (0) reproduces; with the option on, columns that stay clear of 2^-256 are computed exactly as before.
+ * The environment variable PCSF_RESCALE=1 sets it for every new context (used by the command line).
+ */
+#define PCSF_OPT_RESCALE 1
+int pcsf_option_set(pcsf_ctx *ctx, int option, int64_t value);
+
+/*
  * Tree shape = T.t (lib/CamlPaml/T.mli:3, T.ml:57-112): leaves are nodes 0..n_leaves-1 in
  * left-to-right order, internal nodes follow in post-order, root = 2*n_leaves-2.
  *   children[2*(i-n_leaves)+{0,1}] = (left,right) child of internal node i; both < i.

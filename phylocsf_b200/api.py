@@ -48,6 +48,9 @@ class Context:
     def stream_set(self, cuda_stream_ptr):
         self._check(self._L.pcsf_stream_set(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
 
+    def option_set(self, option, value):
+        self._check(self._L.pcsf_option_set(self._h, option, int(value)))
+
     def tree_set(self, n_leaves, children, branch_len):
         ch = np.ascontiguousarray(children, dtype=np.int32).ravel()
         bl = _f64(branch_len)[: 2 * n_leaves - 2]

@@ -64,7 +64,7 @@ struct pcsf_ctx {
     DevBuf d_region_off, d_codes, d_nt, d_aln_off, d_aln_len;
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
-    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs;
+    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs, d_gexp;
     std::vector<int32_t> pair_model, pair_status;  // P sets built by pcsf_pt_build_pairs
     int last_all_models = 0;
     // timing
@@ -73,6 +73,7 @@ struct pcsf_ctx {
     int64_t launches = 0;
     int prune_smem_optin = 0;
     int skew_ns = 1500;
+    int rescale = 0;  // PCSF_OPT_RESCALE
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
     int timeline_cap = 0;
 };
@@ -208,11 +209,18 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         p.timeline = (long long*)ctx->timeline;
         p.timeline_cap = ctx->timeline_cap;
         p.skew_ns = ctx->skew_ns;
+        TRY(reserve(ctx, ctx->d_gexp, sizeof(int32_t) * (size_t)grid * std::max(1, ctx->max_levels) * TILE_COLS));
+        p.global_exp = (int32_t*)ctx->d_gexp.p;
         const int smem = prune_smem_for(p.n_ops, p.n_items, ctx->n_leaves);
         if (smem > ctx->prune_smem_optin)
             return fail(ctx, PCSF_ERR_INVALID_ARG, "tree too large for the pruning kernel's shared memory (" + std::to_string(smem) + " bytes)");
-        CU(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        prune_kernel<<<grid, PRUNE_THREADS, smem, ctx->stream>>>(p);
+        if (ctx->rescale) {  // PCSF_OPT_RESCALE: separate instantiation, the default path carries no extra code
+            CU(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            prune_kernel<true><<<grid, PRUNE_THREADS, smem, ctx->stream>>>(p);
+        } else {
+            CU(cudaFuncSetAttribute(prune_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            prune_kernel<false><<<grid, PRUNE_THREADS, smem, ctx->stream>>>(p);
+        }
         CU(cudaGetLastError());
         ctx->launches++;
     }
@@ -366,6 +374,7 @@ int pcsf_create(int device_id, pcsf_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     ctx->prune_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("PCSF_SKEW_NS")) ctx->skew_ns = atoi(e);  // tuning knob, see prune_kernel
+    if (const char* e = getenv("PCSF_RESCALE")) ctx->rescale = atoi(e) ? 1 : 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->stream = ctx->own_stream;
     for (auto& ev : ctx->ev)
@@ -391,7 +400,7 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
                       &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
-                      &ctx->d_pair_status, &ctx->d_qs};
+                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp};
     for (auto* b : bufs) fr(*b);
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
@@ -409,6 +418,15 @@ int pcsf_stream_set(pcsf_ctx* ctx, void* cuda_stream) {
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return PCSF_OK;
+}
+
+int pcsf_option_set(pcsf_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (option == PCSF_OPT_RESCALE) {
+        ctx->rescale = value ? 1 : 0;
+        return PCSF_OK;
+    }
+    return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: unknown option");
 }
 
 int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const double* branch_len) {

@@ -255,6 +255,7 @@ struct PruneParams {
     int ops_bytes;           // n_ops * sizeof(Op) rounded up to 16
     int items_bytes;         // n_items * sizeof(Item) rounded up to 16
     int skew_ns;             // start-up offset of the second compute warp of every SM sub-partition
+    int32_t* global_exp;     // [gridDim.x][n_levels][TILE_COLS] exponents of parked partials (rescale only)
     long long* timeline;     // PCSF_TIMELINE builds only: [warp][event][2] = (code, clock64) of CTA 0
     int timeline_cap;
 };
@@ -297,6 +298,31 @@ __device__ __forceinline__ void reg_alloc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// Underflow rescue (optional; the reference has none, lib/CamlPaml/PhyloLik.ml:87-92): when the largest
+// of a column's 64 partials drops below 2^-256 the column is multiplied by the exact power of two that
+// brings it back to [1,2) and the exponent is remembered; log z gets it back at the root. Columns that
+// never come near the threshold are computed exactly as without the option.
+__device__ __forceinline__ void rescale_columns(double (&cur)[PRUNE_T][8][2], int (&esum)[PRUNE_T]) {
+#pragma unroll
+    for (int T = 0; T < PRUNE_T; T++) {
+        double m = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) m = fmax(m, fmax(cur[T][j][0], cur[T][j][1]));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        if (m > 0.0 && m < 0x1p-256) {  // uniform within the quad
+            const int e = ilogb(m);
+            const double f = scalbn(1.0, -e);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                cur[T][j][0] *= f;
+                cur[T][j][1] *= f;
+            }
+            esum[T] += e;
+        }
+    }
+}
+
 // One CTA per SM, warp-specialised:
 //   warpgroup 0 (128 threads, registers trimmed to 56) moves data only. In program order it stages
 //     - the P image of every internal edge into a 2 x 32 KB ring (TMA bulk copy, one thread),
@@ -309,6 +335,7 @@ __device__ __forceinline__ void reg_alloc() {
 //     image (K3), then one pass of LDS.128 + DMUL over the staged multiplicand.
 // All hand-offs are mbarriers; there is no CTA-wide barrier after start-up.
 // shared memory map: [P ring | M ring | barriers | ops | items | tile codes]
+template <bool RESCALE>
 __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PruneParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* Pring = smem;
@@ -427,10 +454,14 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
         const bool warp_active = wcol < ncols;
 
         double cur[PRUNE_T][8][2];
+        int esum[PRUNE_T];  // power-of-two exponent taken out of each column so far (rescale option)
 #pragma unroll
-        for (int T = 0; T < PRUNE_T; T++)
+        for (int T = 0; T < PRUNE_T; T++) {
+            esum[T] = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) cur[T][j][0] = cur[T][j][1] = 1.0;
+        }
+        int32_t* gexp = p.global_exp + ((size_t)blockIdx.x * p.n_levels) * TILE_COLS + wcol + g;
 
         for (int oi = 0; oi < p.n_ops; oi++) {
             const Op op = ops_s[oi];
@@ -486,7 +517,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                         ap += __shfl_xor_sync(0xffffffffu, ap, 2);
                         const int c = wcol + 8 * T + g;
                         if (t == 0 && c < ncols) {
-                            p.out_logz[sp.out0 + tcol0 + c] = log(zp);
+                            p.out_logz[sp.out0 + tcol0 + c] = (RESCALE && esum[T]) ? log(zp) + (double)esum[T] * 0.6931471805599453 : log(zp);
                             p.out_anc[sp.out0 + tcol0 + c] = ap;
                         }
                     }
@@ -531,6 +562,13 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     for (int T = 0; T < PRUNE_T; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) slot[(T * 8 + j) * 32] = make_double2(acc[T][j][0], acc[T][j][1]);
+                    if (RESCALE) {  // the parked message keeps its exponent; the sibling subtree starts at 0
+#pragma unroll
+                        for (int T = 0; T < PRUNE_T; T++) {
+                            if (t == 0) gexp[(size_t)op.c * TILE_COLS + 8 * T] = esum[T];
+                            esum[T] = 0;
+                        }
+                    }
                     // The producer reads the level back with a TMA bulk copy (async proxy). Writer-side
                     // ordering: CTA-scope fence (writer and reader share the SM), generic->async proxy fence,
                     // then the release-arrive on pushed[] that the producer acquires before issuing the copy.
@@ -553,6 +591,14 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                             cur[T][j][0] = acc[T][j][0] * v.x;
                             cur[T][j][1] = acc[T][j][1] * v.y;
                         }
+                    if (RESCALE) {
+                        if (op.kind == OP_GEMM_POP) {
+                            __syncwarp();  // lane t == 0 of the quad wrote the exponents at the push
+#pragma unroll
+                            for (int T = 0; T < PRUNE_T; T++) esum[T] += gexp[(size_t)op.c * TILE_COLS + 8 * T];
+                        }
+                        rescale_columns(cur, esum);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&mempty[st]);

@@ -301,3 +301,52 @@ def test_device_omega_eigen_matches_host(params_base):
         inst = o.OmegaInstance(ps.tree, list(v), rho)
         assert abs(H.DB * (lpr[i] - o.omega_lpr_leaves(inst, regs[0]))) < 1e-6
     ctx.close()
+
+
+def _lpr_extended_precision(model, codes):
+    """Pruning in numpy longdouble (x87 80-bit: exponent range down to 1e-4932), as the yardstick for the
+    rescale option where plain FP64 underflows."""
+    t = model.tree
+    P = model.pms.astype(np.longdouble)
+    prior = model.prior().astype(np.longdouble)
+    n, ncols = t.n_leaves, codes.shape[0]
+    alpha = {}
+    for l in range(n):
+        a = np.ones((ncols, 64), dtype=np.longdouble)
+        known = codes[:, l] < 64
+        a[known] = 0
+        a[known, codes[known, l]] = 1
+        alpha[l] = a
+    for i in range(n, t.size):
+        lc, rc = t.children[i]
+        alpha[i] = (alpha[lc] @ P[lc].T) * (alpha[rc] @ P[rc].T)
+    z = alpha[t.root] @ prior
+    return float(np.log(z).sum())
+
+
+def test_rescale_option_rescues_underflow(params_base):
+    """PCSF_OPT_RESCALE: uniform-random columns on the 120-leaf tree underflow to -inf without it (the
+    reference's behaviour); with it the score is finite and equals an extended-precision evaluation.
+    Columns that never get near the threshold are unchanged to the last bit."""
+    if np.finfo(np.longdouble).minexp > -16000:
+        pytest.skip("no extended-precision long double on this platform")
+    ps = H.oracle_paramset(params_base, "120mammals")
+    rng = np.random.default_rng(3)
+    bad = rng.integers(0, 64, size=(9, 120)).astype(np.uint8)
+    good = o.simulate_columns(ps.model.coding_model.model(1.0), 21, rng)
+    regs = [bad, good]
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    lpr0, elpr0, st0 = ctx.lpr_all([0, 1])
+    assert np.isneginf(lpr0[:, 0]).all() and np.isfinite(lpr0[:, 1]).all()
+    ctx.option_set(1, 1)
+    lpr1, elpr1, st1 = ctx.lpr_all([0, 1])
+    assert np.isfinite(lpr1).all() and (st1 == 0).all()
+    assert (lpr1[:, 1] == lpr0[:, 1]).all() and (elpr1[:, 1] == elpr0[:, 1]).all()
+    for m, inst in enumerate((ps.model.coding_model, ps.model.noncoding_model)):
+        want = _lpr_extended_precision(inst.model(1.0), bad)
+        assert abs(lpr1[m, 0] - want) < 1e-9 * abs(want), (lpr1[m, 0], want)
+    ctx.close()
