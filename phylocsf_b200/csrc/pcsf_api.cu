@@ -32,9 +32,6 @@ struct Model {
     DevBuf d_scales, d_status;
     int nscales = 0;
     std::vector<int32_t> status;
-    const double* S() const { return d_params; }
-    const double* Sinv() const { return d_params + 4096; }
-    const double* lambda() const { return d_params + 8192; }
     const double* prior() const { return d_params + 8192 + 64; }
     const double* logprior() const { return d_params + 8192 + 128; }
 };

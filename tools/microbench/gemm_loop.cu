@@ -48,6 +48,29 @@ __global__ void __launch_bounds__(512) gemm_loop(const double* __restrict__ Pimg
 #pragma unroll
                     for (int t = 0; t < T; t++) dmma(acc[t][j][0], acc[t][j][1], cur[t][s >> 1][s & 1], bf);
                 }
+        } else if (MODE == 3) {  // s outer, T middle, j inner: 8 consecutive DMMAs share the A operand
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                double bf[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) bf[j] = Pb[(j * 16 + s) * 32];
+#pragma unroll
+                for (int t = 0; t < T; t++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) dmma(acc[t][j][0], acc[t][j][1], cur[t][s >> 1][s & 1], bf[j]);
+            }
+        } else if (MODE == 4) {  // like 0 but B fragments of k-steps 2s2, 2s2+1 fetched with one LDS.128
+            const double2* Pb2 = reinterpret_cast<const double2*>(Ps) + lane;
+#pragma unroll
+            for (int s2 = 0; s2 < 8; s2++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double2 bf = Pb2[(j * 8 + s2) * 32];
+#pragma unroll
+                    for (int t = 0; t < T; t++) dmma(acc[t][j][0], acc[t][j][1], cur[t][s2][0], bf.x);
+#pragma unroll
+                    for (int t = 0; t < T; t++) dmma(acc[t][j][0], acc[t][j][1], cur[t][s2][1], bf.y);
+                }
         } else {
             const double bf = Pb[0];
 #pragma unroll
@@ -96,11 +119,12 @@ int main() {
     double h[4096]; for (int i = 0; i < 4096; i++) h[i] = 1.0 / 64;
     cudaMemcpy(P, h, sizeof(h), cudaMemcpyHostToDevice);
     printf("[\n");
-    int ws[] = {4, 8, 12, 16};
-    for (int wi = 0; wi < 4; wi++) {
+    int ws[] = {4, 8};
+    for (int wi = 0; wi < 2; wi++) {
         const int w = ws[wi];
-        run<2, 0>(P, out, sms, w); run<2, 1>(P, out, sms, w); run<2, 2>(P, out, sms, w);
-        run<1, 0>(P, out, sms, w); run<1, 1>(P, out, sms, w); run<1, 2>(P, out, sms, w);
+        run<2, 0>(P, out, sms, w); run<2, 1>(P, out, sms, w); run<2, 3>(P, out, sms, w); run<2, 4>(P, out, sms, w);
+        run<1, 0>(P, out, sms, w); run<1, 3>(P, out, sms, w); run<1, 4>(P, out, sms, w);
+        if (w <= 8) { run<3, 0>(P, out, sms, w); run<3, 3>(P, out, sms, w); }
     }
     printf("{}]\n");
     return 0;
