@@ -13,8 +13,8 @@ leaf codes per pass), so no L2 flush is needed between iterations.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 value   = device-resident throughput (leaf codes already in HBM), CUDA events, max over ranks
-e2e     = the same pass through the C ABI from pinned HOST buffers: H2D of the nucleotide rows,
-          on-device pleaves, pruning, region reduction, D2H of the per-region results
+e2e     = the same pass through the C ABI from pinned HOST buffers (pcsf_score_alignments): H2D of the
+          nucleotide rows in chunks overlapped with on-device pleaves, pruning, region reduction, D2H
 roofline= the pruning kernel against the FP64 tensor (DMMA) peak
 cpu_baseline / --impl reference = the CPU oracle (oracle/, a restatement of the reference's OCaml
           path; the reference itself needs OCaml+GSL, absent here) on a bounded sample, all host threads
@@ -243,8 +243,7 @@ def main():
         ctx.lpr_all([0, 1], out=outs)
 
     def step_e2e():
-        ctx.batch_upload_alignments(aln_off, aln_len, nt_np, FRAMES)
-        ctx.lpr_all([0, 1], out=outs)
+        ctx.score_alignments(aln_off, aln_len, nt_np, FRAMES, [0, 1], out=outs)
 
     uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
@@ -310,7 +309,7 @@ def main():
             "config": config,
             "e2e": {"value": e2e_value, "unit": "codon-columns/s", "h2d_bytes_per_step": int(nt_np.nbytes + aln_off.nbytes + aln_len.nbytes),
                     "d2h_bytes_per_step": int(outs[0].nbytes + outs[1].nbytes), "ms_per_step": ms_e2e / args.steps,
-                    "path": "pcsf_batch_upload_alignments (H2D + on-device pleaves) + pcsf_lpr_all, pinned host buffers"},
+                    "path": "pcsf_score_alignments: pinned host nucleotide rows -> chunked H2D overlapped with on-device pleaves + pruning + reduction -> D2H"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "pcsf::prune_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -128,6 +128,16 @@ int pcsf_lpr_all(pcsf_ctx *ctx, int n_models, const int32_t *model_ids, const in
                  double *out_lpr, double *out_elpr_anc, int32_t *out_status);
 
 /*
+ * pcsf_batch_upload_alignments + pcsf_lpr_all in one call, pipelined: the alignments are processed in
+ * chunks of ~2 M codon columns, and the host->device copy of chunk k+1 runs on a second stream while
+ * chunk k is being scored. out_* are indexed [m * (nalign*frames) + region], regions numbered as in
+ * pcsf_batch_upload_alignments. No batch remains staged afterwards.
+ */
+int pcsf_score_alignments(pcsf_ctx *ctx, int64_t nalign, const int64_t *aln_off, const int32_t *aln_len,
+                          const uint8_t *nt, int frames, int n_models, const int32_t *model_ids,
+                          const int32_t *scale_idx, double *out_lpr, double *out_elpr_anc, int32_t *out_status);
+
+/*
  * The same for an explicit list of evaluations: evaluation e scores region eval_region[e] under
  * model eval_model[e] with P tables of scale index eval_scale[e]. This is the shape one round of
  * batched maximize_lpr candidates has (one candidate rho per (region, model)).

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libphylocsf_b200.so")
 SYMBOLS = [
     "pcsf_version", "pcsf_device_count", "pcsf_create", "pcsf_destroy", "pcsf_last_error", "pcsf_stream_set", "pcsf_option_set",
     "pcsf_tree_set", "pcsf_model_set", "pcsf_pt_build", "pcsf_pt_get", "pcsf_batch_upload",
-    "pcsf_batch_upload_alignments", "pcsf_batch_nregions", "pcsf_batch_ncols", "pcsf_lpr_all", "pcsf_lpr",
+    "pcsf_batch_upload_alignments", "pcsf_batch_nregions", "pcsf_batch_ncols", "pcsf_lpr_all", "pcsf_score_alignments", "pcsf_lpr",
     "pcsf_models_set", "pcsf_omega_models_set", "pcsf_model_get", "pcsf_pt_build_pairs", "pcsf_lpr_pairs", "pcsf_column_terms", "pcsf_maximize_lpr", "pcsf_last_ms", "pcsf_launch_count",
 ]
 
@@ -56,6 +56,7 @@ def load():
     L.pcsf_batch_ncols.argtypes = [vp]
     L.pcsf_batch_ncols.restype = i64
     L.pcsf_lpr_all.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
+    L.pcsf_score_alignments.argtypes = [vp, i64, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     L.pcsf_lpr.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     L.pcsf_models_set.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     L.pcsf_omega_models_set.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp]

@@ -108,6 +108,22 @@ class Context:
         self._check(self._L.pcsf_lpr_all(self._h, m, N.ptr(mids), N.ptr(sidx), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
         return lpr, elpr, st
 
+    def score_alignments(self, aln_off, aln_len, nt, frames, model_ids, scale_idx=None, out=None):
+        """Pipelined pleaves + lpr_leaves from host nucleotide rows (H2D of the next chunk overlaps compute)."""
+        ao = np.ascontiguousarray(aln_off, dtype=np.int64)
+        al = np.ascontiguousarray(aln_len, dtype=np.int32)
+        if isinstance(nt, np.ndarray):
+            nt = np.ascontiguousarray(nt, dtype=np.uint8)
+        mids = np.ascontiguousarray(model_ids, dtype=np.int32)
+        sidx = None if scale_idx is None else np.ascontiguousarray(scale_idx, dtype=np.int32)
+        m, R = mids.size, ao.size * frames
+        lpr, elpr = out if out is not None else (np.empty((m, R)), np.empty((m, R)))
+        st = np.zeros((m, R), dtype=np.int32)
+        self._check(self._L.pcsf_score_alignments(self._h, ao.size, N.ptr(ao), N.ptr(al), N.ptr(nt), frames, m, N.ptr(mids),
+                                                  N.ptr(sidx), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
+        self.nregions = 0
+        return lpr, elpr, st
+
     def lpr(self, eval_model, eval_scale, eval_region):
         em = np.ascontiguousarray(eval_model, dtype=np.int32)
         es = np.ascontiguousarray(eval_scale, dtype=np.int32)

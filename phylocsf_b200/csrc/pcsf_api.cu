@@ -3,6 +3,7 @@
 #include "../../include/phylocsf_b200.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,6 +63,10 @@ struct pcsf_ctx {
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
     DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs, d_gexp;
+    // pcsf_score_alignments: double-buffered chunk staging on a second stream
+    DevBuf pipe_nt[2], pipe_aln_off[2], pipe_aln_len[2], pipe_codes[2], pipe_roff[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::vector<int32_t> pair_model, pair_status;  // P sets built by pcsf_pt_build_pairs
     int last_all_models = 0;
     // timing
@@ -166,7 +171,8 @@ int prune_smem_for(int n_ops, int n_items, int n_leaves) {
 }
 
 // Launch K2+K3 over `spans`, then K4 over the given segments. Outputs land in ctx->d_lpr/d_elpr.
-int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vector<PSet>& psets, int64_t out_cols) {
+int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vector<PSet>& psets, int64_t out_cols,
+              const uint8_t* codes = nullptr) {
     std::vector<Span> spans = spans_in;
     int64_t tiles = 0;
     for (auto& s : spans) {
@@ -196,7 +202,7 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         p.n_spans = (int)spans.size();
         p.n_tiles = tiles;
         p.psets = (const PSet*)ctx->d_psets.p;
-        p.codes = (const uint8_t*)ctx->d_codes.p;
+        p.codes = codes ? codes : (const uint8_t*)ctx->d_codes.p;
         p.out_logz = (double*)ctx->d_out_logz.p;
         p.out_anc = (double*)ctx->d_out_anc.p;
         p.global_stack = (uint8_t*)ctx->d_gstack.p;
@@ -397,12 +403,19 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
                       &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
-                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp};
+                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
+                      &ctx->pipe_aln_off[1], &ctx->pipe_aln_len[0], &ctx->pipe_aln_len[1], &ctx->pipe_codes[0], &ctx->pipe_codes[1],
+                      &ctx->pipe_roff[0], &ctx->pipe_roff[1]};
     for (auto* b : bufs) fr(*b);
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
     if (ctx->d_items) cudaFree(ctx->d_items);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -651,6 +664,122 @@ int pcsf_lpr_all(pcsf_ctx* ctx, int n_models, const int32_t* model_ids, const in
             const int st = ctx->models[model_ids[m]].status[scale_idx ? scale_idx[m] : 0];
             for (int64_t r = 0; r < ctx->nregions; r++)
                 out_status[m * ctx->nregions + r] = st | (std::isfinite(out_lpr[m * ctx->nregions + r]) ? 0 : PCSF_ST_NOT_FINITE);
+        }
+    return PCSF_OK;
+}
+
+int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off, const int32_t* aln_len, const uint8_t* nt,
+                          int frames, int n_models, const int32_t* model_ids, const int32_t* scale_idx, double* out_lpr,
+                          double* out_elpr_anc, int32_t* out_status) {
+    TRY(check_ready(ctx, false));
+    if (nalign < 0 || !aln_off || !aln_len || (frames != 1 && frames != 3 && frames != 6) || n_models < 1 || !model_ids || !out_lpr)
+        return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_score_alignments: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<PSet> psets;
+    for (int m = 0; m < n_models; m++) {
+        const int sc = scale_idx ? scale_idx[m] : 0;
+        TRY(check_model(ctx, model_ids[m], sc));
+        psets.push_back(make_pset(ctx, model_ids[m], sc));
+    }
+    if (!ctx->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int64_t R_total = nalign * frames;
+    // chunks of whole alignments, ~2 M codon columns each (tens of ms of compute, a few ms of copy)
+    int64_t chunk_cols = 2000000;
+    if (const char* e = getenv("PCSF_CHUNK_COLS")) chunk_cols = std::max<int64_t>(1, atoll(e));  // tests force many chunks
+    std::vector<int64_t> chunk_begin{0};
+    {
+        int64_t cols = 0;
+        for (int64_t a = 0; a < nalign; a++) {
+            if (aln_len[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment length");
+            int64_t c = 0;
+            for (int f = 0; f < frames; f++) { const int rem = aln_len[a] - (f % 3); c += rem >= 3 ? rem / 3 : 0; }
+            if (cols > 0 && cols + c > chunk_cols) { chunk_begin.push_back(a); cols = 0; }
+            cols += c;
+        }
+        chunk_begin.push_back(nalign);
+    }
+    CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+    std::vector<int64_t> h_aoff[2], h_roff[2];
+    for (size_t k = 0; k + 1 < chunk_begin.size(); k++) {
+        const int b = (int)(k & 1);
+        const int64_t a0 = chunk_begin[k], a1 = chunk_begin[k + 1], na = a1 - a0;
+        if (na == 0) continue;
+        int64_t lo = INT64_MAX, hi = 0;
+        for (int64_t a = a0; a < a1; a++) {
+            lo = std::min(lo, aln_off[a]);
+            hi = std::max(hi, aln_off[a] + (int64_t)aln_len[a] * ctx->n_leaves);
+        }
+        if (hi > lo && !nt) return fail(ctx, PCSF_ERR_INVALID_ARG, "null nucleotide buffer");
+        // the host-side staging vectors of buffer b may still feed an in-flight pageable copy of chunk k-2
+        if (k >= 2) CU(cudaEventSynchronize(ctx->ev_copied[b]));
+        h_aoff[b].resize(na);
+        h_roff[b].assign(na * frames + 1, 0);
+        for (int64_t a = a0; a < a1; a++) {
+            h_aoff[b][a - a0] = aln_off[a] - lo;
+            for (int f = 0; f < frames; f++) {
+                const int rem = aln_len[a] - (f % 3);
+                h_roff[b][(a - a0) * frames + f + 1] = h_roff[b][(a - a0) * frames + f] + (rem >= 3 ? rem / 3 : 0);
+            }
+        }
+        const int64_t nreg = na * frames, total = h_roff[b][nreg];
+        TRY(reserve(ctx, ctx->pipe_nt[b], std::max<int64_t>(hi - lo, 1)));
+        TRY(reserve(ctx, ctx->pipe_aln_off[b], sizeof(int64_t) * na));
+        TRY(reserve(ctx, ctx->pipe_aln_len[b], sizeof(int32_t) * na));
+        TRY(reserve(ctx, ctx->pipe_roff[b], sizeof(int64_t) * (nreg + 1)));
+        TRY(reserve(ctx, ctx->pipe_codes[b], (size_t)std::max<int64_t>(total, 1) * ctx->n_leaves));
+        // ---- copy stream: stage chunk k once the kernels of chunk k-2 have released buffer b ----
+        if (k >= 2) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0));
+        if (hi > lo) CU(cudaMemcpyAsync(ctx->pipe_nt[b].p, nt + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaMemcpyAsync(ctx->pipe_aln_off[b].p, h_aoff[b].data(), sizeof(int64_t) * na, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaMemcpyAsync(ctx->pipe_aln_len[b].p, aln_len + a0, sizeof(int32_t) * na, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaMemcpyAsync(ctx->pipe_roff[b].p, h_roff[b].data(), sizeof(int64_t) * (nreg + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        // ---- compute stream: pleaves, pruning, reduction, results back ----
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        frame_codes_kernel<<<(unsigned)nreg, 128, 0, ctx->stream>>>(
+            (const uint8_t*)ctx->pipe_nt[b].p, (const int64_t*)ctx->pipe_aln_off[b].p, (const int32_t*)ctx->pipe_aln_len[b].p,
+            (const int64_t*)ctx->pipe_roff[b].p, nreg, frames, ctx->n_leaves, (uint8_t*)ctx->pipe_codes[b].p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        std::vector<Span> spans;
+        for (int m = 0; m < n_models; m++) spans.push_back(Span{0, (int64_t)m * total, 0, (int32_t)total, m});
+        const int64_t n_segs = nreg * n_models;
+        TRY(run_prune(ctx, spans, psets, total * n_models, (const uint8_t*)ctx->pipe_codes[b].p));
+        TRY(reserve(ctx, ctx->d_seg_begin, sizeof(int64_t) * n_segs));
+        TRY(reserve(ctx, ctx->d_seg_end, sizeof(int64_t) * n_segs));
+        make_segments_kernel<<<(unsigned)((n_segs + 255) / 256), 256, 0, ctx->stream>>>(
+            (const int64_t*)ctx->pipe_roff[b].p, nreg, n_models, total, (int64_t*)ctx->d_seg_begin.p, (int64_t*)ctx->d_seg_end.p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        TRY(run_reduce(ctx, n_segs));
+        for (int m = 0; m < n_models; m++) {
+            CU(cudaMemcpyAsync(out_lpr + (size_t)m * R_total + a0 * frames, (const double*)ctx->d_lpr.p + (size_t)m * nreg,
+                               sizeof(double) * nreg, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_elpr_anc)
+                CU(cudaMemcpyAsync(out_elpr_anc + (size_t)m * R_total + a0 * frames, (const double*)ctx->d_elpr.p + (size_t)m * nreg,
+                                   sizeof(double) * nreg, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    }
+    CU(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+    ctx->ms[0] = t;  // whole pipelined pass
+    ctx->last_all_models = 0;
+    ctx->nregions = -1;  // no single staged batch remains
+    if (out_status)
+        for (int m = 0; m < n_models; m++) {
+            const int st = ctx->models[model_ids[m]].status[scale_idx ? scale_idx[m] : 0];
+            for (int64_t r = 0; r < R_total; r++)
+                out_status[m * R_total + r] = st | (std::isfinite(out_lpr[m * R_total + r]) ? 0 : PCSF_ST_NOT_FINITE);
         }
     return PCSF_OK;
 }

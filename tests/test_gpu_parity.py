@@ -350,3 +350,49 @@ def test_rescale_option_rescues_underflow(params_base):
         want = _lpr_extended_precision(inst.model(1.0), bad)
         assert abs(lpr1[m, 0] - want) < 1e-9 * abs(want), (lpr1[m, 0], want)
     ctx.close()
+
+
+def test_pipelined_score_alignments_equals_two_step_path(params_base, monkeypatch):
+    """pcsf_score_alignments (chunked, H2D on a second stream) gives bit-identical results to
+    pcsf_batch_upload_alignments + pcsf_lpr_all, with the chunk size forced small enough for many chunks."""
+    monkeypatch.setenv("PCSF_CHUNK_COLS", "300")
+    ps = H.oracle_paramset(params_base, "29mammals")
+    rng = np.random.default_rng(9)
+    n = ps.tree.n_leaves
+    lens = [30, 111, 3, 2, 64, 300, 17, 90, 45, 201, 6, 150]
+    rows, off = [], [0]
+    for L in lens:
+        a = rng.choice(np.frombuffer(b"ACGTacgtN-", dtype=np.uint8), size=(n, L), p=[.2, .2, .2, .2, .03, .03, .03, .03, .04, .04])
+        rows.append(a)
+        off.append(off[-1] + n * L)
+    nt = np.concatenate([a.ravel() for a in rows])
+    for frames in (1, 3, 6):
+        ctx = H.make_context(ps)
+        ctx.pt_build(0, [1.0])
+        ctx.pt_build(1, [1.0])
+        ctx.batch_upload_alignments(off[:-1], lens, nt, frames)
+        a = ctx.lpr_all([0, 1])
+        b = ctx.score_alignments(off[:-1], lens, nt, frames, [0, 1])
+        assert a[0].shape == b[0].shape == (2, len(lens) * frames)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+        ctx.close()
+
+
+@pytest.mark.parametrize("species", [["dmel", "dvir"], ["dmel", "dana", "dvir"], ["dmel", "dsim", "dsec", "dyak"]])
+def test_tiny_trees(params_base, species):
+    """Two-, three- and four-leaf trees (after --species pruning, Newick.subtree merges the spliced
+    branches): a walk that is a single cherry, a cherry plus one edge, and two cherries joined at the root."""
+    ps = H.oracle_paramset(params_base, "12flies", species=species)
+    assert ps.tree.n_leaves == len(species)
+    rng = np.random.default_rng(1)
+    regs = [rng.integers(0, 65, size=(n, len(species))).astype(np.uint8) for n in (1, 19, 130)]
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0, 0.2])
+    ctx.pt_build(1, [1.0, 0.2])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    for si, rho in enumerate((1.0, 0.2)):
+        lpr, elpr, st = ctx.lpr_all([0, 1], [si, si])
+        lo, eo = H.oracle_fixed(ps, regs, rho=rho)
+        assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB and np.abs(H.DB * (elpr - eo)).max() < TOL_DB
+    ctx.close()
