@@ -2,6 +2,7 @@
 // (src/PhyloCSF.ml:17-49,469-491) over the B200 compute library. Same options, same output lines.
 #include <unistd.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -25,7 +26,7 @@ static const char* kUsage =
     "  --orf=AsIs|ATGStop|StopStop|StopStop3|ToFirstStop|FromLastStop|ToOrFromStop  search for ORFs (default AsIs)\n"
     "  --minCodons=INT              minimum ORF length for searching over ORFs (default 25 codons)\n"
     "  --allScores                  report scores of all regions evaluated, not just the max\n"
-    "  -p INT                       accepted for compatibility; regions are batched on the GPU instead\n"
+    "  -p INT                       host threads that read and prepare alignments (default: all cores); scoring is batched on the GPU\n"
     " output control:\n"
     "  --bls                        include alignment branch length score (BLS) for the reported region in output\n"
     "  --ancComp                    include ancestral sequence composition score in output\n"
@@ -104,8 +105,6 @@ int main(int argc, char** argv) {
     }
     if (opt.orf != AsIs && opt.frames == 1)
         std::cerr << "Warning: --orf with --frames=1; are you sure you don't want to search for ORFs in three or six frames?\n";
-    if (opt.procs > 1)
-        std::cerr << "Warning: ignoring -p; regions of many alignments are evaluated together on the GPU\n";
     if (const char* d = std::getenv("PCSF_DEVICE")) opt.device = std::atoi(d);
     if (const char* b = std::getenv("PCSF_BATCH_COLS")) opt.batch_cols = std::atoll(b);
 
@@ -154,21 +153,58 @@ int main(int argc, char** argv) {
             fns.push_back("");
         } else fns = fns_input;
 
-        for (const std::string& fn : fns) {
-            const std::string name = fn.empty() ? "(STDIN)" : fn;
-            std::vector<std::string> lines;
-            if (fn.empty() && from_stdin) lines = read_lines(std::cin);
+        // Files are read and prepared (parse, checks, regions, leaf codes) by a pool of host threads, a
+        // block at a time, and appended to the GPU batch in input order. The reference's -p N forked
+        // per-region workers; here N only caps the host threads (default: all cores).
+        struct Slot {
+            Driver::Prepared prep;
+            bool missing = false;
+        };
+        unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
+        if (opt.procs > 1) nthreads = (unsigned)opt.procs;
+        if (const char* t = std::getenv("PCSF_HOST_THREADS")) nthreads = std::max(1, std::atoi(t));
+        const size_t block = 64 * (size_t)nthreads;
+        for (size_t b0 = 0; b0 < fns.size(); b0 += block) {
+            const size_t b1 = std::min(fns.size(), b0 + block);
+            std::vector<Slot> slots(b1 - b0);
+            std::atomic<size_t> next{b0};
+            auto work = [&]() {
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= b1) return;
+                    const std::string& fn = fns[i];
+                    const std::string name = fn.empty() ? "(STDIN)" : fn;
+                    std::vector<std::string> lines;
+                    if (fn.empty() && from_stdin) lines = read_lines(std::cin);
+                    else {
+                        std::ifstream in(fn);
+                        if (!in) {
+                            slots[i - b0].missing = true;
+                            slots[i - b0].prep.job.name = name;
+                            continue;
+                        }
+                        lines = read_lines(in);
+                    }
+                    slots[i - b0].prep = drv.prepare(name, lines);
+                }
+            };
+            const unsigned nt = (unsigned)std::min<size_t>(nthreads, b1 - b0);
+            if (nt <= 1) work();
             else {
-                std::ifstream in(fn);
-                if (!in) {
+                std::vector<std::thread> pool;
+                for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+                for (auto& t : pool) t.join();
+            }
+            for (size_t i = b0; i < b1; i++) {
+                Slot& sl = slots[i - b0];
+                if (sl.missing) {
                     drv.flush(std::cout);
-                    std::cout << name << "\tabort\tSys_error(\"" << fn << ": No such file or directory\")\n";
+                    std::cout << sl.prep.job.name << "\tabort\tSys_error(\"" << fns[i] << ": No such file or directory\")\n";
                     std::cout.flush();
                     return 255;
                 }
-                lines = read_lines(in);
+                if (!drv.append(std::move(sl.prep), std::cout)) return 255;
             }
-            if (!drv.add_alignment(name, lines, std::cout)) return 255;
         }
         drv.flush(std::cout);
     } catch (const std::exception& e) {

@@ -83,6 +83,7 @@ class Driver {
         ps = load_paramset(paramset_prefix, o.species, o.strategy == STRAT_MLE || o.strategy == STRAT_FIXED);
         n_leaves = ps.tree.n_leaves;
         leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
+        leaf_set.insert(leaf_labels.begin(), leaf_labels.end());
         if (o.strategy != STRAT_NOP) {
             if (pcsf_create(o.device, &ctx) != PCSF_OK)
                 throw failure("phylocsf_b200: no usable CUDA device (there is no CPU fallback)");
@@ -103,9 +104,18 @@ class Driver {
         if (ctx) pcsf_destroy(ctx);
     }
 
-    // Returns false when the run must stop (an alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
-    bool add_alignment(const std::string& name, const std::vector<std::string>& lines, std::ostream& out) {
+    // Everything of process_alignment that precedes scoring (src/PhyloCSF.ml:283-308,320), for one
+    // alignment: parse, sanity checks, leaf order, candidate regions, leaf codes. Thread-safe (reads
+    // only the immutable parts of the driver), so many alignments can be prepared in parallel.
+    struct Prepared {
         AlnJob job;
+        std::vector<uint8_t> codes;
+        std::vector<int> region_cols;
+        std::string abort;  // non-empty: the alignment aborted with this Printexc text
+    };
+    Prepared prepare(const std::string& name, const std::vector<std::string>& lines) const {
+        Prepared p;
+        AlnJob& job = p.job;
         job.name = name;
         try {
             Alignment a = input_mfa(lines);
@@ -116,9 +126,9 @@ class Driver {
                 throw failure("the reference sequence (first alignment row) must be ungapped");
             job.aln = a.seqs;
             for (auto& s : a.seqs) job.rc_aln.push_back(revcomp(s));
-            std::set<std::string> tsp(leaf_labels.begin(), leaf_labels.end()), wtf;
+            std::set<std::string> wtf;
             for (auto& sp : a.species)
-                if (!tsp.count(sp)) wtf.insert(sp);
+                if (!leaf_set.count(sp)) wtf.insert(sp);
             if (!wtf.empty()) {
                 std::string m = "parameters not available for species:";
                 for (auto& s : wtf) m += " " + s;
@@ -128,24 +138,38 @@ class Driver {
             job.regions = candidate_regions(job.aln[0], opt.orf, opt.frames, opt.min_codons);
             if (job.regions.empty()) job.failure = "Failure(\"no sufficiently long ORFs found\")";
         } catch (const HostError& e) {
-            flush(out);
-            out << name << "\tabort\t" << e.what() << "\n";
-            out.flush();
-            return false;
+            p.abort = e.what();
+            return p;
         }
         std::vector<int> leaf_ord(n_leaves, -1);
         for (int l = 0; l < n_leaves; l++) {
             auto it = job.which_row.find(leaf_labels[l]);
             if (it != job.which_row.end()) leaf_ord[l] = it->second;
         }
-        job.first_region = (int64_t)region_off.size() - 1;
-        for (const Region& r : job.regions) {
-            const int nc = pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, codes);
-            region_off.push_back(region_off.back() + nc);
+        for (const Region& r : job.regions)
+            p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, p.codes));
+        return p;
+    }
+
+    // Appends a prepared alignment to the current batch (in input order). Returns false when the run
+    // must stop (the alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
+    bool append(Prepared&& p, std::ostream& out) {
+        if (!p.abort.empty()) {
+            flush(out);
+            out << p.job.name << "\tabort\t" << p.abort << "\n";
+            out.flush();
+            return false;
         }
-        jobs.push_back(std::move(job));
+        p.job.first_region = (int64_t)region_off.size() - 1;
+        for (int nc : p.region_cols) region_off.push_back(region_off.back() + nc);
+        codes.insert(codes.end(), p.codes.begin(), p.codes.end());
+        jobs.push_back(std::move(p.job));
         if (region_off.back() >= opt.batch_cols) flush(out);
         return true;
+    }
+
+    bool add_alignment(const std::string& name, const std::vector<std::string>& lines, std::ostream& out) {
+        return append(prepare(name, lines), out);
     }
 
     void flush(std::ostream& out) {
@@ -175,6 +199,7 @@ class Driver {
     pcsf_ctx* ctx = nullptr;
     int n_leaves = 0;
     std::vector<std::string> leaf_labels;
+    std::set<std::string> leaf_set;
     std::vector<AlnJob> jobs;
     std::vector<uint8_t> codes;
     std::vector<int64_t> region_off{0};
