@@ -64,7 +64,11 @@ struct AlnJob {
     std::vector<std::string> aln, rc_aln;
     std::map<std::string, int> which_row;
     std::vector<Region> regions;
-    int64_t first_region = 0;
+    int64_t first_region = 0;  // index of this alignment's first staged region in the GPU batch
+    int64_t first_rec = 0;     // index of its first candidate region in the batch's score records
+    // frame mode (fixed strategy + ORF search): the batch holds whole reading frames, and candidate
+    // region k is columns [reg_col0[k], reg_col0[k] + reg_ncols[k]) of staged frame reg_frame[k]
+    std::vector<int> reg_frame, reg_col0, reg_ncols;
     std::string failure;  // per-alignment failure text (no ORFs)
 };
 
@@ -146,10 +150,31 @@ class Driver {
             auto it = job.which_row.find(leaf_labels[l]);
             if (it != job.which_row.end()) leaf_ord[l] = it->second;
         }
-        for (const Region& r : job.regions)
-            p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, p.codes));
+        if (!frame_mode()) {
+            for (const Region& r : job.regions)
+                p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, p.codes));
+            return p;
+        }
+        // Frame mode: under the fixed strategy every column's log-likelihood is independent of the region
+        // it is scored in, so nested / overlapping ORFs (ATGStop emits one ORF per upstream ATG of a stop)
+        // share columns. Stage each reading frame that holds a candidate once; ORF scores become
+        // segment sums of the per-column terms.
+        int frame_slot[6] = {-1, -1, -1, -1, -1, -1};
+        const int hi_all = (int)job.aln[0].size() - 1;
+        for (const Region& r : job.regions) {
+            const int ofs = r.lo % 3, f = (r.rc ? 3 : 0) + ofs;
+            if (frame_slot[f] < 0) {
+                frame_slot[f] = (int)p.region_cols.size();
+                p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, ofs, hi_all, p.codes));
+            }
+            job.reg_frame.push_back(frame_slot[f]);
+            job.reg_col0.push_back((r.lo - ofs) / 3);
+            job.reg_ncols.push_back((r.hi - r.lo + 1) / 3);
+        }
         return p;
     }
+
+    bool frame_mode() const { return opt.strategy == STRAT_FIXED && opt.orf != AsIs; }
 
     // Appends a prepared alignment to the current batch (in input order). Returns false when the run
     // must stop (the alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
@@ -161,6 +186,8 @@ class Driver {
             return false;
         }
         p.job.first_region = (int64_t)region_off.size() - 1;
+        p.job.first_rec = n_rec;
+        n_rec += (int64_t)p.job.regions.size();
         for (int nc : p.region_cols) region_off.push_back(region_off.back() + nc);
         codes.insert(codes.end(), p.codes.begin(), p.codes.end());
         jobs.push_back(std::move(p.job));
@@ -175,11 +202,11 @@ class Driver {
     void flush(std::ostream& out) {
         if (jobs.empty()) return;
         const int64_t R = (int64_t)region_off.size() - 1;
-        std::vector<ScoreRecord> rec(R);
+        std::vector<ScoreRecord> rec(n_rec);
         if (R > 0) {
             if (opt.strategy != STRAT_NOP) check(pcsf_batch_upload(ctx, R, region_off.data(), codes.data()));
             switch (opt.strategy) {
-                case STRAT_FIXED: score_fixed(rec); break;
+                case STRAT_FIXED: if (frame_mode()) score_fixed_frames(rec); else score_fixed(rec); break;
                 case STRAT_MLE: score_mle(rec); break;
                 case STRAT_OMEGA: score_omega(rec); break;
                 case STRAT_NOP: break;
@@ -189,6 +216,7 @@ class Driver {
         jobs.clear();
         codes.clear();
         region_off.assign(1, 0);
+        n_rec = 0;
     }
 
     int64_t evaluations = 0;  // likelihood evaluations (region x model) issued, for --debug statistics
@@ -203,6 +231,7 @@ class Driver {
     std::vector<AlnJob> jobs;
     std::vector<uint8_t> codes;
     std::vector<int64_t> region_off{0};
+    int64_t n_rec = 0;  // candidate regions in the current batch (= staged regions except in frame mode)
 
     void check(int rc) {
         if (rc != PCSF_OK && rc != PCSF_ERR_NUMERIC) throw failure(std::string("phylocsf_b200: ") + pcsf_last_error(ctx));
@@ -223,6 +252,39 @@ class Driver {
             rec[r].anc_comp = db(elpr[r] - elpr[R + r]);
             rec[r].diag = {{"rho", sf2(1.0)}, {"L(C)", sf2(db(lpr[r]))}, {"L(NC)", sf2(db(lpr[R + r]))}};
         }
+    }
+
+    // llr_FixedLik for ORF candidates from per-column terms of whole frames. The column sums run in
+    // column order, as the reference's `lpr := !lpr +. log ...` does (src/PhyloCSFModel.ml:76-81).
+    void score_fixed_frames(std::vector<ScoreRecord>& rec) {
+        const int64_t R = (int64_t)region_off.size() - 1, C = region_off.back();
+        std::vector<double> lpr(2 * R), elpr(2 * R), clz[2], can[2];
+        std::vector<int32_t> st(2 * R);
+        const int32_t mids[2] = {0, 1};
+        check(pcsf_lpr_all(ctx, 2, mids, nullptr, lpr.data(), elpr.data(), st.data()));
+        evaluations += 2 * R;
+        for (int m = 0; m < 2; m++) {
+            clz[m].resize(C);
+            can[m].resize(C);
+            check(pcsf_column_terms(ctx, m, clz[m].data(), can[m].data()));
+        }
+        for (const AlnJob& j : jobs)
+            for (size_t k = 0; k < j.regions.size(); k++) {
+                ScoreRecord& rc = rec[j.first_rec + k];
+                const int64_t b = j.first_region + j.reg_frame[k];
+                const int32_t bad = (st[b] | st[R + b]) & ~PCSF_ST_NOT_FINITE;
+                if (bad) { rc.exn = status_exn(bad); continue; }
+                const int64_t c0 = region_off[b] + j.reg_col0[k];
+                double l[2] = {0.0, 0.0}, e[2] = {0.0, 0.0};
+                for (int m = 0; m < 2; m++)
+                    for (int c = 0; c < j.reg_ncols[k]; c++) {
+                        l[m] += clz[m][c0 + c];
+                        e[m] += can[m][c0 + c];
+                    }
+                rc.score = db(l[0] - l[1]);
+                rc.anc_comp = db(e[0] - e[1]);
+                rc.diag = {{"rho", sf2(1.0)}, {"L(C)", sf2(db(l[0]))}, {"L(NC)", sf2(db(l[1]))}};
+            }
     }
 
     // ---- PhyloCSFModel.llr_MaxLik ~init:1. (src/PhyloCSFModel.ml:130-136) ----
@@ -395,7 +457,7 @@ class Driver {
         std::vector<int> ok;
         if (fail.empty()) {
             for (size_t k = 0; k < j.regions.size(); k++) {
-                const ScoreRecord& s = rec[j.first_region + k];
+                const ScoreRecord& s = rec[j.first_rec + k];
                 const Region& rg = j.regions[k];
                 if (s.exn.empty()) { ok.push_back((int)k); continue; }
                 out << j.name << "\texception\t" << rg.lo << "\t" << rg.hi;
@@ -410,7 +472,7 @@ class Driver {
             return;
         }
         auto line = [&](const char* ty, int k) {
-            const ScoreRecord& s = rec[j.first_region + k];
+            const ScoreRecord& s = rec[j.first_rec + k];
             const Region& rg = j.regions[k];
             const std::vector<std::string>& rows = rg.rc ? j.rc_aln : j.aln;
             out << j.name << "\t" << ty << "\t" << fmt4(s.score);
@@ -431,7 +493,7 @@ class Driver {
             for (int k : ok) line("orf_score(decibans)", k);
         int best = ok[0];
         for (size_t i = 1; i < ok.size(); i++)
-            if (!ocaml_ge(rec[j.first_region + best], j.regions[best], rec[j.first_region + ok[i]], j.regions[ok[i]])) best = ok[i];
+            if (!ocaml_ge(rec[j.first_rec + best], j.regions[best], rec[j.first_rec + ok[i]], j.regions[ok[i]])) best = ok[i];
         line((opt.orf != AsIs || opt.frames != 1) ? "max_score(decibans)" : "score(decibans)", best);
         out.flush();
     }

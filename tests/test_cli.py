@@ -154,6 +154,9 @@ def test_reference_goldens_through_the_cli(params_base):
     ("29mammals", "Aldh2.mRNA.fa", ["--strategy=fixed", "--orf=ATGStop", "--frames=3", "--removeRefGaps", "--allScores"],
      dict(strategy="fixed", orf="ATGStop", frames=3, remove_ref_gaps=True, all_scores=True)),
     ("12flies", "tal-AA.fa", ["--strategy=omega", "--frames=3", "--allScores", "--debug"], dict(strategy="omega", frames=3, all_scores=True, debug=True)),
+    # fixed + ORF search on both strands: scored from per-column terms of whole frames (frame mode)
+    ("29mammals", "Aldh2.mRNA.fa", ["--strategy=fixed", "--orf=StopStop3", "--frames=6", "--removeRefGaps", "--allScores", "--ancComp", "--debug", "--minCodons=30"],
+     dict(strategy="fixed", orf="StopStop3", frames=6, remove_ref_gaps=True, all_scores=True, anc_comp=True, debug=True, min_codons=30)),
 ])
 def test_scores_match_oracle_lines(params_base, pset, fn, flags, kw):
     path = ex(params_base, fn)
