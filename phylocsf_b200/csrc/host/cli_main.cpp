@@ -136,7 +136,16 @@ int main(int argc, char** argv) {
                 }
             }
         }
-        Driver drv(opt, prefix);
+        std::vector<int> devices;  // PCSF_DEVICES=0,1,.. or "all": batches go round-robin over these GPUs
+        if (const char* ds = std::getenv("PCSF_DEVICES")) {
+            if (std::string(ds) == "all") for (int d = 0; d < pcsf_device_count(); d++) devices.push_back(d);
+            else {
+                std::stringstream ss(ds);
+                std::string tok;
+                while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(std::atoi(tok.c_str()));
+            }
+        }
+        Driver drv(opt, prefix, devices);
 
         std::vector<std::string> fns;
         bool from_stdin = false;
@@ -198,7 +207,7 @@ int main(int argc, char** argv) {
             for (size_t i = b0; i < b1; i++) {
                 Slot& sl = slots[i - b0];
                 if (sl.missing) {
-                    drv.flush(std::cout);
+                    drv.finish(std::cout);
                     std::cout << sl.prep.job.name << "\tabort\tSys_error(\"" << fns[i] << ": No such file or directory\")\n";
                     std::cout.flush();
                     return 255;
@@ -206,7 +215,7 @@ int main(int argc, char** argv) {
                 if (!drv.append(std::move(sl.prep), std::cout)) return 255;
             }
         }
-        drv.flush(std::cout);
+        drv.finish(std::cout);
     } catch (const std::exception& e) {
         std::cerr << "Fatal error: exception " << e.what() << "\n";
         return 2;

@@ -10,7 +10,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <future>
+#include <memory>
 #include <functional>
 #include <iostream>
 #include <map>
@@ -72,6 +75,14 @@ struct AlnJob {
     std::string failure;  // per-alignment failure text (no ORFs)
 };
 
+// The regions of many alignments, staged and scored together on one GPU.
+struct Batch {
+    std::vector<AlnJob> jobs;
+    std::vector<uint8_t> codes;          // [column][leaf]
+    std::vector<int64_t> region_off{0};  // staged regions (whole frames in frame mode)
+    int64_t n_rec = 0;                   // candidate regions (= staged regions except in frame mode)
+};
+
 inline std::string status_exn(int32_t st) {
     if (st & PCSF_ST_NEG_T) return "Invalid_argument(\"CamlPaml.Q.to_Pt\")";
     if (st & (PCSF_ST_NEG_ENTRY | PCSF_ST_ROWSUM)) return "Failure(\"CamlPaml.Q.substitution matrix: expm(t*Q) failed its checks\")";
@@ -81,130 +92,40 @@ inline std::string status_exn(int32_t st) {
     return "";
 }
 
-class Driver {
+// One GPU: a compute context with the tree and models installed, and the three strategies over a Batch.
+class DeviceScorer {
   public:
-    Driver(const Options& o, const std::string& paramset_prefix) : opt(o) {
-        ps = load_paramset(paramset_prefix, o.species, o.strategy == STRAT_MLE || o.strategy == STRAT_FIXED);
+    DeviceScorer(const Options& o, const ParamSet& pset, int device) : opt(o), ps(pset) {
         n_leaves = ps.tree.n_leaves;
-        leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
-        leaf_set.insert(leaf_labels.begin(), leaf_labels.end());
-        if (o.strategy != STRAT_NOP) {
-            if (pcsf_create(o.device, &ctx) != PCSF_OK)
-                throw failure("phylocsf_b200: no usable CUDA device (there is no CPU fallback)");
-            const auto ch = ps.tree.children_array();
-            std::vector<double> bl(ps.tree.branches.begin(), ps.tree.branches.begin() + ps.tree.root());
-            check(pcsf_tree_set(ctx, n_leaves, ch.data(), bl.data()));
-            if (ps.have_ecm)
-                for (int w = 0; w < 2; w++)
-                    check(pcsf_model_set(ctx, w, ps.qd[w].S.data(), ps.qd[w].Sinv.data(), ps.qd[w].lam.data(), ps.qd[w].pi_eq.data()));
-            if (o.strategy == STRAT_FIXED) {
-                const double one = 1.0;
-                check(pcsf_pt_build(ctx, 0, 1, &one, nullptr));
-                check(pcsf_pt_build(ctx, 1, 1, &one, nullptr));
-            }
+        if (o.strategy == STRAT_NOP) return;
+        if (pcsf_create(device, &ctx) != PCSF_OK)
+            throw failure("phylocsf_b200: no usable CUDA device " + std::to_string(device) + " (there is no CPU fallback)");
+        const auto ch = ps.tree.children_array();
+        std::vector<double> bl(ps.tree.branches.begin(), ps.tree.branches.begin() + ps.tree.root());
+        check(pcsf_tree_set(ctx, n_leaves, ch.data(), bl.data()));
+        if (ps.have_ecm)
+            for (int w = 0; w < 2; w++)
+                check(pcsf_model_set(ctx, w, ps.qd[w].S.data(), ps.qd[w].Sinv.data(), ps.qd[w].lam.data(), ps.qd[w].pi_eq.data()));
+        if (o.strategy == STRAT_FIXED) {
+            const double one = 1.0;
+            check(pcsf_pt_build(ctx, 0, 1, &one, nullptr));
+            check(pcsf_pt_build(ctx, 1, 1, &one, nullptr));
         }
     }
-    ~Driver() {
+    ~DeviceScorer() {
         if (ctx) pcsf_destroy(ctx);
     }
-
-    // Everything of process_alignment that precedes scoring (src/PhyloCSF.ml:283-308,320), for one
-    // alignment: parse, sanity checks, leaf order, candidate regions, leaf codes. Thread-safe (reads
-    // only the immutable parts of the driver), so many alignments can be prepared in parallel.
-    struct Prepared {
-        AlnJob job;
-        std::vector<uint8_t> codes;
-        std::vector<int> region_cols;
-        std::string abort;  // non-empty: the alignment aborted with this Printexc text
-    };
-    Prepared prepare(const std::string& name, const std::vector<std::string>& lines) const {
-        Prepared p;
-        AlnJob& job = p.job;
-        job.name = name;
-        try {
-            Alignment a = input_mfa(lines);
-            if (opt.remove_ref_gaps) remove_ref_gaps(a.seqs);
-            for (auto& s : a.seqs)
-                for (auto& c : s) c = c == 'u' ? 't' : (c == 'U' ? 'T' : c);
-            if (!opt.allow_ref_gaps && a.seqs[0].find('-') != std::string::npos)
-                throw failure("the reference sequence (first alignment row) must be ungapped");
-            job.aln = a.seqs;
-            for (auto& s : a.seqs) job.rc_aln.push_back(revcomp(s));
-            std::set<std::string> wtf;
-            for (auto& sp : a.species)
-                if (!leaf_set.count(sp)) wtf.insert(sp);
-            if (!wtf.empty()) {
-                std::string m = "parameters not available for species:";
-                for (auto& s : wtf) m += " " + s;
-                throw failure(m);
-            }
-            for (size_t i = 0; i < a.species.size(); i++) job.which_row[a.species[i]] = (int)i;
-            job.regions = candidate_regions(job.aln[0], opt.orf, opt.frames, opt.min_codons);
-            if (job.regions.empty()) job.failure = "Failure(\"no sufficiently long ORFs found\")";
-        } catch (const HostError& e) {
-            p.abort = e.what();
-            return p;
-        }
-        std::vector<int> leaf_ord(n_leaves, -1);
-        for (int l = 0; l < n_leaves; l++) {
-            auto it = job.which_row.find(leaf_labels[l]);
-            if (it != job.which_row.end()) leaf_ord[l] = it->second;
-        }
-        if (!frame_mode()) {
-            for (const Region& r : job.regions)
-                p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, p.codes));
-            return p;
-        }
-        // Frame mode: under the fixed strategy every column's log-likelihood is independent of the region
-        // it is scored in, so nested / overlapping ORFs (ATGStop emits one ORF per upstream ATG of a stop)
-        // share columns. Stage each reading frame that holds a candidate once; ORF scores become
-        // segment sums of the per-column terms (SURVEY.md 8f.2).
-        int frame_slot[6] = {-1, -1, -1, -1, -1, -1};
-        const int hi_all = (int)job.aln[0].size() - 1;
-        for (const Region& r : job.regions) {
-            const int ofs = r.lo % 3, f = (r.rc ? 3 : 0) + ofs;
-            if (frame_slot[f] < 0) {
-                frame_slot[f] = (int)p.region_cols.size();
-                p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, ofs, hi_all, p.codes));
-            }
-            job.reg_frame.push_back(frame_slot[f]);
-            job.reg_col0.push_back((r.lo - ofs) / 3);
-            job.reg_ncols.push_back((r.hi - r.lo + 1) / 3);
-        }
-        return p;
-    }
+    DeviceScorer(const DeviceScorer&) = delete;
 
     bool frame_mode() const { return opt.strategy == STRAT_FIXED && opt.orf != AsIs; }
 
-    // Appends a prepared alignment to the current batch (in input order). Returns false when the run
-    // must stop (the alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
-    bool append(Prepared&& p, std::ostream& out) {
-        if (!p.abort.empty()) {
-            flush(out);
-            out << p.job.name << "\tabort\t" << p.abort << "\n";
-            out.flush();
-            return false;
-        }
-        p.job.first_region = (int64_t)region_off.size() - 1;
-        p.job.first_rec = n_rec;
-        n_rec += (int64_t)p.job.regions.size();
-        for (int nc : p.region_cols) region_off.push_back(region_off.back() + nc);
-        codes.insert(codes.end(), p.codes.begin(), p.codes.end());
-        jobs.push_back(std::move(p.job));
-        if (region_off.back() >= opt.batch_cols) flush(out);
-        return true;
-    }
-
-    bool add_alignment(const std::string& name, const std::vector<std::string>& lines, std::ostream& out) {
-        return append(prepare(name, lines), out);
-    }
-
-    void flush(std::ostream& out) {
-        if (jobs.empty()) return;
-        const int64_t R = (int64_t)region_off.size() - 1;
-        std::vector<ScoreRecord> rec(n_rec);
+    // Score every candidate region of the batch and render the report lines of its alignments.
+    std::string run(const Batch& b) {
+        cur = &b;
+        const int64_t R = (int64_t)b.region_off.size() - 1;
+        std::vector<ScoreRecord> rec(b.n_rec);
         if (R > 0) {
-            if (opt.strategy != STRAT_NOP) check(pcsf_batch_upload(ctx, R, region_off.data(), codes.data()));
+            if (opt.strategy != STRAT_NOP) check(pcsf_batch_upload(ctx, R, b.region_off.data(), b.codes.data()));
             switch (opt.strategy) {
                 case STRAT_FIXED: if (frame_mode()) score_fixed_frames(rec); else score_fixed(rec); break;
                 case STRAT_MLE: score_mle(rec); break;
@@ -212,26 +133,20 @@ class Driver {
                 case STRAT_NOP: break;
             }
         }
-        for (const AlnJob& j : jobs) report(j, rec, out);
-        jobs.clear();
-        codes.clear();
-        region_off.assign(1, 0);
-        n_rec = 0;
+        std::ostringstream out;
+        for (const AlnJob& j : b.jobs) report(j, rec, out);
+        cur = nullptr;
+        return out.str();
     }
 
-    int64_t evaluations = 0;  // likelihood evaluations (region x model) issued, for --debug statistics
+    int64_t evaluations = 0;  // likelihood evaluations (region x model) issued
 
   private:
     Options opt;
-    ParamSet ps;
+    const ParamSet& ps;
     pcsf_ctx* ctx = nullptr;
     int n_leaves = 0;
-    std::vector<std::string> leaf_labels;
-    std::set<std::string> leaf_set;
-    std::vector<AlnJob> jobs;
-    std::vector<uint8_t> codes;
-    std::vector<int64_t> region_off{0};
-    int64_t n_rec = 0;  // candidate regions in the current batch (= staged regions except in frame mode)
+    const Batch* cur = nullptr;
 
     void check(int rc) {
         if (rc != PCSF_OK && rc != PCSF_ERR_NUMERIC) throw failure(std::string("phylocsf_b200: ") + pcsf_last_error(ctx));
@@ -257,7 +172,7 @@ class Driver {
     // llr_FixedLik for ORF candidates from per-column terms of whole frames. The column sums run in
     // column order, as the reference's `lpr := !lpr +. log ...` does (src/PhyloCSFModel.ml:76-81).
     void score_fixed_frames(std::vector<ScoreRecord>& rec) {
-        const int64_t R = (int64_t)region_off.size() - 1, C = region_off.back();
+        const int64_t R = (int64_t)cur->region_off.size() - 1, C = cur->region_off.back();
         std::vector<double> lpr(2 * R), elpr(2 * R), clz[2], can[2];
         std::vector<int32_t> st(2 * R);
         const int32_t mids[2] = {0, 1};
@@ -268,13 +183,13 @@ class Driver {
             can[m].resize(C);
             check(pcsf_column_terms(ctx, m, clz[m].data(), can[m].data()));
         }
-        for (const AlnJob& j : jobs)
+        for (const AlnJob& j : cur->jobs)
             for (size_t k = 0; k < j.regions.size(); k++) {
                 ScoreRecord& rc = rec[j.first_rec + k];
                 const int64_t b = j.first_region + j.reg_frame[k];
                 const int32_t bad = (st[b] | st[R + b]) & ~PCSF_ST_NOT_FINITE;
                 if (bad) { rc.exn = status_exn(bad); continue; }
-                const int64_t c0 = region_off[b] + j.reg_col0[k];
+                const int64_t c0 = cur->region_off[b] + j.reg_col0[k];
                 double l[2] = {0.0, 0.0}, e[2] = {0.0, 0.0};
                 for (int m = 0; m < 2; m++)
                     for (int c = 0; c < j.reg_ncols[k]; c++) {
@@ -412,8 +327,8 @@ class Driver {
             in.rho = 1.0;
             long counts[3][4];
             for (auto& row : counts) for (auto& c : row) c = 1;
-            for (int64_t i = region_off[r] * n_leaves; i < region_off[r + 1] * n_leaves; i++) {
-                const int c = codes[i];
+            for (int64_t i = cur->region_off[r] * n_leaves; i < cur->region_off[r + 1] * n_leaves; i++) {
+                const int c = cur->codes[i];
                 if (c < 64) { counts[0][c / 16]++; counts[1][(c / 4) % 4]++; counts[2][c % 4]++; }
             }
             for (int p = 0; p < 3; p++)
@@ -498,6 +413,150 @@ class Driver {
         out.flush();
     }
 
+};
+
+// The driver proper: prepares alignments (host threads), groups them into batches, hands each batch to a
+// GPU (round-robin over the configured devices, scoring asynchronously while the next batch is being
+// prepared) and prints the report lines in input order.
+class Driver {
+  public:
+    Driver(const Options& o, const std::string& paramset_prefix, std::vector<int> devices = {}) : opt(o) {
+        ps = load_paramset(paramset_prefix, o.species, o.strategy == STRAT_MLE || o.strategy == STRAT_FIXED);
+        n_leaves = ps.tree.n_leaves;
+        leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
+        leaf_set.insert(leaf_labels.begin(), leaf_labels.end());
+        if (devices.empty()) devices.push_back(o.device);
+        if (o.strategy == STRAT_NOP) devices.resize(1);
+        for (int d : devices) dev.emplace_back(new DeviceScorer(o, ps, d));
+    }
+
+    bool frame_mode() const { return opt.strategy == STRAT_FIXED && opt.orf != AsIs; }
+
+    // Everything of process_alignment that precedes scoring (src/PhyloCSF.ml:283-308,320), for one
+    // alignment: parse, sanity checks, leaf order, candidate regions, leaf codes. Thread-safe (reads
+    // only the immutable parts of the driver), so many alignments can be prepared in parallel.
+    struct Prepared {
+        AlnJob job;
+        std::vector<uint8_t> codes;
+        std::vector<int> region_cols;
+        std::string abort;  // non-empty: the alignment aborted with this Printexc text
+    };
+    Prepared prepare(const std::string& name, const std::vector<std::string>& lines) const {
+        Prepared p;
+        AlnJob& job = p.job;
+        job.name = name;
+        try {
+            Alignment a = input_mfa(lines);
+            if (opt.remove_ref_gaps) remove_ref_gaps(a.seqs);
+            for (auto& s : a.seqs)
+                for (auto& c : s) c = c == 'u' ? 't' : (c == 'U' ? 'T' : c);
+            if (!opt.allow_ref_gaps && a.seqs[0].find('-') != std::string::npos)
+                throw failure("the reference sequence (first alignment row) must be ungapped");
+            job.aln = a.seqs;
+            for (auto& s : a.seqs) job.rc_aln.push_back(revcomp(s));
+            std::set<std::string> wtf;
+            for (auto& sp : a.species)
+                if (!leaf_set.count(sp)) wtf.insert(sp);
+            if (!wtf.empty()) {
+                std::string m = "parameters not available for species:";
+                for (auto& s : wtf) m += " " + s;
+                throw failure(m);
+            }
+            for (size_t i = 0; i < a.species.size(); i++) job.which_row[a.species[i]] = (int)i;
+            job.regions = candidate_regions(job.aln[0], opt.orf, opt.frames, opt.min_codons);
+            if (job.regions.empty()) job.failure = "Failure(\"no sufficiently long ORFs found\")";
+        } catch (const HostError& e) {
+            p.abort = e.what();
+            return p;
+        }
+        std::vector<int> leaf_ord(n_leaves, -1);
+        for (int l = 0; l < n_leaves; l++) {
+            auto it = job.which_row.find(leaf_labels[l]);
+            if (it != job.which_row.end()) leaf_ord[l] = it->second;
+        }
+        if (!frame_mode()) {
+            for (const Region& r : job.regions)
+                p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, r.lo, r.hi, p.codes));
+            return p;
+        }
+        // Frame mode: under the fixed strategy every column's log-likelihood is independent of the region
+        // it is scored in, so nested / overlapping ORFs (ATGStop emits one ORF per upstream ATG of a stop)
+        // share columns. Stage each reading frame that holds a candidate once; ORF scores become
+        // segment sums of the per-column terms (SURVEY.md 8f.2).
+        int frame_slot[6] = {-1, -1, -1, -1, -1, -1};
+        const int hi_all = (int)job.aln[0].size() - 1;
+        for (const Region& r : job.regions) {
+            const int ofs = r.lo % 3, f = (r.rc ? 3 : 0) + ofs;
+            if (frame_slot[f] < 0) {
+                frame_slot[f] = (int)p.region_cols.size();
+                p.region_cols.push_back(pleaves(n_leaves, leaf_ord, r.rc ? job.rc_aln : job.aln, ofs, hi_all, p.codes));
+            }
+            job.reg_frame.push_back(frame_slot[f]);
+            job.reg_col0.push_back((r.lo - ofs) / 3);
+            job.reg_ncols.push_back((r.hi - r.lo + 1) / 3);
+        }
+        return p;
+    }
+
+    // Appends a prepared alignment to the current batch (in input order). Returns false when the run
+    // must stop (the alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
+    bool append(Prepared&& p, std::ostream& out) {
+        if (!p.abort.empty()) {
+            finish(out);
+            out << p.job.name << "\tabort\t" << p.abort << "\n";
+            out.flush();
+            return false;
+        }
+        p.job.first_region = (int64_t)batch.region_off.size() - 1;
+        p.job.first_rec = batch.n_rec;
+        batch.n_rec += (int64_t)p.job.regions.size();
+        for (int nc : p.region_cols) batch.region_off.push_back(batch.region_off.back() + nc);
+        batch.codes.insert(batch.codes.end(), p.codes.begin(), p.codes.end());
+        batch.jobs.push_back(std::move(p.job));
+        if (batch.region_off.back() >= opt.batch_cols) flush(out);
+        return true;
+    }
+
+    bool add_alignment(const std::string& name, const std::vector<std::string>& lines, std::ostream& out) {
+        return append(prepare(name, lines), out);
+    }
+
+    // Hand the current batch to the next GPU; at most one batch per device is in flight.
+    void flush(std::ostream& out) {
+        if (batch.jobs.empty()) return;
+        if (inflight.size() >= dev.size()) drain_one(out);
+        auto b = std::make_shared<Batch>(std::move(batch));
+        batch = Batch();
+        DeviceScorer* d = dev[next_dev++ % dev.size()].get();  // the oldest in-flight batch ran on this device: it is free
+        inflight.push_back(std::async(std::launch::async, [d, b]() { return d->run(*b); }));
+    }
+    // Wait for everything in flight and print it (end of input, or before an abort line).
+    void finish(std::ostream& out) {
+        flush(out);
+        while (!inflight.empty()) drain_one(out);
+    }
+    int64_t evaluations() const {
+        int64_t n = 0;
+        for (auto& d : dev) n += d->evaluations;
+        return n;
+    }
+
+  private:
+    Options opt;
+    ParamSet ps;
+    int n_leaves = 0;
+    std::vector<std::string> leaf_labels;
+    std::set<std::string> leaf_set;
+    std::vector<std::unique_ptr<DeviceScorer>> dev;
+    Batch batch;
+    std::deque<std::future<std::string>> inflight;
+    size_t next_dev = 0;
+
+    void drain_one(std::ostream& out) {
+        out << inflight.front().get();
+        out.flush();
+        inflight.pop_front();
+    }
 };
 
 }  // namespace host

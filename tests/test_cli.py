@@ -195,3 +195,24 @@ def test_omega_100vertebrates_species_subset(params_base, tmp_path):
     want = run_oracle(params_base, "100vertebrates", str(path), path.read_text().split("\n")[:-1], strategy="omega", frames=3,
                       all_scores=True, species=sp)
     same_lines(got, want)
+
+
+@pytest.mark.gpu
+def test_multi_device_dispatch_keeps_order(params_base, monkeypatch):
+    """Batches go round-robin over the configured devices and are scored asynchronously; the output must
+    be identical to a single-context run. PCSF_DEVICES=0,0 exercises the dispatcher on a one-GPU box (two
+    contexts on the same device); with more GPUs visible, 'all' is checked as well."""
+    import ctypes
+
+    files = [ex(params_base, "ALDH2.exon5.fa")] * 9
+    flags = ["--strategy=mle", "--frames=3", "--allScores", "--ancComp"]
+    one = run_cli(params_base, "29mammals", files, *flags)
+    monkeypatch.setenv("PCSF_BATCH_COLS", "150")  # ~1 alignment per batch
+    monkeypatch.setenv("PCSF_DEVICES", "0,0")
+    two = run_cli(params_base, "29mammals", files, *flags)
+    assert two == one
+    from phylocsf_b200 import _native as N
+
+    if N.load().pcsf_device_count() >= 2:
+        monkeypatch.setenv("PCSF_DEVICES", "all")
+        assert run_cli(params_base, "29mammals", files, *flags) == one
