@@ -10,6 +10,8 @@
 //                            (lib/CamlPaml/PhyloLik.ml:73-93,127-138; src/PhyloCSFModel.ml:76-81)
 //   K4  region_reduce_kernel per-region sums of the per-column terms (src/PhyloCSFModel.ml:79-81)
 //   K0  frame_codes_kernel   pleaves on the device (src/PhyloCSF.ml:219-246) from nucleotide rows
+//   K5  omega_eig_kernel     omega-model rate matrix assembly + batched Jacobi diagonalisation
+//                            (src/OmegaModel.ml:21-80, lib/CamlPaml/Q.ml:124-177)
 //
 // FP64 tensor path on sm_100a is warp-level mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4); tcgen05 has no
 // f64 kind. Operand staging uses TMA bulk copies (cp.async.bulk, SASS UBLKCP) + mbarriers.
