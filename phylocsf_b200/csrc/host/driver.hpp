@@ -287,12 +287,17 @@ class DeviceScorer {
             } else {
                 for (int64_t i = 0; i < n; i++) { pair_model[i] = (int32_t)live[i]; pair_scale[i] = xs[i]; }
             }
-            for (int64_t i = 0; i < n; i++) eval_pair[i] = i;
             pstat.assign(n, 0);
             estat.assign(n, 0);
             lpr.assign(n, 0.0);
-            check(pcsf_pt_build_pairs(ctx, n, pair_model.data(), pair_scale.data(), pstat.data()));
-            check(pcsf_lpr_pairs(ctx, n, eval_pair.data(), live.data(), lpr.data(), nullptr, estat.data()));
+            // one P set per candidate: keep the tables of one launch sequence under ~16 GiB
+            const int64_t max_sets = std::max<int64_t>(1, (int64_t)((16ull << 30) / ((size_t)(2 * n_leaves - 2) * 65 * 64 * 8)));
+            for (int64_t c0 = 0; c0 < n; c0 += max_sets) {
+                const int64_t nc = std::min(max_sets, n - c0);
+                for (int64_t i = 0; i < nc; i++) eval_pair[c0 + i] = i;
+                check(pcsf_pt_build_pairs(ctx, nc, pair_model.data() + c0, pair_scale.data() + c0, pstat.data() + c0));
+                check(pcsf_lpr_pairs(ctx, nc, eval_pair.data() + c0, live.data() + c0, lpr.data() + c0, nullptr, estat.data() + c0));
+            }
             evaluations += n;
             for (int64_t i = 0; i < n; i++) {
                 const int64_t r = live[i];
