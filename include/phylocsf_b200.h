@@ -184,6 +184,13 @@ int pcsf_maximize_lpr(pcsf_ctx *ctx, int model_id, double init, double lo, doubl
                       double *out_rho, double *out_lpr, double *out_elpr_anc, int32_t *out_status,
                       int32_t *out_nevals);
 
+/* The same for several models at once (llr_MaxLik maximises the coding and the noncoding model,
+ * src/PhyloCSFModel.ml:130-136): all (region, model) searches advance in the same rounds, so every
+ * launch sequence carries n_models times the work. out_* are indexed [m * nregions + region]. */
+int pcsf_maximize_lpr_multi(pcsf_ctx *ctx, int n_models, const int32_t *model_ids, double init, double lo, double hi,
+                            double accuracy, double *out_rho, double *out_lpr, double *out_elpr_anc,
+                            int32_t *out_status, int32_t *out_nevals);
+
 /* Timing of the most recent call, measured with CUDA events on the context's stream:
  * which = 0 pruning kernel (K2+K3 fused), 1 region reduction (K4), 2 P(t) build (K1),
  * 3 H2D copies, 4 D2H copies. Returns milliseconds, or a negative value if not recorded. */

@@ -13,7 +13,7 @@ SYMBOLS = [
     "pcsf_version", "pcsf_device_count", "pcsf_create", "pcsf_destroy", "pcsf_last_error", "pcsf_stream_set", "pcsf_option_set",
     "pcsf_tree_set", "pcsf_model_set", "pcsf_pt_build", "pcsf_pt_get", "pcsf_batch_upload",
     "pcsf_batch_upload_alignments", "pcsf_batch_nregions", "pcsf_batch_ncols", "pcsf_lpr_all", "pcsf_score_alignments", "pcsf_lpr",
-    "pcsf_models_set", "pcsf_omega_models_set", "pcsf_model_get", "pcsf_pt_build_pairs", "pcsf_lpr_pairs", "pcsf_column_terms", "pcsf_maximize_lpr", "pcsf_last_ms", "pcsf_launch_count",
+    "pcsf_models_set", "pcsf_omega_models_set", "pcsf_model_get", "pcsf_pt_build_pairs", "pcsf_lpr_pairs", "pcsf_column_terms", "pcsf_maximize_lpr", "pcsf_maximize_lpr_multi", "pcsf_last_ms", "pcsf_launch_count",
 ]
 
 PCSF_OK = 0
@@ -65,6 +65,7 @@ def load():
     L.pcsf_lpr_pairs.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.pcsf_column_terms.argtypes = [vp, ctypes.c_int, vp, vp]
     L.pcsf_maximize_lpr.argtypes = [vp, ctypes.c_int, dbl, dbl, dbl, dbl, vp, vp, vp, vp, vp]
+    L.pcsf_maximize_lpr_multi.argtypes = [vp, ctypes.c_int, vp, dbl, dbl, dbl, dbl, vp, vp, vp, vp, vp]
     L.pcsf_last_ms.argtypes = [vp, ctypes.c_int]
     L.pcsf_last_ms.restype = dbl
     L.pcsf_launch_count.argtypes = [vp]

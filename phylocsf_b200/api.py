@@ -179,6 +179,15 @@ class Context:
                                               N.ptr(elpr), N.ptr(st), N.ptr(ne)), ok_numeric=not check)
         return rho, lpr, elpr, st, ne
 
+    def maximize_lpr_multi(self, model_ids, init=1.0, lo=1e-2, hi=10.0, accuracy=0.01, check=True):
+        mids = np.ascontiguousarray(model_ids, dtype=np.int32)
+        m, R = mids.size, self.nregions
+        rho, lpr, elpr = np.empty((m, R)), np.empty((m, R)), np.empty((m, R))
+        st, ne = np.zeros((m, R), dtype=np.int32), np.zeros((m, R), dtype=np.int32)
+        self._check(self._L.pcsf_maximize_lpr_multi(self._h, m, N.ptr(mids), init, lo, hi, accuracy, N.ptr(rho), N.ptr(lpr),
+                                                    N.ptr(elpr), N.ptr(st), N.ptr(ne)), ok_numeric=not check)
+        return rho, lpr, elpr, st, ne
+
     def last_ms(self, which):
         return float(self._L.pcsf_last_ms(self._h, which))
 

@@ -205,13 +205,14 @@ class DeviceScorer {
     // ---- PhyloCSFModel.llr_MaxLik ~init:1. (src/PhyloCSFModel.ml:130-136) ----
     void score_mle(std::vector<ScoreRecord>& rec) {
         const int64_t R = (int64_t)rec.size();
-        std::vector<double> rho[2], lpr[2], elpr[2];
-        std::vector<int32_t> st[2], ne[2];
-        for (int m = 0; m < 2; m++) {
-            rho[m].resize(R); lpr[m].resize(R); elpr[m].resize(R); st[m].resize(R); ne[m].resize(R);
-            check(pcsf_maximize_lpr(ctx, m, 1.0, 1e-2, 10.0, 0.01, rho[m].data(), lpr[m].data(), elpr[m].data(), st[m].data(), ne[m].data()));
-            for (int64_t r = 0; r < R; r++) evaluations += ne[m][r];
-        }
+        std::vector<double> rho2(2 * R), lpr2(2 * R), elpr2(2 * R);
+        std::vector<int32_t> st2(2 * R), ne2(2 * R);
+        const int32_t mids[2] = {0, 1};
+        check(pcsf_maximize_lpr_multi(ctx, 2, mids, 1.0, 1e-2, 10.0, 0.01, rho2.data(), lpr2.data(), elpr2.data(), st2.data(), ne2.data()));
+        for (int64_t i = 0; i < 2 * R; i++) evaluations += ne2[i];
+        const double *rho[2] = {rho2.data(), rho2.data() + R}, *lpr[2] = {lpr2.data(), lpr2.data() + R},
+                     *elpr[2] = {elpr2.data(), elpr2.data() + R};
+        const int32_t* st[2] = {st2.data(), st2.data() + R};
         for (int64_t r = 0; r < R; r++) {
             const int32_t b0 = st[0][r] & ~PCSF_ST_RANDOM_INIT, b1 = st[1][r] & ~PCSF_ST_RANDOM_INIT;
             if (b0 || b1) { rec[r].exn = status_exn(b0 ? b0 : b1); continue; }  // coding model is maximised first

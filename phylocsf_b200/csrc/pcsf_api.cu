@@ -1008,94 +1008,90 @@ int pcsf_column_terms(pcsf_ctx* ctx, int m, double* col_logz, double* col_anc) {
 // (lo, hi, init, Brent's first golden-section point, find_init's fixed random stream) share one
 // P set and run as a single span over the whole batch.
 // -------------------------------------------------------------------------------------------------
-int pcsf_maximize_lpr(pcsf_ctx* ctx, int model_id, double init, double lo, double hi, double accuracy,
-                      double* out_rho, double* out_lpr, double* out_elpr_anc, int32_t* out_status,
-                      int32_t* out_nevals) {
+int pcsf_maximize_lpr_multi(pcsf_ctx* ctx, int n_models, const int32_t* model_ids, double init, double lo, double hi,
+                            double accuracy, double* out_rho, double* out_lpr, double* out_elpr_anc, int32_t* out_status,
+                            int32_t* out_nevals) {
     TRY(check_ready(ctx, true));
-    if (model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set)
-        return fail(ctx, PCSF_ERR_STATE, "pcsf_maximize_lpr: model not set");
+    if (n_models < 1 || !model_ids) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_maximize_lpr: no models");
+    for (int m = 0; m < n_models; m++)
+        if (model_ids[m] < 0 || model_ids[m] >= (int)ctx->models.size() || !ctx->models[model_ids[m]].set)
+            return fail(ctx, PCSF_ERR_STATE, "pcsf_maximize_lpr: model not set");
     if (!out_rho || !out_lpr) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_maximize_lpr: null output");
     if (lo >= hi || lo <= 0.0) return fail(ctx, PCSF_ERR_INVALID_ARG, "CamlPaml.Fit.find_init");  // Fit.ml:28
     CU(cudaSetDevice(ctx->device));
-    const int64_t R = ctx->nregions;
-    Model& m = ctx->models[model_id];
-    std::vector<MaximizeLpr> st((size_t)R, MaximizeLpr(init, lo, hi, accuracy));
-    std::vector<double> lpr(R), elpr(R);
-    std::vector<int32_t> status(R);
-    // candidates of a round
-    std::vector<int64_t> live;
-    std::vector<double> xs;
-    std::vector<double> uniq;
-    std::vector<int32_t> e_model, e_scale;
-    std::vector<int64_t> e_region;
-    std::vector<double> r_lpr, r_elpr;
-    std::vector<int32_t> r_status;
-    // bound the P tables of one launch to ~16 GiB
+    const int64_t R = ctx->nregions, N = R * n_models;
+    std::vector<MaximizeLpr> st((size_t)N, MaximizeLpr(init, lo, hi, accuracy));  // [model][region]
+    // candidates of a round, model-major so that candidates common to all regions of a model share one P set
+    std::vector<int64_t> live, e_pair, e_region;
+    std::vector<double> xs, pair_scale, r_lpr, r_elpr;
+    std::vector<int32_t> pair_model, r_status, p_status;
+    // bound the P tables of one launch sequence to ~16 GiB
     const size_t pset_bytes = (size_t)ctx->n_branches * PT_SLOT_BYTES;
     const int64_t max_sets = std::max<int64_t>(1, (int64_t)((16ull << 30) / pset_bytes));
     double ms_prune = 0, ms_reduce = 0, ms_pt = 0;
     for (;;) {
         live.clear();
         xs.clear();
-        for (int64_t r = 0; r < R; r++)
-            if (!st[r].done()) {
-                live.push_back(r);
-                xs.push_back(st[r].candidate());
+        for (int64_t i = 0; i < N; i++)
+            if (!st[i].done()) {
+                live.push_back(i);
+                xs.push_back(st[i].candidate());
             }
         if (live.empty()) break;
-        for (size_t c0 = 0; c0 < live.size(); c0 += (size_t)max_sets) {
-            const size_t c1 = std::min(live.size(), c0 + (size_t)max_sets);
-            // unique scales of this chunk, in first-appearance order (keeps common candidates in one span)
-            uniq.clear();
-            e_model.clear();
-            e_scale.clear();
+        size_t c0 = 0;
+        while (c0 < live.size()) {
+            pair_model.clear();
+            pair_scale.clear();
+            e_pair.clear();
             e_region.clear();
-            {
-                std::vector<std::pair<double, int>> seen;  // small when candidates are common
-                double last_x = std::nan("");
-                int last_i = -1;
-                for (size_t i = c0; i < c1; i++) {
-                    const double x = xs[i];
-                    int idx;
-                    if (x == last_x) idx = last_i;
-                    else {
-                        idx = (int)uniq.size();
-                        uniq.push_back(x);
-                    }
-                    last_x = x;
-                    last_i = idx;
-                    e_model.push_back(model_id);
-                    e_scale.push_back(idx);
-                    e_region.push_back(live[i]);
+            size_t c1 = c0;
+            for (; c1 < live.size(); c1++) {
+                const int32_t mid = model_ids[live[c1] / R];
+                const double x = xs[c1];
+                if (pair_model.empty() || pair_model.back() != mid || pair_scale.back() != x) {
+                    if ((int64_t)pair_model.size() >= max_sets) break;
+                    pair_model.push_back(mid);
+                    pair_scale.push_back(x);
                 }
+                e_pair.push_back((int64_t)pair_model.size() - 1);
+                e_region.push_back(live[c1] % R);
             }
-            TRY(pt_build_device(ctx, m, (int)uniq.size(), uniq.data()));
+            const int64_t np = (int64_t)pair_model.size(), ne = (int64_t)e_region.size();
+            p_status.assign(np, 0);
+            const int rc = pcsf_pt_build_pairs(ctx, np, pair_model.data(), pair_scale.data(), p_status.data());
+            if (rc != PCSF_OK && rc != PCSF_ERR_NUMERIC) return rc;
             ms_pt += ctx->ms[2];
-            const int64_t ne = (int64_t)e_region.size();
             r_lpr.resize(ne);
             r_elpr.resize(ne);
             r_status.resize(ne);
-            TRY(pcsf_lpr(ctx, ne, e_model.data(), e_scale.data(), e_region.data(), r_lpr.data(), r_elpr.data(), r_status.data()));
+            TRY(pcsf_lpr_pairs(ctx, ne, e_pair.data(), e_region.data(), r_lpr.data(), r_elpr.data(), r_status.data()));
             ms_prune += ctx->ms[0];
             ms_reduce += ctx->ms[1];
             for (int64_t i = 0; i < ne; i++) st[live[c0 + i]].feed(r_lpr[i], r_elpr[i], r_status[i]);
+            c0 = c1;
         }
     }
     bool bad = false;
-    for (int64_t r = 0; r < R; r++) {
-        out_rho[r] = st[r].result_x;
-        out_lpr[r] = st[r].result_f;
-        if (out_elpr_anc) out_elpr_anc[r] = st[r].result_elpr;
-        if (out_status) out_status[r] = st[r].status;
-        if (out_nevals) out_nevals[r] = st[r].nevals;
-        bad |= (st[r].status & ~PCSF_ST_RANDOM_INIT) != 0;
+    for (int64_t i = 0; i < N; i++) {
+        out_rho[i] = st[i].result_x;
+        out_lpr[i] = st[i].result_f;
+        if (out_elpr_anc) out_elpr_anc[i] = st[i].result_elpr;
+        if (out_status) out_status[i] = st[i].status;
+        if (out_nevals) out_nevals[i] = st[i].nevals;
+        bad |= (st[i].status & ~PCSF_ST_RANDOM_INIT) != 0;
     }
     ctx->ms[0] = ms_prune;
     ctx->ms[1] = ms_reduce;
     ctx->ms[2] = ms_pt;
-    m.nscales = 0;  // the candidate tables are scratch
     if (bad) return fail(ctx, PCSF_ERR_NUMERIC, "maximize_lpr failed for at least one region (see status)");
     return PCSF_OK;
+}
+
+int pcsf_maximize_lpr(pcsf_ctx* ctx, int model_id, double init, double lo, double hi, double accuracy,
+                      double* out_rho, double* out_lpr, double* out_elpr_anc, int32_t* out_status,
+                      int32_t* out_nevals) {
+    const int32_t mid = model_id;
+    return pcsf_maximize_lpr_multi(ctx, 1, &mid, init, lo, hi, accuracy, out_rho, out_lpr, out_elpr_anc, out_status, out_nevals);
 }
 
 #ifdef PCSF_TIMELINE

@@ -222,6 +222,25 @@ def test_mle_simulated_120mammals(params_base):
     ctx.close()
 
 
+def test_mle_multi_model_equals_per_model_calls(params_base):
+    """pcsf_maximize_lpr_multi (coding and noncoding searches advanced in the same rounds, as
+    llr_MaxLik needs both, src/PhyloCSFModel.ml:130-136) returns bit-identical results to one
+    pcsf_maximize_lpr call per model, in either model order."""
+    ps = H.oracle_paramset(params_base, "29mammals")
+    rng = np.random.default_rng(23)
+    regs = [o.simulate_columns(ps.model.coding_model.model(r), n, rng) for r, n in ((0.5, 31), (1.0, 9), (2.0, 64), (1.3, 1))]
+    ctx = H.make_context(ps)
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    single = [ctx.maximize_lpr(m) for m in (0, 1)]
+    for order in ((0, 1), (1, 0)):
+        multi = ctx.maximize_lpr_multi(list(order))
+        for k, m in enumerate(order):
+            for a, b in zip(single[m], multi):
+                assert (a == b[k]).all(), (order, m)
+    ctx.close()
+
+
 def test_mle_boundary_and_flat_regions(params_base):
     """Regions whose likelihood is monotone in rho: identical sequences (best rho -> lower bound) make
     find_init exhaust its 250 random tries and return the boundary (Fit.ml:42-47); the device driver

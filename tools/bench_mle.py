@@ -48,13 +48,22 @@ torch.cuda.synchronize()
 t0 = time.perf_counter()
 tot_evals = 0
 ms = {"pt_build": 0.0, "prune": 0.0, "reduce": 0.0}
-for m in (0, 1):
-    rho, lpr, elpr, st, ne = ctx.maximize_lpr(m)
+if os.environ.get("PCSF_MLE_PER_MODEL"):  # one call per model (the older path), for comparison
+    for m in (0, 1):
+        rho, lpr, elpr, st, ne = ctx.maximize_lpr(m)
+        tot_evals += int(ne.sum())
+        ms["prune"] += ctx.last_ms(0)
+        ms["reduce"] += ctx.last_ms(1)
+        ms["pt_build"] += ctx.last_ms(2)
+        res[m] = (rho, lpr, st)
+else:  # both models' searches advance in the same rounds (what the command line does)
+    rho, lpr, elpr, st, ne = ctx.maximize_lpr_multi([0, 1])
     tot_evals += int(ne.sum())
     ms["prune"] += ctx.last_ms(0)
     ms["reduce"] += ctx.last_ms(1)
     ms["pt_build"] += ctx.last_ms(2)
-    res[m] = (rho, lpr, st)
+    for m in (0, 1):
+        res[m] = (rho[m], lpr[m], st[m])
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 score = (10 / np.log(10)) * (res[0][1] - res[1][1])
