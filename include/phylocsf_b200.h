@@ -115,6 +115,12 @@ int pcsf_batch_upload(pcsf_ctx *ctx, int64_t nregions, const int64_t *region_off
  */
 int pcsf_batch_upload_alignments(pcsf_ctx *ctx, int64_t nalign, const int64_t *aln_off, const int32_t *aln_len,
                                  const uint8_t *nt, int frames);
+/* The same with the nucleotide buffer given as `nparts` host pieces; aln_off[] are offsets into their
+ * concatenation (an alignment must lie inside one piece). Lets a multi-threaded reader hand over the
+ * buffers its threads filled without first copying them into one. */
+int pcsf_batch_upload_alignments_parts(pcsf_ctx *ctx, int64_t nalign, const int64_t *aln_off, const int32_t *aln_len,
+                                       int64_t nparts, const uint8_t *const *part_ptr, const int64_t *part_bytes,
+                                       int frames);
 int64_t pcsf_batch_nregions(const pcsf_ctx *ctx);
 int64_t pcsf_batch_ncols(const pcsf_ctx *ctx);
 

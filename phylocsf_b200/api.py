@@ -92,6 +92,19 @@ class Context:
         self._check(self._L.pcsf_batch_upload_alignments(self._h, ao.size, N.ptr(ao), N.ptr(al), N.ptr(nt), frames))
         self.nregions = int(self._L.pcsf_batch_nregions(self._h))
 
+    def batch_upload_alignments_parts(self, aln_off, aln_len, parts, frames):
+        """pcsf_batch_upload_alignments_parts: the nucleotide buffer as a list of uint8 arrays; aln_off are
+        offsets into their concatenation."""
+        import ctypes
+        ao = np.ascontiguousarray(aln_off, dtype=np.int64)
+        al = np.ascontiguousarray(aln_len, dtype=np.int32)
+        parts = [np.ascontiguousarray(q, dtype=np.uint8) for q in parts]
+        ptrs = (ctypes.c_void_p * max(1, len(parts)))(*[q.ctypes.data for q in parts])
+        nbytes = np.array([q.size for q in parts], dtype=np.int64)
+        self._check(self._L.pcsf_batch_upload_alignments_parts(self._h, ao.size, N.ptr(ao), N.ptr(al), len(parts),
+                                                                ctypes.cast(ptrs, ctypes.c_void_p), N.ptr(nbytes), frames))
+        self.nregions = int(self._L.pcsf_batch_nregions(self._h))
+
     @property
     def ncols(self):
         return int(self._L.pcsf_batch_ncols(self._h))

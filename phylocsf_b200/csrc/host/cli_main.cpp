@@ -1,11 +1,17 @@
 // cli_main.cpp — `PhyloCSF parameter_set [file1 file2 ...] [options]`: the reference's command line
 // (src/PhyloCSF.ml:17-49,469-491) over the B200 compute library. Same options, same output lines.
+#include <fcntl.h>
+#include <malloc.h>
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <iterator>
+#include <mutex>
 
 #include "driver.hpp"
 
@@ -43,6 +49,23 @@ static std::string lower(std::string s) {
     std::exit(255);  // exit (-1)
 }
 
+// Whole file into `buf` (kept at its high-water size by the caller, so nothing is allocated or cleared per
+// file); `len` = bytes read. False if the file cannot be opened.
+static bool read_file(const std::string& fn, std::vector<char>& buf, size_t& len) {
+    const int fd = open(fn.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    if (buf.size() < (1u << 16)) buf.resize(1u << 16);
+    len = 0;
+    for (;;) {
+        if (len == buf.size()) buf.resize(buf.size() * 2);
+        const ssize_t r = read(fd, buf.data() + len, buf.size() - len);
+        if (r <= 0) break;
+        len += (size_t)r;
+    }
+    close(fd);
+    return true;
+}
+
 static std::vector<std::string> read_lines(std::istream& in) {
     std::vector<std::string> lines;
     std::string ln;
@@ -51,6 +74,11 @@ static std::vector<std::string> read_lines(std::istream& in) {
 }
 
 int main(int argc, char** argv) {
+    // The reader threads allocate and the appender frees tens of KB per alignment: keep freed memory in the
+    // process instead of trimming and re-faulting it (both serialise the threads on the address-space lock).
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 64 << 20);
     Options opt;
     std::vector<std::string> pos;
     for (int i = 1; i < argc; i++) {
@@ -162,58 +190,123 @@ int main(int argc, char** argv) {
             fns.push_back("");
         } else fns = fns_input;
 
-        // Files are read and prepared (parse, checks, regions, leaf codes) by a pool of host threads, a
-        // block at a time, and appended to the GPU batch in input order. The reference's -p N forked
-        // per-region workers; here N only caps the host threads (default: all cores).
+        // Files are read and prepared (parse, checks, regions, nucleotide rows or leaf codes) by a pool of host
+        // threads and appended to the GPU batch in input order by this thread: an ordered pipeline over chunks
+        // of files, with a bounded window so that the readers run ahead of the appender but not away from it.
+        // The reference's -p N forked per-region workers; here N only caps the host threads (default: all cores).
         struct Slot {
             Driver::Prepared prep;
             bool missing = false;
         };
+        struct Chunk {
+            std::vector<Slot> slots;
+            std::shared_ptr<std::vector<uint8_t>> nt;  // nucleotide rows of the chunk's alignments (fast form): handed to the batch, not copied
+        };
         unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
         if (opt.procs > 1) nthreads = (unsigned)opt.procs;
         if (const char* t = std::getenv("PCSF_HOST_THREADS")) nthreads = std::max(1, std::atoi(t));
-        const size_t block = 64 * (size_t)nthreads;
-        for (size_t b0 = 0; b0 < fns.size(); b0 += block) {
-            const size_t b1 = std::min(fns.size(), b0 + block);
-            std::vector<Slot> slots(b1 - b0);
-            std::atomic<size_t> next{b0};
-            auto work = [&]() {
-                for (;;) {
-                    const size_t i = next.fetch_add(1);
-                    if (i >= b1) return;
-                    const std::string& fn = fns[i];
-                    const std::string name = fn.empty() ? "(STDIN)" : fn;
-                    std::vector<std::string> lines;
-                    if (fn.empty() && from_stdin) lines = read_lines(std::cin);
-                    else {
-                        std::ifstream in(fn);
-                        if (!in) {
-                            slots[i - b0].missing = true;
-                            slots[i - b0].prep.job.name = name;
-                            continue;
-                        }
-                        lines = read_lines(in);
-                    }
-                    slots[i - b0].prep = drv.prepare(name, lines);
-                }
-            };
-            const unsigned nt = (unsigned)std::min<size_t>(nthreads, b1 - b0);
-            if (nt <= 1) work();
-            else {
-                std::vector<std::thread> pool;
-                for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
-                for (auto& t : pool) t.join();
+        const size_t n_files = fns.size();
+        const size_t chunk = 32, n_chunks = (n_files + chunk - 1) / chunk;
+        const size_t window = std::max<size_t>(4, 4 * (size_t)nthreads);  // chunks in flight
+        std::vector<Chunk> ring(window);
+        BufferPool nt_pool;
+        std::vector<char> ready(window, 0);
+        std::mutex mu;
+        std::condition_variable cv_ready, cv_space;
+        size_t next_chunk = 0, consumed = 0;  // under mu
+        bool stop = false;
+        auto prepare_one = [&](size_t i, Slot& sl, std::vector<uint8_t>& nt_buf) {
+            const std::string& fn = fns[i];
+            const std::string name = fn.empty() ? "(STDIN)" : fn;
+            static thread_local std::vector<char> text;  // reused: no allocation per file
+            size_t len = 0;
+            if (fn.empty() && from_stdin) {
+                text.assign(std::istreambuf_iterator<char>(std::cin), std::istreambuf_iterator<char>());
+                len = text.size();
+            } else if (!read_file(fn, text, len)) {
+                sl.missing = true;
+                sl.prep.job.name = name;
+                return;
             }
-            for (size_t i = b0; i < b1; i++) {
-                Slot& sl = slots[i - b0];
+            sl.prep = drv.prepare_text(name, text.data(), len, nt_buf);
+        };
+        auto work = [&]() {
+            Chunk ch;
+            size_t nt_hint = 0;  // bytes the previous chunks needed: reserve once instead of growing
+            for (;;) {
+                size_t c;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_space.wait(lk, [&] { return stop || next_chunk >= n_chunks || next_chunk < consumed + window; });
+                    if (stop || next_chunk >= n_chunks) return;
+                    c = next_chunk++;
+                }
+                ch.slots.clear();
+                ch.slots.resize(std::min(chunk, n_files - c * chunk));
+                ch.nt = nt_pool.get();
+                if (ch.nt->capacity() < nt_hint) ch.nt->reserve(nt_hint);
+                for (size_t k = 0; k < ch.slots.size(); k++) prepare_one(c * chunk + k, ch.slots[k], *ch.nt);
+                nt_hint = std::max(nt_hint, ch.nt->size() + ch.nt->size() / 8);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    ring[c % window] = std::move(ch);
+                    ready[c % window] = 1;
+                }
+                ch = Chunk();
+                cv_ready.notify_all();
+            }
+        };
+        std::vector<std::thread> pool;
+        const unsigned nt = (unsigned)std::min<size_t>(nthreads, std::max<size_t>(1, n_chunks));
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+        auto shut = [&]() {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                stop = true;
+            }
+            cv_space.notify_all();
+            for (auto& t : pool) t.join();
+        };
+        const bool host_profile = std::getenv("PCSF_HOST_PROFILE") != nullptr;  // where the appender's time goes, on stderr
+        double t_wait = 0, t_append = 0;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        for (size_t c = 0; c < n_chunks; c++) {
+            Chunk ch;
+            const double t0 = now();
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_ready.wait(lk, [&] { return ready[c % window] != 0; });
+                ch = std::move(ring[c % window]);
+                ring[c % window] = Chunk();
+                ready[c % window] = 0;
+                consumed = c + 1;
+            }
+            std::vector<Slot>& slots = ch.slots;
+            cv_space.notify_all();
+            const double t1 = now();
+            t_wait += t1 - t0;
+            for (size_t k = 0; k < slots.size(); k++) {
+                Slot& sl = slots[k];
                 if (sl.missing) {
+                    shut();
                     drv.finish(std::cout);
-                    std::cout << sl.prep.job.name << "\tabort\tSys_error(\"" << fns[i] << ": No such file or directory\")\n";
+                    std::cout << sl.prep.job.name << "\tabort\tSys_error(\"" << fns[c * chunk + k] << ": No such file or directory\")\n";
                     std::cout.flush();
                     return 255;
                 }
-                if (!drv.append(std::move(sl.prep), std::cout)) return 255;
+                if (!drv.append(std::move(sl.prep), std::cout, ch.nt)) {
+                    shut();
+                    return 255;
+                }
             }
+            t_append += now() - t1;
+        }
+        shut();
+        if (host_profile) {
+            const double t2 = now();
+            drv.finish(std::cout);
+            std::cerr << "host profile: waited for readers " << t_wait << " s, appended (incl. batch hand-off) " << t_append
+                      << " s, final drain " << now() - t2 << " s, " << nt << " reader threads\n";
         }
         drv.finish(std::cout);
     } catch (const std::exception& e) {

@@ -7,6 +7,9 @@
 // The reference evaluates one region at a time; here the regions of many alignments are staged as
 // one batch (pcsf_batch_upload) and every strategy advances all of them together.
 #pragma once
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +17,7 @@
 #include <fstream>
 #include <future>
 #include <memory>
+#include <mutex>
 #include <functional>
 #include <iostream>
 #include <map>
@@ -21,6 +25,7 @@
 #include <sstream>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/phylocsf_b200.h"
@@ -49,18 +54,67 @@ struct Options {
     int device = 0;
 };
 
-struct ScoreRecord {
-    double score = 0.0, anc_comp = 0.0;
-    std::vector<std::pair<std::string, std::string>> diag;
-    std::string exn;  // non-empty: this region raised (Printexc text)
-};
-
 inline double db(double x) { return 10.0 * x / std::log(10.0); }
 inline std::string sf2(double x) {
     char b[64];
     snprintf(b, sizeof b, "%.2f", x);
     return b;
 }
+
+struct ScoreRecord {
+    double score = 0.0, anc_comp = 0.0;
+    // the strategy's diagnostics (the reference's (string*string) list), kept as numbers and rendered only
+    // when printed (--debug) or when two records tie on both scores (the structural compare reaches them)
+    enum DiagKind : uint8_t { D_NONE, D_FIXED, D_MLE, D_OMEGA } dk = D_NONE;
+    double dv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::string exn;  // non-empty: this region raised (Printexc text)
+
+    std::vector<std::pair<std::string, std::string>> diag() const {
+        static const char* const kFixed[] = {"rho", "L(C)", "L(NC)"};
+        static const char* const kMle[] = {"rho_0", "rho_C", "rho_N", "L(C)", "L(NC)"};
+        static const char* const kOmega[] = {"L(H0)", "rho_H0", "kappa_H0", "omega_H0", "sigma_H0", "L(H1)", "rho_H1", "kappa_H1", "omega_H1", "sigma_H1"};
+        const char* const* keys = dk == D_FIXED ? kFixed : dk == D_MLE ? kMle : kOmega;
+        const int n = dk == D_FIXED ? 3 : dk == D_MLE ? 5 : dk == D_OMEGA ? 10 : 0;
+        std::vector<std::pair<std::string, std::string>> d;
+        for (int i = 0; i < n; i++) d.emplace_back(keys[i], sf2(dv[i]));
+        return d;
+    }
+    void set_diag(DiagKind k, std::initializer_list<double> v) {
+        dk = k;
+        int i = 0;
+        for (double x : v) dv[i++] = x;
+    }
+};
+
+// Recycles the readers' nucleotide buffers: a buffer goes back to the pool when the last batch using it is
+// done, so after the first few batches no buffer is allocated (or page-faulted in) again.
+class BufferPool {
+  public:
+    std::shared_ptr<std::vector<uint8_t>> get() {
+        std::vector<uint8_t>* v = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(st->mu);
+            if (!st->free.empty()) {
+                v = st->free.back().release();
+                st->free.pop_back();
+            }
+        }
+        if (!v) v = new std::vector<uint8_t>();
+        v->clear();
+        std::shared_ptr<State> keep = st;
+        return std::shared_ptr<std::vector<uint8_t>>(v, [keep](std::vector<uint8_t>* q) {
+            std::lock_guard<std::mutex> lk(keep->mu);
+            keep->free.emplace_back(q);
+        });
+    }
+
+  private:
+    struct State {
+        std::mutex mu;
+        std::vector<std::unique_ptr<std::vector<uint8_t>>> free;
+    };
+    std::shared_ptr<State> st = std::make_shared<State>();
+};
 
 struct AlnJob {
     std::string name;
@@ -81,6 +135,19 @@ struct Batch {
     std::vector<uint8_t> codes;          // [column][leaf]
     std::vector<int64_t> region_off{0};  // staged regions (whole frames in frame mode)
     int64_t n_rec = 0;                   // candidate regions (= staged regions except in frame mode)
+    // nucleotide form (AsIs regions): the batch carries leaf-ordered nucleotide rows instead of codon codes
+    // and the device does pleaves for every frame (pcsf_batch_upload_alignments)
+    // The rows are not copied into one buffer: the batch keeps the readers' buffers (shared with the reader
+    // side only until it lets go of them) as the pieces of pcsf_batch_upload_alignments_parts.
+    bool nt_form = false;
+    struct NtPart {
+        std::shared_ptr<std::vector<uint8_t>> buf;
+        size_t begin, end;               // the bytes of `buf` this batch uses
+    };
+    std::vector<NtPart> parts;
+    int64_t nt_bytes = 0;                // total size of the pieces = next alignment's offset
+    std::vector<int64_t> aln_off;        // alignment a: n_leaves rows of aln_len[a] bytes at aln_off[a] of the pieces' concatenation
+    std::vector<int32_t> aln_len;
 };
 
 inline std::string status_exn(int32_t st) {
@@ -120,22 +187,37 @@ class DeviceScorer {
     bool frame_mode() const { return opt.strategy == STRAT_FIXED && opt.orf != AsIs; }
 
     // Score every candidate region of the batch and render the report lines of its alignments.
+    // The device is held only while scoring: the report lines of a batch are rendered while the next batch of
+    // this device is already being uploaded and scored.
     std::string run(const Batch& b) {
-        cur = &b;
         const int64_t R = (int64_t)b.region_off.size() - 1;
         std::vector<ScoreRecord> rec(b.n_rec);
         if (R > 0) {
-            if (opt.strategy != STRAT_NOP) check(pcsf_batch_upload(ctx, R, b.region_off.data(), b.codes.data()));
+            std::lock_guard<std::mutex> device_lock(mu);
+            cur = &b;
+            if (opt.strategy != STRAT_NOP) {
+                if (b.nt_form) {
+                    std::vector<const uint8_t*> pp;
+                    std::vector<int64_t> pb;
+                    for (const Batch::NtPart& q : b.parts) {
+                        pp.push_back(q.buf->data() + q.begin);
+                        pb.push_back((int64_t)(q.end - q.begin));
+                    }
+                    check(pcsf_batch_upload_alignments_parts(ctx, (int64_t)b.aln_len.size(), b.aln_off.data(), b.aln_len.data(),
+                                                             (int64_t)pp.size(), pp.data(), pb.data(), opt.frames));
+                } else
+                    check(pcsf_batch_upload(ctx, R, b.region_off.data(), b.codes.data()));
+            }
             switch (opt.strategy) {
                 case STRAT_FIXED: if (frame_mode()) score_fixed_frames(rec); else score_fixed(rec); break;
                 case STRAT_MLE: score_mle(rec); break;
                 case STRAT_OMEGA: score_omega(rec); break;
                 case STRAT_NOP: break;
             }
+            cur = nullptr;
         }
         std::ostringstream out;
         for (const AlnJob& j : b.jobs) report(j, rec, out);
-        cur = nullptr;
         return out.str();
     }
 
@@ -147,6 +229,7 @@ class DeviceScorer {
     pcsf_ctx* ctx = nullptr;
     int n_leaves = 0;
     const Batch* cur = nullptr;
+    std::mutex mu;  // one batch at a time on the device
 
     void check(int rc) {
         if (rc != PCSF_OK && rc != PCSF_ERR_NUMERIC) throw failure(std::string("phylocsf_b200: ") + pcsf_last_error(ctx));
@@ -165,7 +248,7 @@ class DeviceScorer {
             if (bad) { rec[r].exn = status_exn(bad); continue; }
             rec[r].score = db(lpr[r] - lpr[R + r]);
             rec[r].anc_comp = db(elpr[r] - elpr[R + r]);
-            rec[r].diag = {{"rho", sf2(1.0)}, {"L(C)", sf2(db(lpr[r]))}, {"L(NC)", sf2(db(lpr[R + r]))}};
+            rec[r].set_diag(ScoreRecord::D_FIXED, {1.0, db(lpr[r]), db(lpr[R + r])});
         }
     }
 
@@ -198,7 +281,7 @@ class DeviceScorer {
                     }
                 rc.score = db(l[0] - l[1]);
                 rc.anc_comp = db(e[0] - e[1]);
-                rc.diag = {{"rho", sf2(1.0)}, {"L(C)", sf2(db(l[0]))}, {"L(NC)", sf2(db(l[1]))}};
+                rc.set_diag(ScoreRecord::D_FIXED, {1.0, db(l[0]), db(l[1])});
             }
     }
 
@@ -218,8 +301,7 @@ class DeviceScorer {
             if (b0 || b1) { rec[r].exn = status_exn(b0 ? b0 : b1); continue; }  // coding model is maximised first
             rec[r].score = db(lpr[0][r] - lpr[1][r]);
             rec[r].anc_comp = db(elpr[0][r] - elpr[1][r]);
-            rec[r].diag = {{"rho_0", sf2(1.0)}, {"rho_C", sf2(rho[0][r])}, {"rho_N", sf2(rho[1][r])},
-                           {"L(C)", sf2(db(lpr[0][r]))}, {"L(NC)", sf2(db(lpr[1][r]))}};
+            rec[r].set_diag(ScoreRecord::D_MLE, {1.0, rho[0][r], rho[1][r], db(lpr[0][r]), db(lpr[1][r])});
         }
     }
 
@@ -350,9 +432,7 @@ class DeviceScorer {
             rec[r].score = 10.0 * (lpr1[r] - lpr0[r]) / std::log(10.0);
             rec[r].anc_comp = std::nan("");
             const OmegaInst &a = inst0[r], &b = inst[r];
-            rec[r].diag = {{"L(H0)", sf2(db(lpr0[r]))}, {"rho_H0", sf2(a.rho)}, {"kappa_H0", sf2(a.qs[0])}, {"omega_H0", sf2(a.qs[1])},
-                           {"sigma_H0", sf2(a.qs[2])}, {"L(H1)", sf2(db(lpr1[r]))}, {"rho_H1", sf2(b.rho)}, {"kappa_H1", sf2(b.qs[0])},
-                           {"omega_H1", sf2(b.qs[1])}, {"sigma_H1", sf2(b.qs[2])}};
+            rec[r].set_diag(ScoreRecord::D_OMEGA, {db(lpr0[r]), a.rho, a.qs[0], a.qs[1], a.qs[2], db(lpr1[r]), b.rho, b.qs[0], b.qs[1], b.qs[2]});
         }
     }
 
@@ -365,7 +445,8 @@ class DeviceScorer {
             if (ka[i] > kb[i]) return true;
             if (ka[i] < kb[i]) return false;
         }
-        if (a.diag != b.diag) return a.diag > b.diag;
+        const auto da = a.diag(), dbb = b.diag();
+        if (da != dbb) return da > dbb;
         if (ra.rc != rb.rc) return ra.rc;
         if (ra.lo != rb.lo) return ra.lo > rb.lo;
         return ra.hi >= rb.hi;
@@ -401,12 +482,12 @@ class DeviceScorer {
             if (opt.frames == 6) out << "\t" << (rg.rc ? '-' : '+');
             if (opt.bls) out << "\t" << fmt4(bls_score(ps.nt, rows, j.which_row, rg.lo, rg.hi));
             if (opt.anc_comp) out << "\t" << fmt4(s.anc_comp);
-            const std::string refdna = rows[0].substr(rg.lo, rg.hi - rg.lo + 1);
+            const std::string refdna = (opt.dna || opt.aa) ? rows[0].substr(rg.lo, rg.hi - rg.lo + 1) : std::string();
             if (opt.dna) out << "\t" << refdna;
             if (opt.aa) out << "\t" << translate(refdna);
             if (opt.debug) {
                 out << "\t#";
-                for (auto& kv : s.diag) out << " " << kv.first << "=" << kv.second;
+                for (auto& kv : s.diag()) out << " " << kv.first << "=" << kv.second;
             }
             out << "\n";
         };
@@ -431,6 +512,11 @@ class Driver {
         n_leaves = ps.tree.n_leaves;
         leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
         leaf_set.insert(leaf_labels.begin(), leaf_labels.end());
+        for (int l = 0; l < n_leaves; l++) leaf_index[leaf_labels[l]] = l;
+        for (int c = 0; c < 256; c++) nt_lut[c] = 0;
+        for (const char* q = "ACGTacgtNn-"; *q; q++) nt_lut[(unsigned char)*q] = (uint8_t)*q;  // Code.ml:39-51
+        nt_lut[(unsigned char)'u'] = 't';                                                        // src/PhyloCSF.ml:266,285
+        nt_lut[(unsigned char)'U'] = 'T';
         if (devices.empty()) devices.push_back(o.device);
         if (o.strategy == STRAT_NOP) devices.resize(1);
         for (int d : devices) dev.emplace_back(new DeviceScorer(o, ps, d));
@@ -446,7 +532,130 @@ class Driver {
         std::vector<uint8_t> codes;
         std::vector<int> region_cols;
         std::string abort;  // non-empty: the alignment aborted with this Printexc text
+        bool nt_form = false;     // prepared by prepare_fast: n_leaves rows of aln_len nucleotides at offset
+        size_t nt_off = 0;        // nt_off of the buffer the caller passed (shared by a chunk of alignments)
+        int32_t aln_len = 0;
     };
+
+    // Fast form of prepare() for the bulk case: AsIs regions of a plain, well-formed multi-FASTA text. One pass
+    // over the bytes finds the records; the rows go straight into a leaf-ordered nucleotide block (u->t applied,
+    // alphabet checked with the revcomp table) that the device turns into codon codes for every frame, so the
+    // host builds neither per-row strings nor reverse complements nor codes. Anything unusual - an option that
+    // needs the rows on the host, blank or padded lines, a character outside ACGTacgtNn-uU, an unknown or
+    // repeated species, ragged rows, a gapped reference - returns false WITHOUT judging it: the caller then
+    // runs prepare(), which applies the reference's checks in the reference's order with its messages.
+    bool prepare_fast(const std::string& name, const char* data, size_t n, Prepared& p, std::vector<uint8_t>& nt_buf) const {
+        if (opt.orf != AsIs || opt.remove_ref_gaps || opt.bls || opt.strategy == STRAT_OMEGA) return false;
+        if (n == 0 || data[0] != '>') return false;
+        struct Seg { const char *b, *e; };
+        struct Rec { int leaf; size_t seg0, seg1; };
+        static thread_local std::vector<Seg> segs;  // scratch, reused across calls
+        static thread_local std::vector<Rec> recs;
+        static thread_local std::vector<char> seen;
+        segs.clear();
+        recs.clear();
+        seen.assign(n_leaves, 0);
+        auto ws = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\014'; };
+        const char *q = data, *end = data + n;
+        std::string key;
+        while (q < end) {
+            const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
+            const char* le = nl ? nl : end;
+            if (*q == '>') {  // header: species = text up to the first '|', trimmed (src/PhyloCSF.ml:112-114)
+                const char* b = q + 1;
+                const char* bar = (const char*)memchr(b, '|', (size_t)(le - b));
+                const char* e = bar ? bar : le;
+                while (b < e && ws(*b)) b++;
+                while (e > b && ws(e[-1])) e--;
+                key.assign(b, e);
+                auto it = leaf_index.find(key);
+                if (it == leaf_index.end() || seen[it->second]) return false;
+                seen[it->second] = 1;
+                if (!recs.empty()) recs.back().seg1 = segs.size();
+                recs.push_back({it->second, segs.size(), segs.size()});
+            } else {
+                const char *b = q, *e = le;
+                while (e > b && ws(e[-1])) e--;  // trailing CR / blanks; anything else odd fails the alphabet check
+                if (b == e || ws(*b)) return false;
+                segs.push_back({b, e});
+            }
+            q = nl ? nl + 1 : end;
+        }
+        recs.back().seg1 = segs.size();
+        auto rec_len = [&](const Rec& r) {
+            size_t L = 0;
+            for (size_t k = r.seg0; k < r.seg1; k++) L += (size_t)(segs[k].e - segs[k].b);
+            return L;
+        };
+        const size_t len = rec_len(recs[0]);
+        if (len == 0 || len > (size_t)INT32_MAX) return false;
+        for (const Rec& r : recs)
+            if (rec_len(r) != len) return false;
+        const size_t off0 = nt_buf.size();
+        nt_buf.resize(off0 + (size_t)n_leaves * len);
+        uint8_t* const block = nt_buf.data() + off0;
+        if ((int)recs.size() < n_leaves)
+            for (int l = 0; l < n_leaves; l++)
+                if (!seen[l]) memset(block + (size_t)l * len, '-', len);  // absent species marginalise
+        auto reject = [&]() { nt_buf.resize(off0); return false; };
+        for (const Rec& r : recs) {
+            uint8_t* dst = block + (size_t)r.leaf * len;
+            unsigned bad = 0;
+            for (size_t k = r.seg0; k < r.seg1; k++) {
+                const unsigned char* sb = (const unsigned char*)segs[k].b;
+                const size_t L = (size_t)(segs[k].e - segs[k].b);
+                size_t i = 0;
+#if defined(__SSE2__)
+                // 16 characters at a time: copied as they are when all of them are in ACGTNacgtn- (a letter's
+                // upper case is the byte with bit 5 cleared); a block holding anything else - u/U to map, or a
+                // character to reject - goes through the table below
+                const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T'),
+                              cN = _mm_set1_epi8('N'), cDash = _mm_set1_epi8('-'), up = _mm_set1_epi8((char)0xDF);
+                for (; i + 16 <= L; i += 16) {
+                    const __m128i x = _mm_loadu_si128((const __m128i*)(sb + i));
+                    const __m128i u = _mm_and_si128(x, up);
+                    __m128i ok = _mm_or_si128(_mm_cmpeq_epi8(u, cA), _mm_cmpeq_epi8(u, cC));
+                    ok = _mm_or_si128(ok, _mm_or_si128(_mm_cmpeq_epi8(u, cG), _mm_cmpeq_epi8(u, cT)));
+                    ok = _mm_or_si128(ok, _mm_or_si128(_mm_cmpeq_epi8(u, cN), _mm_cmpeq_epi8(x, cDash)));
+                    if (_mm_movemask_epi8(ok) != 0xFFFF) break;
+                    _mm_storeu_si128((__m128i*)(dst + i), x);
+                }
+#endif
+                for (; i < L; i++) {  // the tail, or the rest of a segment that left the fast loop
+                    const uint8_t m = nt_lut[sb[i]];
+                    bad |= (m == 0);
+                    dst[i] = m;
+                }
+                dst += L;
+            }
+            if (bad) return reject();
+        }
+        const uint8_t* ref = block + (size_t)recs[0].leaf * len;
+        if (!opt.allow_ref_gaps && memchr(ref, '-', len)) return reject();
+        AlnJob& job = p.job;
+        job.name = name;
+        job.aln.assign(1, std::string((const char*)ref, len));  // the report reads only the reference row (--dna / --aa)
+        if (opt.frames == 6 && (opt.dna || opt.aa)) job.rc_aln.assign(1, revcomp(job.aln[0]));
+        job.regions = candidate_regions(job.aln[0], AsIs, opt.frames, opt.min_codons);
+        for (const Region& r : job.regions) p.region_cols.push_back(r.hi - r.lo + 1 >= 3 ? (r.hi - r.lo + 1) / 3 : 0);
+        p.nt_form = true;
+        p.nt_off = off0;
+        p.aln_len = (int32_t)len;
+        return true;
+    }
+    // prepare() on raw text: the fast form when it applies, else the general one on the text's lines
+    Prepared prepare_text(const std::string& name, const char* data, size_t n, std::vector<uint8_t>& nt_buf) const {
+        Prepared p;
+        if (prepare_fast(name, data, n, p, nt_buf)) return p;
+        std::vector<std::string> lines;
+        const char *q = data, *end = data + n;
+        while (q < end) {  // like std::getline
+            const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
+            lines.emplace_back(q, nl ? nl : end);
+            q = nl ? nl + 1 : end;
+        }
+        return prepare(name, lines);
+    }
     Prepared prepare(const std::string& name, const std::vector<std::string>& lines) const {
         Prepared p;
         AlnJob& job = p.job;
@@ -506,18 +715,35 @@ class Driver {
 
     // Appends a prepared alignment to the current batch (in input order). Returns false when the run
     // must stop (the alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
-    bool append(Prepared&& p, std::ostream& out) {
+    // `nt_buf`: the buffer prepare_text filled for this alignment (nucleotide form only).
+    bool append(Prepared&& p, std::ostream& out, const std::shared_ptr<std::vector<uint8_t>>& nt_buf = nullptr) {
         if (!p.abort.empty()) {
             finish(out);
             out << p.job.name << "\tabort\t" << p.abort << "\n";
             out.flush();
             return false;
         }
+        if (!batch.jobs.empty() && batch.nt_form != p.nt_form) flush(out);  // a batch is staged in one form
+        batch.nt_form = p.nt_form;
+        if (batch.jobs.empty() && !p.nt_form) {  // size the staging buffer once instead of growing (and re-faulting) it by doubling
+            const size_t want = (size_t)(opt.batch_cols + 4096) * n_leaves + p.codes.size();
+            if (batch.codes.capacity() < want) batch.codes.reserve(want);
+        }
         p.job.first_region = (int64_t)batch.region_off.size() - 1;
         p.job.first_rec = batch.n_rec;
         batch.n_rec += (int64_t)p.job.regions.size();
         for (int nc : p.region_cols) batch.region_off.push_back(batch.region_off.back() + nc);
-        batch.codes.insert(batch.codes.end(), p.codes.begin(), p.codes.end());
+        if (p.nt_form) {
+            const size_t nb = (size_t)p.aln_len * n_leaves;
+            if (batch.parts.empty() || batch.parts.back().buf != nt_buf || batch.parts.back().end != p.nt_off)
+                batch.parts.push_back({nt_buf, p.nt_off, p.nt_off});
+            batch.parts.back().end += nb;
+            batch.aln_off.push_back(batch.nt_bytes);
+            batch.aln_len.push_back(p.aln_len);
+            batch.nt_bytes += (int64_t)nb;
+        } else {
+            batch.codes.insert(batch.codes.end(), p.codes.begin(), p.codes.end());
+        }
         batch.jobs.push_back(std::move(p.job));
         if (batch.region_off.back() >= opt.batch_cols) flush(out);
         return true;
@@ -526,15 +752,24 @@ class Driver {
     bool add_alignment(const std::string& name, const std::vector<std::string>& lines, std::ostream& out) {
         return append(prepare(name, lines), out);
     }
+    size_t jobs_in_batch() const { return batch.jobs.size(); }
 
-    // Hand the current batch to the next GPU; at most one batch per device is in flight.
+    // Hand the current batch to the next GPU (round-robin). Up to two batches per device are in flight: one
+    // being scored, and either one waiting for the device or one whose report is being rendered.
     void flush(std::ostream& out) {
         if (batch.jobs.empty()) return;
-        if (inflight.size() >= dev.size()) drain_one(out);
+        if (inflight.size() >= 2 * dev.size()) drain_one(out);
         auto b = std::make_shared<Batch>(std::move(batch));
         batch = Batch();
-        DeviceScorer* d = dev[next_dev++ % dev.size()].get();  // the oldest in-flight batch ran on this device: it is free
-        inflight.push_back(std::async(std::launch::async, [d, b]() { return d->run(*b); }));
+        if (!spare.empty()) {  // staging buffers of a finished batch: their pages are already faulted in
+            batch.codes.swap(spare.back().codes);
+            batch.region_off.swap(spare.back().region_off);
+            batch.aln_off.swap(spare.back().aln_off);
+            batch.aln_len.swap(spare.back().aln_len);
+            spare.pop_back();
+        }
+        DeviceScorer* d = dev[next_dev++ % dev.size()].get();
+        inflight.push_back({std::async(std::launch::async, [d, b]() { return d->run(*b); }), b});
     }
     // Wait for everything in flight and print it (end of input, or before an abort line).
     void finish(std::ostream& out) {
@@ -553,14 +788,28 @@ class Driver {
     int n_leaves = 0;
     std::vector<std::string> leaf_labels;
     std::set<std::string> leaf_set;
+    std::unordered_map<std::string, int> leaf_index;  // species -> tree leaf
+    uint8_t nt_lut[256];                              // alignment character -> staged character, 0 = not allowed
     std::vector<std::unique_ptr<DeviceScorer>> dev;
     Batch batch;
-    std::deque<std::future<std::string>> inflight;
+    std::deque<std::pair<std::future<std::string>, std::shared_ptr<Batch>>> inflight;
+    std::vector<Batch> spare;  // emptied staging buffers, capacity kept
     size_t next_dev = 0;
 
     void drain_one(std::ostream& out) {
-        out << inflight.front().get();
+        out << inflight.front().first.get();
         out.flush();
+        Batch& b = *inflight.front().second;
+        Batch keep;
+        keep.codes.swap(b.codes);
+        keep.region_off.swap(b.region_off);
+        keep.aln_off.swap(b.aln_off);
+        keep.aln_len.swap(b.aln_len);
+        keep.codes.clear();
+        keep.region_off.assign(1, 0);
+        keep.aln_off.clear();
+        keep.aln_len.clear();
+        spare.push_back(std::move(keep));
         inflight.pop_front();
     }
 };

@@ -570,9 +570,25 @@ int pcsf_batch_upload(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off
 
 int pcsf_batch_upload_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off, const int32_t* aln_len,
                                  const uint8_t* nt, int frames) {
+    int64_t nt_bytes = 0;
+    if (ctx && nalign > 0 && aln_off && aln_len)
+        for (int64_t a = 0; a < nalign; a++)
+            nt_bytes = std::max<int64_t>(nt_bytes, aln_off[a] + (int64_t)std::max(aln_len[a], 0) * ctx->n_leaves);
+    if (nt_bytes > 0 && !nt) return fail(ctx, PCSF_ERR_INVALID_ARG, "null nucleotide buffer");
+    return pcsf_batch_upload_alignments_parts(ctx, nalign, aln_off, aln_len, nt_bytes > 0 ? 1 : 0, &nt, &nt_bytes, frames);
+}
+
+int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off, const int32_t* aln_len,
+                                       int64_t nparts, const uint8_t* const* part_ptr, const int64_t* part_bytes, int frames) {
     TRY(check_ready(ctx, false));
-    if (nalign < 0 || !aln_off || !aln_len || (frames != 1 && frames != 3 && frames != 6))
+    if (nalign < 0 || !aln_off || !aln_len || nparts < 0 || (nparts > 0 && (!part_ptr || !part_bytes)) ||
+        (frames != 1 && frames != 3 && frames != 6))
         return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload_alignments: bad argument");
+    int64_t have = 0;
+    for (int64_t i = 0; i < nparts; i++) {
+        if (part_bytes[i] < 0 || (part_bytes[i] > 0 && !part_ptr[i])) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload_alignments: bad part");
+        have += part_bytes[i];
+    }
     CU(cudaSetDevice(ctx->device));
     const int64_t nregions = nalign * frames;
     std::vector<int64_t> roff(nregions + 1, 0);
@@ -586,14 +602,21 @@ int pcsf_batch_upload_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* a
         }
     }
     const int64_t total = roff[nregions];
-    if (nt_bytes > 0 && !nt) return fail(ctx, PCSF_ERR_INVALID_ARG, "null nucleotide buffer");
+    if (nt_bytes > have) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload_alignments: an alignment lies outside the nucleotide buffer");
     TRY(reserve(ctx, ctx->d_nt, std::max<int64_t>(nt_bytes, 1)));
     TRY(reserve(ctx, ctx->d_aln_off, sizeof(int64_t) * std::max<int64_t>(nalign, 1)));
     TRY(reserve(ctx, ctx->d_aln_len, sizeof(int32_t) * std::max<int64_t>(nalign, 1)));
     TRY(reserve(ctx, ctx->d_codes, (size_t)std::max<int64_t>(total, 1) * ctx->n_leaves));
     TRY(reserve(ctx, ctx->d_region_off, sizeof(int64_t) * (nregions + 1)));
     CU(cudaEventRecord(ctx->ev[6], ctx->stream));
-    if (nt_bytes > 0) CU(cudaMemcpyAsync(ctx->d_nt.p, nt, nt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        int64_t at = 0;
+        for (int64_t i = 0; i < nparts && at < nt_bytes; i++) {
+            const int64_t nb = std::min(part_bytes[i], nt_bytes - at);
+            if (nb > 0) CU(cudaMemcpyAsync((uint8_t*)ctx->d_nt.p + at, part_ptr[i], nb, cudaMemcpyHostToDevice, ctx->stream));
+            at += part_bytes[i];
+        }
+    }
     if (nalign > 0) {
         CU(cudaMemcpyAsync(ctx->d_aln_off.p, aln_off, sizeof(int64_t) * nalign, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_aln_len.p, aln_len, sizeof(int32_t) * nalign, cudaMemcpyHostToDevice, ctx->stream));

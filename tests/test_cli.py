@@ -129,7 +129,94 @@ def test_usage_and_missing_base(params_base):
     assert r.returncode == 0 and r.stdout == "(STDIN)\tscore(decibans)\t0.0000\n"
 
 
+def _variants(params_base, tmp_path):
+    """tal-AA in the shapes the fast reader takes itself (wrapped lines, CRLF, RNA letters, lower case, a header
+    with a |comment) and in shapes it hands to the general reader (a blank line, a padded line)."""
+    lines = gp.example_lines("tal-AA.fa")
+    recs, cur = [], None
+    for l in lines:
+        if l.startswith(">"):
+            cur = [l[1:].strip(), ""]
+            recs.append(cur)
+        elif cur is not None:
+            cur[1] += l.strip()
+
+    def write(name, text):
+        q = tmp_path / name
+        q.write_bytes(text.encode())
+        return str(q)
+
+    wrap = lambda s, n: "\n".join(s[i:i + n] for i in range(0, len(s), n))
+    plain = "".join(">%s\n%s\n" % (h, s) for h, s in recs)
+    files = {
+        "plain": write("plain.fa", plain),
+        "wrapped": write("wrapped.fa", "".join(">%s\n%s\n" % (h, wrap(s, 17)) for h, s in recs)),
+        "crlf": write("crlf.fa", plain.replace("\n", "\r\n")),
+        "rna_lower": write("rna.fa", "".join(">%s | some comment\n%s\n" % (h, s.replace("T", "u").replace("A", "a")) for h, s in recs)),
+        "no_final_newline": write("nonl.fa", plain[:-1]),
+        "blank_line": write("blank.fa", plain.replace("\n>", "\n\n>", 1)),
+        "padded": write("padded.fa", "".join(">%s\n  %s \n" % (h, s) for h, s in recs)),
+    }
+    return files, plain.split("\n")[:-1]
+
+
+def test_reader_variants_nop(params_base, tmp_path):
+    """Every shape is accepted and reported in input order; a shape the fast reader declines in the middle of
+    the list starts a new batch in the other form without reordering the output."""
+    files, _ = _variants(params_base, tmp_path)
+    order = ["plain", "wrapped", "blank_line", "crlf", "padded", "rna_lower", "no_final_newline"]
+    got = run_cli(params_base, "12flies", [files[k] for k in order], "--strategy=nop", "--frames=6")
+    assert [l.split("\t")[0] for l in got] == [files[k] for k in order]
+    assert all(l.split("\t")[1:] == got[0].split("\t")[1:] for l in got)
+
+
 # ------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["fixed", "mle"])
+def test_reader_variants_score_like_the_oracle(params_base, tmp_path, strategy):
+    """The fast reader (nucleotide rows staged as they are read, pleaves on the device) and the general reader
+    (host pleaves) give the oracle's lines for the same alignment in every shape, mixed in one run."""
+    files, lines = _variants(params_base, tmp_path)
+    order = ["plain", "wrapped", "blank_line", "crlf", "padded", "rna_lower", "no_final_newline"]
+    flags = ["--strategy=" + strategy, "--frames=6", "--allScores", "--ancComp", "--dna", "--aa"]
+    got = run_cli(params_base, "12flies", [files[k] for k in order], *flags)
+    per = len(got) // len(order)
+    assert per * len(order) == len(got) and per == 7
+    for i, k in enumerate(order):
+        src = lines
+        if k == "rna_lower":  # the oracle sees the same text the file holds
+            src = open(files[k]).read().split("\n")[:-1]
+        want = run_oracle(params_base, "12flies", files[k], src, strategy=strategy, frames=6, all_scores=True, anc_comp=True, dna=True, aa=True)
+        same_lines(got[i * per:(i + 1) * per], want)
+
+
+@pytest.mark.gpu
+def test_fast_reader_missing_species_and_gaps(params_base, tmp_path):
+    """Species absent from the alignment marginalise; gaps and N in non-reference rows marginalise their codons."""
+    import numpy as np
+
+    ops = o.load_paramset(os.path.join(params_base, "PhyloCSF_Parameters", "29mammals"), o.Options(strategy="fixed"))
+    labels = ops.tree.labels[: ops.tree.n_leaves]
+    rng = np.random.default_rng(8)
+    rows = o.codes_to_alignment(o.simulate_columns(ops.model.coding_model.model(1.0), 50, rng))
+    keep = [0, 3, 4, 9, 17, 28, 11]  # reference first, not in tree order
+    text = ""
+    for n, i in enumerate(keep):
+        r = rows[i]
+        if n == 2:
+            r = r[:30] + "---" + r[33:60] + "NN" + r[62:]
+        if n == 4:
+            r = "-" * 40 + r[40:]
+        text += ">%s\n%s\n" % (labels[i], r)
+    path = tmp_path / "subset.fa"
+    path.write_text(text)
+    flags = ["--strategy=fixed", "--frames=6", "--allScores", "--ancComp"]
+    got = run_cli(params_base, "29mammals", [str(path)] * 2, *flags)
+    want = run_oracle(params_base, "29mammals", str(path), text.split("\n")[:-1], strategy="fixed", frames=6, all_scores=True, anc_comp=True)
+    same_lines(got, want * 2)
+
+
+
 @pytest.mark.gpu
 def test_reference_goldens_through_the_cli(params_base):
     """src/test.ml:27-59, the reference's own end-to-end tests (default strategy mle)."""

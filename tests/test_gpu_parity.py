@@ -159,6 +159,34 @@ def test_device_pleaves_frames(params_base):
     ctx.close()
 
 
+def test_device_pleaves_from_parts_equals_one_buffer(params_base):
+    """pcsf_batch_upload_alignments_parts (nucleotide buffer handed over in pieces, as the command line's
+    reader threads produce it) stages exactly what pcsf_batch_upload_alignments stages: identical scores,
+    for alignments of different lengths spread over pieces of different sizes (one piece empty)."""
+    ps = H.oracle_paramset(params_base, "12flies")
+    n = ps.tree.n_leaves
+    rng = np.random.default_rng(3)
+    lens = [30, 7, 2, 91, 45]
+    alns = [np.frombuffer(b"ACGTacgtN-", dtype=np.uint8)[rng.integers(0, 10, size=(n, L))] for L in lens]
+    flat = np.concatenate([a.reshape(-1) for a in alns])
+    off = np.concatenate([[0], np.cumsum([a.size for a in alns])[:-1]])
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    ctx.batch_upload_alignments(off, lens, flat, 6)
+    one = ctx.lpr_all([0, 1])
+    cut1, cut2 = int(off[2]), int(off[4])
+    parts = [flat[:cut1], flat[:0], flat[cut1:cut2], flat[cut2:]]
+    ctx.batch_upload_alignments_parts(off, lens, parts, 6)
+    assert ctx.nregions == 6 * len(lens)
+    many = ctx.lpr_all([0, 1])
+    for a, b in zip(one, many):
+        assert np.array_equal(a, b, equal_nan=True)
+    with pytest.raises(Exception):  # an alignment beyond the pieces
+        ctx.batch_upload_alignments_parts(off, lens, parts[:-1], 6)
+    ctx.close()
+
+
 def _oracle_mle(ps, regs):
     out = []
     for c in regs:

@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
 """End-to-end timing of the drop-in command line on simulated alignment files (GPU box):
-    python tools/bench_cli.py <paramset> <n_alignments> <codons> -- <PhyloCSF flags...>
-Writes N multi-FASTA files simulated under the parameter set's coding/noncoding ECMs (half each),
-runs phylocsf_b200/bin/PhyloCSF --files on them and reports wall-clock throughput. This is the
-whole drop-in path: file parsing, host pleaves, batching, GPU scoring, report."""
+    python tools/bench_cli.py <paramset> <n_alignments> <codons> [repeat] -- <PhyloCSF flags...>
+Writes N multi-FASTA files simulated under the parameter set's coding/noncoding ECMs (half each), lists
+each of them `repeat` times (default 1; the files stay in the page cache), runs
+phylocsf_b200/bin/PhyloCSF --files on the list and reports wall-clock throughput of the whole process
+(start-up and CUDA context creation included). This is the whole drop-in path: file reading, batching,
+GPU scoring, report. PCSF_HOST_PROFILE=1 adds the reader / appender split on stderr."""
 import json
 import os
 import subprocess
@@ -21,6 +23,7 @@ from phylocsf_b200 import host, simulate  # noqa: E402
 from tools import golden_params as gp  # noqa: E402
 
 pset, N, ncod = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+REPEAT = int(sys.argv[4]) if sys.argv[4] != "--" else 1
 flags = sys.argv[sys.argv.index("--") + 1:]
 base = gp.materialize(tempfile.mkdtemp(), sets=[pset])
 ps = host.ParamSet(os.path.join(base, "PhyloCSF_Parameters", pset))
@@ -48,11 +51,13 @@ for a in range(N):
             f.write(">%s\n%s\n" % (lab, nt[a, l].tobytes().decode()))
     names.append(fn)
 lst = os.path.join(d, "list.txt")
-open(lst, "w").write("\n".join(names) + "\n")
+open(lst, "w").write(("\n".join(names) + "\n") * REPEAT)
+N *= REPEAT
 env = dict(os.environ, PHYLOCSF_BASE=base)
 t0 = time.perf_counter()
 r = subprocess.run([os.path.join(ROOT, "phylocsf_b200", "bin", "PhyloCSF"), pset, lst, "--files"] + flags, env=env, capture_output=True, text=True)
 dt = time.perf_counter() - t0
 lines = r.stdout.splitlines()
 print(json.dumps({"paramset": pset, "alignments": N, "codons": ncod, "flags": flags, "rc": r.returncode, "seconds": dt,
-                  "alignments_per_s": N / dt, "output_lines": len(lines), "first_line": lines[0] if lines else r.stderr[:300]}))
+                  "alignments_per_s": N / dt, "output_lines": len(lines), "first_line": lines[0] if lines else r.stderr[:300],
+                  "stderr_tail": r.stderr[-300:]}))
