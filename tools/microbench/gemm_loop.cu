@@ -71,6 +71,30 @@ __global__ void __launch_bounds__(512) gemm_loop(const double* __restrict__ Pimg
 #pragma unroll
                     for (int t = 0; t < T; t++) dmma(acc[t][j][0], acc[t][j][1], cur[t][s2][1], bf.y);
                 }
+        } else if (MODE == 5) {  // B fragments of n-tiles 2jp, 2jp+1 (same k-step) in one LDS.128: 4 independent accumulator chains per load
+            const double2* Pb2 = reinterpret_cast<const double2*>(Ps) + lane;
+#pragma unroll
+            for (int s = 0; s < 16; s++)
+#pragma unroll
+                for (int jp = 0; jp < 4; jp++) {
+                    const double2 bf = Pb2[(s * 4 + jp) * 32];
+#pragma unroll
+                    for (int t = 0; t < T; t++) dmma(acc[t][2 * jp][0], acc[t][2 * jp][1], cur[t][s >> 1][s & 1], bf.x);
+#pragma unroll
+                    for (int t = 0; t < T; t++) dmma(acc[t][2 * jp + 1][0], acc[t][2 * jp + 1][1], cur[t][s >> 1][s & 1], bf.y);
+                }
+        } else if (MODE == 6) {  // like 5 with the loop over n-tile pairs outermost: 4 chains, 16 k-steps each, then the next pair
+            const double2* Pb2 = reinterpret_cast<const double2*>(Ps) + lane;
+#pragma unroll
+            for (int jp = 0; jp < 4; jp++)
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    const double2 bf = Pb2[(jp * 16 + s) * 32];
+#pragma unroll
+                    for (int t = 0; t < T; t++) dmma(acc[t][2 * jp][0], acc[t][2 * jp][1], cur[t][s >> 1][s & 1], bf.x);
+#pragma unroll
+                    for (int t = 0; t < T; t++) dmma(acc[t][2 * jp + 1][0], acc[t][2 * jp + 1][1], cur[t][s >> 1][s & 1], bf.y);
+                }
         } else {
             const double bf = Pb[0];
 #pragma unroll
@@ -123,6 +147,7 @@ int main() {
     for (int wi = 0; wi < 2; wi++) {
         const int w = ws[wi];
         run<2, 0>(P, out, sms, w); run<2, 1>(P, out, sms, w); run<2, 3>(P, out, sms, w); run<2, 4>(P, out, sms, w);
+        run<2, 5>(P, out, sms, w); run<2, 6>(P, out, sms, w); run<1, 5>(P, out, sms, w); run<1, 6>(P, out, sms, w);
         run<1, 0>(P, out, sms, w); run<1, 3>(P, out, sms, w); run<1, 4>(P, out, sms, w);
         if (w <= 8) { run<3, 0>(P, out, sms, w); run<3, 3>(P, out, sms, w); }
     }
