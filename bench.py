@@ -15,7 +15,7 @@ leaf codes per pass), so no L2 flush is needed between iterations.
 value   = device-resident throughput (leaf codes already in HBM), CUDA events, max over ranks
 e2e     = the same pass through the C ABI from pinned HOST buffers (pcsf_score_alignments): H2D of the
           nucleotide rows in chunks overlapped with on-device pleaves, pruning, region reduction, D2H
-roofline= the pruning kernel against the FP64 tensor (DMMA) peak
+roofline= the pruning kernel (wide form, prune_wide_kernel: the one this workload runs) against the FP64 tensor (DMMA) peak
 cpu_baseline / --impl reference = the CPU oracle (oracle/, a restatement of the reference's OCaml
           path; the reference itself needs OCaml+GSL, absent here) on a bounded sample, all host threads
 """
@@ -312,7 +312,7 @@ def main():
                     "path": "pcsf_score_alignments: pinned host nucleotide rows -> chunked H2D overlapped with on-device pleaves + pruning + reduction -> D2H"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "pcsf::prune_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"kernel": "pcsf::prune_wide_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms,
                          "flop_per_codon_column": FLOP_PER_COLUMN, "peak_source": peak_note},
         }

@@ -75,6 +75,7 @@ struct pcsf_ctx {
     int64_t launches = 0;
     int prune_smem_optin = 0;
     int skew_ns = 1500;
+    int wide = -1;  // pruning kernel form: 0 narrow (128-column tiles), 1 wide (192), -1 chosen per launch (PCSF_WIDE overrides)
     int rescale = 0;  // PCSF_OPT_RESCALE
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
     int timeline_cap = 0;
@@ -171,13 +172,35 @@ int prune_smem_for(int n_ops, int n_items, int n_leaves) {
 }
 
 // Launch K2+K3 over `spans`, then K4 over the given segments. Outputs land in ctx->d_lpr/d_elpr.
+int prune_wide_smem_for(int n_ops, int n_items, int n_leaves) {
+    return W_P_STAGES * FRAG_BYTES + W_L_STAGES * PT_SLOT_BYTES + W_BAR_BYTES + r16(n_ops * (int)sizeof(Op)) +
+           r16(n_items * (int)sizeof(Item)) + 2 * r16(W_TILE_COLS * n_leaves) + W_WARPS * 32;  // + per-warp scratch lines
+}
+
 int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vector<PSet>& psets, int64_t out_cols,
               const uint8_t* codes = nullptr) {
     std::vector<Span> spans = spans_in;
     int64_t tiles = 0;
+    // Which form: a sub-partition's time for a tile is (its warps with columns) x (one contraction), so in units
+    // of 64 columns a narrow tile costs ceil(n/64) <= 2 and a wide tile ceil(n/64) <= 3. Full wide tiles run at
+    // 89 % of the DMMA peak against 86.5 % for narrow ones; part-filled wide tiles run ~4 % behind narrow ones
+    // (measured with 100-column regions). Long spans (fixed strategy) go wide, one short region per P set
+    // (mle, omega) stays narrow.
+    bool wide = ctx->wide > 0;
+    if (ctx->wide < 0) {
+        double cost_n = 0, cost_w = 0;
+        for (const Span& s : spans) {
+            const int64_t n = s.ncols;
+            cost_n += ((n / TILE_COLS) * 2 + ((n % TILE_COLS) + 63) / 64) / 0.865;
+            cost_w += (n / W_TILE_COLS) * 3 / 0.89 + (((n % W_TILE_COLS) + 63) / 64) / 0.83;
+        }
+        wide = cost_w < cost_n && prune_wide_smem_for((int)ctx->ops.size(), (int)ctx->items.size(), ctx->n_leaves) <= ctx->prune_smem_optin;
+    }
+    const int tile_cols = wide ? W_TILE_COLS : TILE_COLS;
+    const size_t level_bytes = wide ? W_LEVEL_BYTES : STACK_LEVEL_BYTES;
     for (auto& s : spans) {
         s.tile0 = tiles;
-        tiles += (s.ncols + TILE_COLS - 1) / TILE_COLS;
+        tiles += (s.ncols + tile_cols - 1) / tile_cols;
     }
     // spans with zero columns would break the tile0 search (duplicate tile0): drop them
     spans.erase(std::remove_if(spans.begin(), spans.end(), [](const Span& s) { return s.ncols == 0; }), spans.end());
@@ -190,7 +213,7 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         CU(cudaMemcpyAsync(ctx->d_spans.p, spans.data(), sizeof(Span) * spans.size(), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_psets.p, psets.data(), sizeof(PSet) * psets.size(), cudaMemcpyHostToDevice, ctx->stream));
         const int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
-        if (ctx->max_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * ctx->max_levels * STACK_LEVEL_BYTES));
+        if (ctx->max_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * ctx->max_levels * level_bytes));
         PruneParams p;
         memset(&p, 0, sizeof(p));
         p.ops = ctx->d_ops;
@@ -212,12 +235,20 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         p.timeline = (long long*)ctx->timeline;
         p.timeline_cap = ctx->timeline_cap;
         p.skew_ns = ctx->skew_ns;
-        TRY(reserve(ctx, ctx->d_gexp, sizeof(int32_t) * (size_t)grid * std::max(1, ctx->max_levels) * TILE_COLS));
+        TRY(reserve(ctx, ctx->d_gexp, sizeof(int32_t) * (size_t)grid * std::max(1, ctx->max_levels) * tile_cols));
         p.global_exp = (int32_t*)ctx->d_gexp.p;
-        const int smem = prune_smem_for(p.n_ops, p.n_items, ctx->n_leaves);
+        const int smem = wide ? prune_wide_smem_for(p.n_ops, p.n_items, ctx->n_leaves) : prune_smem_for(p.n_ops, p.n_items, ctx->n_leaves);
         if (smem > ctx->prune_smem_optin)
             return fail(ctx, PCSF_ERR_INVALID_ARG, "tree too large for the pruning kernel's shared memory (" + std::to_string(smem) + " bytes)");
-        if (ctx->rescale) {  // PCSF_OPT_RESCALE: separate instantiation, the default path carries no extra code
+        if (wide) {
+            if (ctx->rescale) {
+                CU(cudaFuncSetAttribute(prune_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                prune_wide_kernel<true><<<grid, W_THREADS, smem, ctx->stream>>>(p);
+            } else {
+                CU(cudaFuncSetAttribute(prune_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                prune_wide_kernel<false><<<grid, W_THREADS, smem, ctx->stream>>>(p);
+            }
+        } else if (ctx->rescale) {  // PCSF_OPT_RESCALE: separate instantiation, the default path carries no extra code
             CU(cudaFuncSetAttribute(prune_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             prune_kernel<true><<<grid, PRUNE_THREADS, smem, ctx->stream>>>(p);
         } else {
@@ -377,6 +408,7 @@ int pcsf_create(int device_id, pcsf_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     ctx->prune_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("PCSF_SKEW_NS")) ctx->skew_ns = atoi(e);  // tuning knob, see prune_kernel
+    if (const char* e = getenv("PCSF_WIDE")) ctx->wide = atoi(e);
     if (const char* e = getenv("PCSF_RESCALE")) ctx->rescale = atoi(e) ? 1 : 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->stream = ctx->own_stream;
@@ -1125,11 +1157,11 @@ int pcsf_debug_timeline(pcsf_ctx* ctx, int cap, long long* out) {
         if (ctx->timeline) cudaFree(ctx->timeline);
         ctx->timeline = nullptr;
         ctx->timeline_cap = cap;
-        CU(cudaMalloc(&ctx->timeline, (size_t)cap * PRUNE_WARPS * 16));
-        CU(cudaMemset(ctx->timeline, 0xff, (size_t)cap * PRUNE_WARPS * 16));
+        CU(cudaMalloc(&ctx->timeline, (size_t)cap * 16 * 16));
+        CU(cudaMemset(ctx->timeline, 0xff, (size_t)cap * 16 * 16));
         return PCSF_OK;
     }
-    CU(cudaMemcpy(out, ctx->timeline, (size_t)ctx->timeline_cap * PRUNE_WARPS * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, ctx->timeline, (size_t)ctx->timeline_cap * 16 * 16, cudaMemcpyDeviceToHost));
     return PCSF_OK;
 }
 #endif

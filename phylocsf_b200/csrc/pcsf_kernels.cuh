@@ -291,6 +291,16 @@ __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
@@ -298,6 +308,16 @@ __device__ __forceinline__ void reg_dealloc() {
 template <int N>
 __device__ __forceinline__ void reg_alloc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// A ring stage is read through the generic proxy (LDS) and refilled through the async proxy (TMA). The
+// empty-barrier arrive alone does not order the two: without a proxy fence between a warp's last read of a
+// stage and its arrive, a refill was observed to overtake reads still queued in the load/store unit (rare
+// single-entry corruptions, run-to-run differences of 1e-13 in log z). Every lane fences its own reads.
+__device__ __forceinline__ void release_stage(uint64_t* empty_bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
 }
 
 // Underflow rescue (optional; the reference has none, lib/CamlPaml/PhyloLik.ml:87-92): when the largest
@@ -483,8 +503,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                                 cur[T][j][1] = k ? cur[T][j][1] * v.y : v.y;
                             }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&mempty[st]);
+                    release_stage(&mempty[st], lane);
                     mq++;
                 }
                 continue;
@@ -552,8 +571,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&pempty[pst]);
+            release_stage(&pempty[pst], lane);
             pq++;
             TL_MARK(oi * 8 + 2);
             // ------------------------------ epilogue ------------------------------
@@ -602,12 +620,357 @@ __global__ void __launch_bounds__(PRUNE_THREADS, 1) prune_kernel(const PrunePara
                         rescale_columns(cur, esum);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&mempty[st]);
+                release_stage(&mempty[st], lane);
                 mq++;
             }
             TL_MARK(oi * 8 + 4);
         }
+    }
+}
+
+// =================================================================================================
+// K2+K3, wide form: three compute warps per SM sub-partition
+// =================================================================================================
+// Two warps inside the contraction saturate a sub-partition's DMMA pipe (98.6 %); one alone reaches 84-89 %
+// (it has too few independent accumulator chains in flight). With two compute warps per sub-partition the
+// pipe therefore idles whenever either of them is outside the contraction (barrier round trips, multiplicand
+// pass, cherries, pushes: ~14 % of an edge). This form keeps THREE compute warps per sub-partition (12 per
+// CTA, 192-column tiles), which needs the compute warps down at 160 registers and the shared memory freed
+// of the 2 x 64 KB multiplicand ring. Both come from the same change: nothing is staged per column any more.
+//   - A leaf message is read straight out of the leaf's P^T table (65 rows x 512 B, one TMA bulk copy per
+//     leaf into a 2-stage ring) with the column's code as the row index: 16 LDS.128 per thread, into the
+//     registers of the partials the contraction has just consumed.
+//   - A parked partial is written to and read back from the CTA's global (L2-resident) stack by the very
+//     thread that owns it, so parking needs no barrier, fence or staging at all.
+//   - The producer warpgroup shrinks to one thread issuing TMA copies (P images into a 3-stage ring, leaf
+//     tables) and three warps that load the next tile's leaf codes into a double buffer.
+// A tile of <= 128 columns keeps warps 8..11 idle and costs what it costs in the narrow form.
+constexpr int W_WARPS = 12;
+constexpr int W_THREADS = 128 + W_WARPS * 32;                   // 512: launch allocation 128 registers per thread
+constexpr int W_TILE_COLS = W_WARPS * 16;                       // 192
+constexpr int W_LEVEL_BYTES = W_WARPS * STACK_ENTRY_BYTES;      // one CTA's parked partial: 96 KB
+constexpr int W_P_STAGES = 3;
+constexpr int W_L_STAGES = 2;
+constexpr int W_BAR_BYTES = 128;                                // pfull[3] pempty[3] lfull[2] lempty[2] cfull[2] cempty[2]
+constexpr int W_CODE_THREADS = 96;                              // warps 1..3 of the producer warpgroup
+constexpr int W_PROD_REGS = 32;                                 // (128 - 32) * 128 released = (160 - 128) * 384 taken
+constexpr int W_COMPUTE_REGS = 160;
+static_assert(PRUNE_T == 2, "the wide form is written for two 8-column tiles per warp");
+
+__device__ __forceinline__ int w_codes_bytes(int n_leaves) { return (W_TILE_COLS * n_leaves + 15) & ~15; }
+
+template <bool RESCALE>
+__global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PruneParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* Pring = smem;
+    uint8_t* Lring = smem + W_P_STAGES * FRAG_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Lring + W_L_STAGES * PT_SLOT_BYTES);
+    uint64_t* pfull = bars;
+    uint64_t* pempty = bars + 3;
+    uint64_t* lfull = bars + 6;
+    uint64_t* lempty = bars + 8;
+    uint64_t* cfull = bars + 10;
+    uint64_t* cempty = bars + 12;
+    Op* ops_s = reinterpret_cast<Op*>(reinterpret_cast<uint8_t*>(bars) + W_BAR_BYTES);
+    Item* items_s = reinterpret_cast<Item*>(reinterpret_cast<uint8_t*>(ops_s) + p.ops_bytes);
+    uint8_t* codes_s = reinterpret_cast<uint8_t*>(items_s) + p.items_bytes;  // two buffers of w_codes_bytes
+    const int cbytes = w_codes_bytes(p.n_leaves);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < W_P_STAGES; i++) {
+            mbar_init(&pfull[i], 1);
+            mbar_init(&pempty[i], W_WARPS);
+        }
+        for (int i = 0; i < W_L_STAGES; i++) {
+            mbar_init(&lfull[i], 1);
+            mbar_init(&lempty[i], W_WARPS);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&cfull[i], W_CODE_THREADS);
+            mbar_init(&cempty[i], W_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = tid; i < p.n_ops; i += W_THREADS) ops_s[i] = p.ops[i];
+    for (int i = tid; i < p.n_items; i += W_THREADS) items_s[i] = p.items[i];
+    __syncthreads();
+
+    if (tid < 128) {
+        // ====================================== producer warpgroup ======================================
+        reg_dealloc<W_PROD_REGS>();
+        if (tid == 0) {  // the TMA thread: P images and leaf tables, in program order, as far ahead as the rings allow
+            uint32_t pq = 0, lq = 0;
+            for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const Span sp = p.spans[find_span(p.spans, p.n_spans, tile)];
+                const double* tables = p.psets[sp.pset].tables;
+                for (int ii = 0; ii < p.n_items; ii++) {
+                    const Item it = items_s[ii];
+                    if (it.kind == ITEM_P) {
+                        const uint32_t st = pq % W_P_STAGES, u = pq / W_P_STAGES;
+                        if (u >= 1) mbar_wait(&pempty[st], (u - 1) & 1);
+                        mbar_expect_tx(&pfull[st], FRAG_BYTES);
+                        tma_bulk_g2s(Pring + st * FRAG_BYTES, tables + (size_t)it.a * PT_SLOT, FRAG_BYTES, &pfull[st]);
+                        pq++;
+                    } else if (it.kind == ITEM_LEAF) {
+                        const uint32_t st = lq % W_L_STAGES, u = lq / W_L_STAGES;
+                        if (u >= 1) mbar_wait(&lempty[st], (u - 1) & 1);
+                        mbar_expect_tx(&lfull[st], PT_SLOT_BYTES);
+                        tma_bulk_g2s(Lring + st * PT_SLOT_BYTES, tables + (size_t)it.a * PT_SLOT, PT_SLOT_BYTES, &lfull[st]);
+                        lq++;
+                    }  // ITEM_POP: nothing to stage, the owning thread reads its parked partial back itself
+                }
+            }
+        } else if (tid >= 32) {  // leaf codes of the CTA's k-th tile into buffer k % 2 (columns past the end of the span marginalise)
+            const int ctid = tid - 32;
+            uint32_t k = 0;
+            for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, k++) {
+                const Span sp = p.spans[find_span(p.spans, p.n_spans, tile)];
+                const int64_t tcol0 = (tile - sp.tile0) * W_TILE_COLS;
+                const int ncols = (int)min((int64_t)W_TILE_COLS, (int64_t)sp.ncols - tcol0);
+                if (k >= 2) mbar_wait(&cempty[k & 1], ((k >> 1) - 1) & 1);
+                uint8_t* dst = codes_s + (k & 1) * cbytes;
+                const uint8_t* src = p.codes + (size_t)(sp.col0 + tcol0) * p.n_leaves;
+                const int nbytes = ncols * p.n_leaves, total = W_TILE_COLS * p.n_leaves;
+                for (int i = ctid; i < total; i += W_CODE_THREADS) dst[i] = (i < nbytes) ? src[i] : (uint8_t)64;
+                mbar_arrive(&cfull[k & 1]);
+            }
+        }
+        return;
+    }
+
+    // ========================================= compute warps =========================================
+    // 160 registers hold 128 of partials and accumulators; everything that is needed once per tile only
+    // (where the tile's results go, which prior to use) lives in a per-warp scratch line of shared memory,
+    // and addresses are kept as 32-bit shared-memory offsets, so that the loop scalars stay in registers.
+    reg_alloc<W_COMPUTE_REGS>();
+    const int ctid = tid - 128, lane = ctid & 31, cw = ctid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t pq = 0, lq = 0;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t lring0 = smem0 + W_P_STAGES * FRAG_BYTES + t * 16;
+    const uint32_t codes00 = smem_u32(codes_s) + (cw * WARP_COLS + g) * p.n_leaves;  // this lane's first column in buffer 0
+    int64_t* const scratch = reinterpret_cast<int64_t*>(codes_s + 2 * cbytes) + cw * 4;  // {out index of column 0 of the tile, pset}
+    // No start-up offsets and no barrier among the warps of a sub-partition: left alone they spread out over
+    // the edge by themselves (timeline: thousands of clocks apart). Both were measured: offsets of 0.8-3 us
+    // change nothing, re-aligning the three warps after every contraction costs 6 points (83.3 %).
+#ifdef PCSF_TIMELINE
+    int tl_n = 0;
+#endif
+
+    for (uint32_t k = 0; (int64_t)blockIdx.x + (int64_t)k * gridDim.x < p.n_tiles; k++) {
+        bool warp_active;
+        int ncols;
+        {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+            const Span sp = p.spans[find_span(p.spans, p.n_spans, tile)];
+            const int64_t tcol0 = (tile - sp.tile0) * W_TILE_COLS;  // first column of the tile within the span
+            ncols = (int)min((int64_t)W_TILE_COLS, (int64_t)sp.ncols - tcol0);
+            warp_active = cw * WARP_COLS < ncols;
+            if (lane == 0) {
+                scratch[0] = sp.out0 + tcol0;
+                scratch[1] = sp.pset;
+            }
+            __syncwarp();
+        }
+        mbar_wait(&cfull[k & 1], (k >> 1) & 1);
+        const uint32_t codes0 = codes00 + (k & 1) * cbytes;  // code row of this lane's column g (column 8+g: + 8 n_leaves)
+
+        double cur[2][8][2];
+        int esum[2] = {0, 0};  // power-of-two exponent taken out of each column so far (rescale option)
+#pragma unroll
+        for (int T = 0; T < 2; T++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) cur[T][j][0] = cur[T][j][1] = 1.0;
+
+        // leaf message of leaf `leaf` for this lane's columns, out of the staged P^T table: row = code, 16 B at state 8j+2t
+        auto leaf_rows = [&](uint32_t st, int leaf, uint32_t& a0, uint32_t& a1) {
+            uint32_t c0 = lds_u8(codes0 + leaf), c1 = lds_u8(codes0 + 8 * p.n_leaves + leaf);
+            c0 = c0 > 64 ? 64 : c0;
+            c1 = c1 > 64 ? 64 : c1;
+            const uint32_t base = lring0 + st * PT_SLOT_BYTES;
+            a0 = base + c0 * 512;
+            a1 = base + c1 * 512;
+        };
+        auto park = [&](int level) {  // this thread's 256 bytes of stack level `level`
+            return p.global_stack + ((size_t)blockIdx.x * p.n_levels + level) * W_LEVEL_BYTES + (size_t)cw * STACK_ENTRY_BYTES + lane * 16;
+        };
+        auto park_exp = [&](int level) {
+            return p.global_exp + ((size_t)blockIdx.x * p.n_levels + level) * W_TILE_COLS + cw * WARP_COLS + g;
+        };
+
+        for (int oi = 0; oi < p.n_ops; oi++) {
+            const Op op = ops_s[oi];
+            if (op.kind == OP_CHERRY) {
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    const uint32_t st = lq % W_L_STAGES;
+                    mbar_wait(&lfull[st], (lq / W_L_STAGES) & 1);
+                    if (warp_active) {
+                        uint32_t a0, a1;
+                        leaf_rows(st, kk ? op.b : op.a, a0, a1);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const double2 v0 = lds_f64x2(a0 + j * 64), v1 = lds_f64x2(a1 + j * 64);
+                            cur[0][j][0] = kk ? cur[0][j][0] * v0.x : v0.x;
+                            cur[0][j][1] = kk ? cur[0][j][1] * v0.y : v0.y;
+                            cur[1][j][0] = kk ? cur[1][j][0] * v1.x : v1.x;
+                            cur[1][j][1] = kk ? cur[1][j][1] * v1.y : v1.y;
+                        }
+                    }
+                    release_stage(&lempty[st], lane);
+                    lq++;
+                }
+                continue;
+            }
+            if (op.kind == OP_ROOT) {
+                if (warp_active) {
+                    const int64_t out0 = scratch[0];
+                    const PSet ps = p.psets[scratch[1]];
+                    const double2* pr = reinterpret_cast<const double2*>(ps.prior + 2 * t);
+                    const double2* lp = reinterpret_cast<const double2*>(ps.logprior + 2 * t);
+#pragma unroll
+                    for (int T = 0; T < 2; T++) {
+                        double zp = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const double2 pj = __ldg(pr + 4 * j);
+                            cur[T][j][0] *= pj.x;  // alpha_root[x] * prior[x]
+                            cur[T][j][1] *= pj.y;
+                            zp += cur[T][j][0];
+                            zp += cur[T][j][1];
+                        }
+                        zp += __shfl_xor_sync(0xffffffffu, zp, 1);
+                        zp += __shfl_xor_sync(0xffffffffu, zp, 2);
+                        double ap = 0.0;
+                        if (zp != 0.0) {  // PhyloLik.ml:131-132: impossible data => zero posterior
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const double2 lj = __ldg(lp + 4 * j);
+                                ap += (cur[T][j][0] / zp) * lj.x;
+                                ap += (cur[T][j][1] / zp) * lj.y;
+                            }
+                        }
+                        ap += __shfl_xor_sync(0xffffffffu, ap, 1);
+                        ap += __shfl_xor_sync(0xffffffffu, ap, 2);
+                        const int c = cw * WARP_COLS + 8 * T + g;
+                        if (t == 0 && c < ncols) {
+                            p.out_logz[out0 + c] = (RESCALE && esum[T]) ? log(zp) + (double)esum[T] * 0.6931471805599453 : log(zp);
+                            p.out_anc[out0 + c] = ap;
+                        }
+                    }
+                }
+                continue;
+            }
+            // ------------------------------ K3: contraction over one internal edge ------------------------------
+            TL_MARK(oi * 8 + 0);
+            const uint32_t pst = pq % W_P_STAGES;
+            mbar_wait(&pfull[pst], (pq / W_P_STAGES) & 1);
+            TL_MARK(oi * 8 + 1);
+            double acc[2][8][2];
+            if (warp_active) {
+                const double* Pb = reinterpret_cast<const double*>(Pring + pst * FRAG_BYTES) + lane;
+#pragma unroll
+                for (int T = 0; T < 2; T++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[T][j][0] = acc[T][j][1] = 0.0;
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double bf = Pb[(j * 16 + s) * 32];
+#pragma unroll
+                        for (int T = 0; T < 2; T++) dmma(acc[T][j][0], acc[T][j][1], cur[T][s >> 1][s & 1], bf);
+                    }
+                }
+            }
+            release_stage(&pempty[pst], lane);
+            pq++;
+            TL_MARK(oi * 8 + 2);
+            // ------------------------------ epilogue ------------------------------
+            if (op.kind == OP_GEMM_PUSH) {  // park the message; only this thread ever touches these addresses
+                if (warp_active) {
+                    double2* slot = reinterpret_cast<double2*>(park(op.c));
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+#if !defined(W_ABL_NOPARK)
+                            slot[(T * 8 + j) * 32] = make_double2(acc[T][j][0], acc[T][j][1]);
+#endif
+                        }
+                    if (RESCALE) {  // the parked message keeps its exponent; the sibling subtree starts at 0
+#pragma unroll
+                        for (int T = 0; T < 2; T++) {
+                            if (t == 0) park_exp(op.c)[8 * T] = esum[T];
+                            esum[T] = 0;
+                        }
+                    }
+                }
+            } else if (op.kind == OP_GEMM_POP) {
+                if (warp_active) {
+                    const double2* slot = reinterpret_cast<const double2*>(park(op.c));
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+#if defined(W_ABL_NOPARK)
+                            cur[T][j][0] = acc[T][j][0];
+                            cur[T][j][1] = acc[T][j][1];
+#elif defined(W_ABL_NOMUL)
+                            const double2 v = slot[(T * 8 + j) * 32];
+                            cur[T][j][0] = __longlong_as_double(__double_as_longlong(acc[T][j][0]) ^ (__double_as_longlong(v.x) & 1));
+                            cur[T][j][1] = __longlong_as_double(__double_as_longlong(acc[T][j][1]) ^ (__double_as_longlong(v.y) & 1));
+#else
+                            const double2 v = slot[(T * 8 + j) * 32];
+                            cur[T][j][0] = acc[T][j][0] * v.x;
+                            cur[T][j][1] = acc[T][j][1] * v.y;
+#endif
+                        }
+                    if (RESCALE) {
+                        __syncwarp();  // lane t == 0 of the quad wrote the exponents at the push
+#pragma unroll
+                        for (int T = 0; T < 2; T++) esum[T] += park_exp(op.c)[8 * T];
+                        rescale_columns(cur, esum);
+                    }
+                }
+            } else {  // OP_GEMM_LEAF
+                const uint32_t st = lq % W_L_STAGES;
+                mbar_wait(&lfull[st], (lq / W_L_STAGES) & 1);
+                TL_MARK(oi * 8 + 3);
+                if (warp_active) {
+#if defined(W_ABL_NOLEAF)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { cur[0][j][0] = acc[0][j][0]; cur[0][j][1] = acc[0][j][1]; cur[1][j][0] = acc[1][j][0]; cur[1][j][1] = acc[1][j][1]; }
+#else
+                    uint32_t a0, a1;
+                    leaf_rows(st, op.b, a0, a1);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double2 v0 = lds_f64x2(a0 + j * 64), v1 = lds_f64x2(a1 + j * 64);
+#if defined(W_ABL_NOMUL)
+                        cur[0][j][0] = __longlong_as_double(__double_as_longlong(acc[0][j][0]) ^ (__double_as_longlong(v0.x) & 1));
+                        cur[0][j][1] = __longlong_as_double(__double_as_longlong(acc[0][j][1]) ^ (__double_as_longlong(v0.y) & 1));
+                        cur[1][j][0] = __longlong_as_double(__double_as_longlong(acc[1][j][0]) ^ (__double_as_longlong(v1.x) & 1));
+                        cur[1][j][1] = __longlong_as_double(__double_as_longlong(acc[1][j][1]) ^ (__double_as_longlong(v1.y) & 1));
+#else
+                        cur[0][j][0] = acc[0][j][0] * v0.x;
+                        cur[0][j][1] = acc[0][j][1] * v0.y;
+                        cur[1][j][0] = acc[1][j][0] * v1.x;
+                        cur[1][j][1] = acc[1][j][1] * v1.y;
+#endif
+                    }
+#endif
+                    if (RESCALE) rescale_columns(cur, esum);
+                }
+                release_stage(&lempty[st], lane);
+                lq++;
+            }
+            TL_MARK(oi * 8 + 4);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cempty[k & 1]);  // this warp is done with the tile's codes
     }
 }
 
