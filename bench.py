@@ -282,9 +282,10 @@ def main():
 
     # sanity: the scores are finite and the two halves separate (coding half scores higher)
     score = (10.0 / np.log(10.0)) * (outs[0][0] - outs[0][1])
-    assert np.isfinite(score).all()
-    f0 = score[0::FRAMES]
-    assert f0[: A // 2].mean() > f0[A // 2:].mean()
+    if not os.environ.get("PCSF_BENCH_NO_SANITY"):  # unset except for timing-only kernel ablations (tools/ab.sh)
+        assert np.isfinite(score).all()
+        f0 = score[0::FRAMES]
+        assert f0[: A // 2].mean() > f0[A // 2:].mean()
 
     if world > 1:
         tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)

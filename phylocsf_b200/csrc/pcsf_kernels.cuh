@@ -896,9 +896,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                     for (int T = 0; T < 2; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-#if !defined(W_ABL_NOPARK)
                             slot[(T * 8 + j) * 32] = make_double2(acc[T][j][0], acc[T][j][1]);
-#endif
                         }
                     if (RESCALE) {  // the parked message keeps its exponent; the sibling subtree starts at 0
 #pragma unroll
@@ -915,18 +913,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                     for (int T = 0; T < 2; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-#if defined(W_ABL_NOPARK)
-                            cur[T][j][0] = acc[T][j][0];
-                            cur[T][j][1] = acc[T][j][1];
-#elif defined(W_ABL_NOMUL)
-                            const double2 v = slot[(T * 8 + j) * 32];
-                            cur[T][j][0] = __longlong_as_double(__double_as_longlong(acc[T][j][0]) ^ (__double_as_longlong(v.x) & 1));
-                            cur[T][j][1] = __longlong_as_double(__double_as_longlong(acc[T][j][1]) ^ (__double_as_longlong(v.y) & 1));
-#else
                             const double2 v = slot[(T * 8 + j) * 32];
                             cur[T][j][0] = acc[T][j][0] * v.x;
                             cur[T][j][1] = acc[T][j][1] * v.y;
-#endif
                         }
                     if (RESCALE) {
                         __syncwarp();  // lane t == 0 of the quad wrote the exponents at the push
@@ -940,28 +929,16 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                 mbar_wait(&lfull[st], (lq / W_L_STAGES) & 1);
                 TL_MARK(oi * 8 + 3);
                 if (warp_active) {
-#if defined(W_ABL_NOLEAF)
-#pragma unroll
-                    for (int j = 0; j < 8; j++) { cur[0][j][0] = acc[0][j][0]; cur[0][j][1] = acc[0][j][1]; cur[1][j][0] = acc[1][j][0]; cur[1][j][1] = acc[1][j][1]; }
-#else
                     uint32_t a0, a1;
                     leaf_rows(st, op.b, a0, a1);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const double2 v0 = lds_f64x2(a0 + j * 64), v1 = lds_f64x2(a1 + j * 64);
-#if defined(W_ABL_NOMUL)
-                        cur[0][j][0] = __longlong_as_double(__double_as_longlong(acc[0][j][0]) ^ (__double_as_longlong(v0.x) & 1));
-                        cur[0][j][1] = __longlong_as_double(__double_as_longlong(acc[0][j][1]) ^ (__double_as_longlong(v0.y) & 1));
-                        cur[1][j][0] = __longlong_as_double(__double_as_longlong(acc[1][j][0]) ^ (__double_as_longlong(v1.x) & 1));
-                        cur[1][j][1] = __longlong_as_double(__double_as_longlong(acc[1][j][1]) ^ (__double_as_longlong(v1.y) & 1));
-#else
                         cur[0][j][0] = acc[0][j][0] * v0.x;
                         cur[0][j][1] = acc[0][j][1] * v0.y;
                         cur[1][j][0] = acc[1][j][0] * v1.x;
                         cur[1][j][1] = acc[1][j][1] * v1.y;
-#endif
                     }
-#endif
                     if (RESCALE) rescale_columns(cur, esum);
                 }
                 release_stage(&lempty[st], lane);
