@@ -66,6 +66,14 @@ int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
  * The environment variable PCSF_RESCALE=1 sets it for every new context (used by the command line).
  */
 #define PCSF_OPT_RESCALE 1
+/*
+ * PCSF_OPT_PRUNE_FORM: which form of the pruning kernel a launch uses. 0 (default) = chosen per launch from
+ * the lengths of its spans; 1 = narrow (128-column tiles, two compute warps per SM sub-partition);
+ * 2 = wide (192-column tiles, three). Both forms compute every column with the same arithmetic in the same
+ * order: results are bit-identical (tested). The environment variable PCSF_WIDE=0/1 forces narrow/wide
+ * for every new context.
+ */
+#define PCSF_OPT_PRUNE_FORM 2
 int pcsf_option_set(pcsf_ctx *ctx, int option, int64_t value);
 
 /*

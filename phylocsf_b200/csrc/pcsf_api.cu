@@ -468,6 +468,11 @@ int pcsf_option_set(pcsf_ctx* ctx, int option, int64_t value) {
         ctx->rescale = value ? 1 : 0;
         return PCSF_OK;
     }
+    if (option == PCSF_OPT_PRUNE_FORM) {
+        if (value < 0 || value > 2) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_PRUNE_FORM takes 0, 1 or 2");
+        ctx->wide = value == 0 ? -1 : (int)value - 1;
+        return PCSF_OK;
+    }
     return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: unknown option");
 }
 

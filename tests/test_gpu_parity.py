@@ -99,6 +99,61 @@ def test_fixed_simulated_58mammals_ragged(mammals58):
     ctx.close()
 
 
+@pytest.mark.parametrize("pset", ["58mammals", "120mammals", "12flies"])
+def test_both_kernel_forms_match_oracle_and_each_other(params_base, pset):
+    """The narrow (128-column tiles) and the wide (192-column tiles, leaf messages read from the staged P^T
+    table, thread-owned parking) form of the pruning kernel, each forced with PCSF_OPT_PRUNE_FORM: both within
+    1e-7 dB of the oracle and bit-identical to each other, per region and per column, on ragged region lengths
+    around both tile sizes with gaps and missing species; evaluated twice to catch run-to-run differences."""
+    import phylocsf_b200 as pb
+
+    ps = H.oracle_paramset(params_base, pset)
+    n = ps.tree.n_leaves
+    rng = np.random.default_rng(17)
+    mc, mn = ps.model.coding_model.model(1.0), ps.model.noncoding_model.model(1.0)
+    lens = [191, 192, 193, 1, 0, 127, 128, 129, 385, 16, 15, 17, 640, 64]
+    if pset == "120mammals":
+        lens = [193, 1, 129, 40]  # keeps the CPU oracle affordable
+    regs = []
+    for i, L in enumerate(lens):
+        regs.append(o.simulate_columns(mc if i % 2 == 0 else mn, L, rng) if L else np.zeros((0, n), dtype=np.uint8))
+    regs[0][:, n // 3] = 64
+    regs[2][5, :] = 64
+    regs[2][20:40, n // 2:] = 64
+    lo, eo = H.oracle_fixed(ps, regs)
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    got = {}
+    for form in (pb.Context.FORM_NARROW, pb.Context.FORM_WIDE):
+        ctx.option_set(pb.Context.OPT_PRUNE_FORM, form)
+        for rep in range(2):
+            lpr, elpr, st = ctx.lpr_all([0, 1])
+            cols = [ctx.column_terms(m) for m in (0, 1)]
+            assert (st == 0).all()
+            assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB and np.abs(H.DB * (elpr - eo)).max() < TOL_DB
+            key = (lpr.copy(), elpr.copy(), [c[0].copy() for c in cols], [c[1].copy() for c in cols])
+            if form in got:
+                prev = got[form]
+                assert (prev[0] == key[0]).all() and (prev[1] == key[1]).all()
+                assert all((a == b).all() for a, b in zip(prev[2], key[2]))
+            got[form] = key
+        # one span per (model, region): tiles start at region starts
+        em = np.repeat([0, 1], len(regs))
+        er = np.tile(np.arange(len(regs)), 2)
+        l2, e2, _ = ctx.lpr(em, np.zeros_like(em), er)
+        assert (l2.reshape(2, -1) == got[form][0]).all() and (e2.reshape(2, -1) == got[form][1]).all()
+    a, b = got[pb.Context.FORM_NARROW], got[pb.Context.FORM_WIDE]
+    assert all((x == y).all() for x, y in zip(a[2], b[2])) and all((x == y).all() for x, y in zip(a[3], b[3]))  # per column
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    ctx.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_AUTO)
+    with pytest.raises(Exception):
+        ctx.option_set(pb.Context.OPT_PRUNE_FORM, 3)
+    ctx.close()
+
+
 @pytest.mark.parametrize("pset", ["120mammals", "100vertebrates", "29mammals", "7yeast"])
 def test_fixed_other_trees(params_base, pset):
     ps = H.oracle_paramset(params_base, pset)
@@ -371,8 +426,9 @@ def _lpr_extended_precision(model, codes):
     return float(np.log(z).sum())
 
 
-def test_rescale_option_rescues_underflow(params_base):
-    """PCSF_OPT_RESCALE: uniform-random columns on the 120-leaf tree underflow to -inf without it (the
+@pytest.mark.parametrize("form", [1, 2])
+def test_rescale_option_rescues_underflow(params_base, form):
+    """(in both forms of the pruning kernel) PCSF_OPT_RESCALE: uniform-random columns on the 120-leaf tree underflow to -inf without it (the
     reference's behaviour); with it the score is finite and equals an extended-precision evaluation.
     Columns that never get near the threshold are unchanged to the last bit."""
     if np.finfo(np.longdouble).minexp > -16000:
@@ -387,6 +443,7 @@ def test_rescale_option_rescues_underflow(params_base):
     ctx.pt_build(1, [1.0])
     off, codes = H.regions_to_batch(regs)
     ctx.batch_upload(off, codes)
+    ctx.option_set(2, form)
     lpr0, elpr0, st0 = ctx.lpr_all([0, 1])
     assert np.isneginf(lpr0[:, 0]).all() and np.isfinite(lpr0[:, 1]).all()
     ctx.option_set(1, 1)
