@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "codon_model.hpp"
@@ -187,6 +188,68 @@ inline double bls_score(const NewickPtr& nt, const std::vector<std::string>& aln
     }
     return total / (newick_total_length(*nt) * (double)(hi - lo + 1));
 }
+
+// The same score, column by column, as a function of WHICH tree leaves are present in the column: the pruned
+// tree's total length is computed with the reference's own recipe (Newick.subtree + total_length, as above) once
+// per distinct set of leaves and memoised per thread, so every region of every alignment sums precomputed
+// doubles in the reference's order. Bit-identical to bls_score.
+class BlsTable {
+  public:
+    struct Mask {
+        uint64_t w[4] = {0, 0, 0, 0};
+        void set(int l) { w[l >> 6] |= 1ull << (l & 63); }
+        bool operator==(const Mask& o) const { return w[0] == o.w[0] && w[1] == o.w[1] && w[2] == o.w[2] && w[3] == o.w[3]; }
+    };
+    static constexpr int kMaxLeaves = 256;
+    BlsTable() = default;
+    BlsTable(NewickPtr tree, const std::vector<std::string>& leaf_labels) : nt_(std::move(tree)) {
+        for (size_t l = 0; l < leaf_labels.size(); l++) index_[leaf_labels[l]] = (int)l;
+        total_ = newick_total_length(*nt_);
+        usable_ = (int)leaf_labels.size() <= kMaxLeaves;
+    }
+    bool usable() const { return usable_; }
+    static bool counts(char c) { return !(c == '-' || c == '.' || c == 'N'); }  // src/PhyloCSF.ml:257
+    double column(const Mask& m) const {
+        static thread_local const BlsTable* owner = nullptr;
+        static thread_local std::unordered_map<Mask, double, Hash> memo;
+        if (owner != this) {
+            memo.clear();
+            owner = this;
+        }
+        auto it = memo.find(m);
+        if (it != memo.end()) return it->second;
+        NewickPtr st = newick_subtree(
+            [&](const std::string& sp) {
+                auto f = index_.find(sp);
+                return f != index_.end() && ((m.w[f->second >> 6] >> (f->second & 63)) & 1);
+            },
+            nt_);
+        const double v = st ? newick_total_length(*st) : 0.0;
+        if (memo.size() > (1u << 20)) memo.clear();
+        memo.emplace(m, v);
+        return v;
+    }
+    // score of positions lo..hi given a way to get the mask of position i
+    template <class MaskAt>
+    double region(int lo, int hi, MaskAt&& mask_at) const {
+        double total = 0.0;
+        for (int i = lo; i <= hi; i++) total += column(mask_at(i));
+        return total / (total_ * (double)(hi - lo + 1));
+    }
+
+  private:
+    struct Hash {
+        size_t operator()(const Mask& m) const {
+            uint64_t h = 0x9e3779b97f4a7c15ull;
+            for (uint64_t x : m.w) h = (h ^ x) * 0xff51afd7ed558ccdull, h ^= h >> 32;
+            return (size_t)h;
+        }
+    };
+    NewickPtr nt_;
+    std::unordered_map<std::string, int> index_;
+    double total_ = 0.0;
+    bool usable_ = false;
+};
 
 inline std::string translate(const std::string& dna) {
     std::string pp(dna.size() / 3, '?');

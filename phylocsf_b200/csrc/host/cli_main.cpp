@@ -315,7 +315,8 @@ int main(int argc, char** argv) {
             const double t2 = now();
             drv.finish(std::cout);
             std::cerr << "host profile: waited for readers " << t_wait << " s, appended (incl. batch hand-off) " << t_append
-                      << " s, final drain " << now() - t2 << " s, " << nt << " reader threads\n";
+                      << " s, final drain " << now() - t2 << " s, " << nt << " reader threads; fast reader took " << drv.n_fast
+                      << " alignments, general reader " << drv.n_general << "\n";
         }
         drv.finish(std::cout);
     } catch (const std::exception& e) {

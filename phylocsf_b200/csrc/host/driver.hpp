@@ -10,6 +10,7 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -127,6 +128,7 @@ struct AlnJob {
     // region k is columns [reg_col0[k], reg_col0[k] + reg_ncols[k]) of staged frame reg_frame[k]
     std::vector<int> reg_frame, reg_col0, reg_ncols;
     std::string failure;  // per-alignment failure text (no ORFs)
+    std::vector<double> bls;  // --bls of every candidate region, when the reader already computed it
 };
 
 // The regions of many alignments, staged and scored together on one GPU.
@@ -164,6 +166,8 @@ class DeviceScorer {
   public:
     DeviceScorer(const Options& o, const ParamSet& pset, int device) : opt(o), ps(pset) {
         n_leaves = ps.tree.n_leaves;
+        leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
+        if (o.bls) bls_table = BlsTable(ps.nt, leaf_labels);
         if (o.strategy == STRAT_NOP) return;
         if (pcsf_create(device, &ctx) != PCSF_OK)
             throw failure("phylocsf_b200: no usable CUDA device " + std::to_string(device) + " (there is no CPU fallback)");
@@ -228,8 +232,29 @@ class DeviceScorer {
     const ParamSet& ps;
     pcsf_ctx* ctx = nullptr;
     int n_leaves = 0;
+    std::vector<std::string> leaf_labels;
+    BlsTable bls_table;
     const Batch* cur = nullptr;
     std::mutex mu;  // one batch at a time on the device
+
+    // --bls of region k of alignment j (src/PhyloCSF.ml:252-262)
+    double region_bls(const AlnJob& j, size_t k) const {
+        if (!j.bls.empty()) return j.bls[k];
+        const Region& rg = j.regions[k];
+        const std::vector<std::string>& rows = rg.rc ? j.rc_aln : j.aln;
+        if (!bls_table.usable()) return bls_score(ps.nt, rows, j.which_row, rg.lo, rg.hi);
+        std::vector<int> leaf_row(n_leaves, -1);
+        for (int l = 0; l < n_leaves; l++) {
+            auto it = j.which_row.find(leaf_labels[l]);
+            if (it != j.which_row.end()) leaf_row[l] = it->second;
+        }
+        return bls_table.region(rg.lo, rg.hi, [&](int i) {
+            BlsTable::Mask m;
+            for (int l = 0; l < n_leaves; l++)
+                if (leaf_row[l] >= 0 && BlsTable::counts(rows[leaf_row[l]][i])) m.set(l);
+            return m;
+        });
+    }
 
     void check(int rc) {
         if (rc != PCSF_OK && rc != PCSF_ERR_NUMERIC) throw failure(std::string("phylocsf_b200: ") + pcsf_last_error(ctx));
@@ -480,7 +505,7 @@ class DeviceScorer {
             out << j.name << "\t" << ty << "\t" << fmt4(s.score);
             if (opt.frames != 1 || opt.orf != AsIs) out << "\t" << rg.lo << "\t" << rg.hi;
             if (opt.frames == 6) out << "\t" << (rg.rc ? '-' : '+');
-            if (opt.bls) out << "\t" << fmt4(bls_score(ps.nt, rows, j.which_row, rg.lo, rg.hi));
+            if (opt.bls) out << "\t" << fmt4(region_bls(j, (size_t)k));
             if (opt.anc_comp) out << "\t" << fmt4(s.anc_comp);
             const std::string refdna = (opt.dna || opt.aa) ? rows[0].substr(rg.lo, rg.hi - rg.lo + 1) : std::string();
             if (opt.dna) out << "\t" << refdna;
@@ -513,6 +538,7 @@ class Driver {
         leaf_labels.assign(ps.tree.labels.begin(), ps.tree.labels.begin() + n_leaves);
         leaf_set.insert(leaf_labels.begin(), leaf_labels.end());
         for (int l = 0; l < n_leaves; l++) leaf_index[leaf_labels[l]] = l;
+        if (o.bls) bls_table = BlsTable(ps.nt, leaf_labels);
         for (int c = 0; c < 256; c++) nt_lut[c] = 0;
         for (const char* q = "ACGTacgtNn-"; *q; q++) nt_lut[(unsigned char)*q] = (uint8_t)*q;  // Code.ml:39-51
         nt_lut[(unsigned char)'u'] = 't';                                                        // src/PhyloCSF.ml:266,285
@@ -545,7 +571,8 @@ class Driver {
     // repeated species, ragged rows, a gapped reference - returns false WITHOUT judging it: the caller then
     // runs prepare(), which applies the reference's checks in the reference's order with its messages.
     bool prepare_fast(const std::string& name, const char* data, size_t n, Prepared& p, std::vector<uint8_t>& nt_buf) const {
-        if (opt.orf != AsIs || opt.remove_ref_gaps || opt.bls || opt.strategy == STRAT_OMEGA) return false;
+        if (opt.orf != AsIs || opt.strategy == STRAT_OMEGA) return false;
+        if (opt.bls && !bls_table.usable()) return false;
         if (n == 0 || data[0] != '>') return false;
         struct Seg { const char *b, *e; };
         struct Rec { int leaf; size_t seg0, seg1; };
@@ -587,7 +614,7 @@ class Driver {
             for (size_t k = r.seg0; k < r.seg1; k++) L += (size_t)(segs[k].e - segs[k].b);
             return L;
         };
-        const size_t len = rec_len(recs[0]);
+        size_t len = rec_len(recs[0]);
         if (len == 0 || len > (size_t)INT32_MAX) return false;
         for (const Rec& r : recs)
             if (rec_len(r) != len) return false;
@@ -630,6 +657,24 @@ class Driver {
             }
             if (bad) return reject();
         }
+        if (opt.remove_ref_gaps && memchr(block + (size_t)recs[0].leaf * len, '-', len)) {
+            // --removeRefGaps (src/PhyloCSF.ml:122-132): drop the columns that are gapped in the reference row, in
+            // place: rows are compacted in ascending order, so a row never overwrites one still to be read
+            static thread_local std::vector<uint32_t> keep;
+            keep.clear();
+            const uint8_t* ref0 = block + (size_t)recs[0].leaf * len;
+            for (size_t i = 0; i < len; i++)
+                if (ref0[i] != '-') keep.push_back((uint32_t)i);
+            const size_t nl = keep.size();
+            if (nl == 0) return reject();
+            for (int l = 0; l < n_leaves; l++) {
+                const uint8_t* src = block + (size_t)l * len;
+                uint8_t* dst = block + (size_t)l * nl;
+                for (size_t j = 0; j < nl; j++) dst[j] = src[keep[j]];
+            }
+            len = nl;
+            nt_buf.resize(off0 + (size_t)n_leaves * len);
+        }
         const uint8_t* ref = block + (size_t)recs[0].leaf * len;
         if (!opt.allow_ref_gaps && memchr(ref, '-', len)) return reject();
         AlnJob& job = p.job;
@@ -638,6 +683,18 @@ class Driver {
         if (opt.frames == 6 && (opt.dna || opt.aa)) job.rc_aln.assign(1, revcomp(job.aln[0]));
         job.regions = candidate_regions(job.aln[0], AsIs, opt.frames, opt.min_codons);
         for (const Region& r : job.regions) p.region_cols.push_back(r.hi - r.lo + 1 >= 3 ? (r.hi - r.lo + 1) / 3 : 0);
+        if (opt.bls) {  // per position: which leaves carry a nucleotide -> the pruned tree's length (memoised)
+            static thread_local std::vector<BlsTable::Mask> masks;
+            masks.assign(len, BlsTable::Mask());
+            for (int l = 0; l < n_leaves; l++) {
+                if (!seen[l]) continue;
+                const uint8_t* row = block + (size_t)l * len;
+                for (size_t i = 0; i < len; i++)
+                    if (BlsTable::counts((char)row[i])) masks[i].set(l);
+            }
+            for (const Region& r : job.regions)  // a '-' strand region reads the rows backwards
+                job.bls.push_back(bls_table.region(r.lo, r.hi, [&](int i) { return masks[r.rc ? len - 1 - (size_t)i : (size_t)i]; }));
+        }
         p.nt_form = true;
         p.nt_off = off0;
         p.aln_len = (int32_t)len;
@@ -646,7 +703,11 @@ class Driver {
     // prepare() on raw text: the fast form when it applies, else the general one on the text's lines
     Prepared prepare_text(const std::string& name, const char* data, size_t n, std::vector<uint8_t>& nt_buf) const {
         Prepared p;
-        if (prepare_fast(name, data, n, p, nt_buf)) return p;
+        if (prepare_fast(name, data, n, p, nt_buf)) {
+            n_fast++;
+            return p;
+        }
+        n_general++;
         std::vector<std::string> lines;
         const char *q = data, *end = data + n;
         while (q < end) {  // like std::getline
@@ -753,6 +814,7 @@ class Driver {
         return append(prepare(name, lines), out);
     }
     size_t jobs_in_batch() const { return batch.jobs.size(); }
+    mutable std::atomic<int64_t> n_fast{0}, n_general{0};  // alignments taken by the fast / the general reader
 
     // Hand the current batch to the next GPU (round-robin). Up to two batches per device are in flight: one
     // being scored, and either one waiting for the device or one whose report is being rendered.
@@ -789,6 +851,7 @@ class Driver {
     std::vector<std::string> leaf_labels;
     std::set<std::string> leaf_set;
     std::unordered_map<std::string, int> leaf_index;  // species -> tree leaf
+    BlsTable bls_table;
     uint8_t nt_lut[256];                              // alignment character -> staged character, 0 = not allowed
     std::vector<std::unique_ptr<DeviceScorer>> dev;
     Batch batch;

@@ -64,6 +64,9 @@ NOP_CASES = [
      dict(orf="ToOrFromStop", frames=6, remove_ref_gaps=True, all_scores=True, min_codons=1)),
     ("29mammals", "ALDH2.exon5.fa", ["--species=Human,Mouse,Rat,Dog,Cow,Horse", "--bls", "--frames=3"],
      dict(species=["Human", "Mouse", "Rat", "Dog", "Cow", "Horse"], bls=True, frames=3)),
+    # AsIs regions of an alignment with a gapped reference: the fast reader compacts the rows itself
+    ("29mammals", "Aldh2.mRNA.fa", ["--removeRefGaps", "--frames=6", "--bls", "--allScores", "--aa"],
+     dict(remove_ref_gaps=True, frames=6, bls=True, all_scores=True, aa=True)),
 ]
 
 
@@ -241,6 +244,8 @@ def test_reference_goldens_through_the_cli(params_base):
     ("29mammals", "Aldh2.mRNA.fa", ["--strategy=fixed", "--orf=ATGStop", "--frames=3", "--removeRefGaps", "--allScores"],
      dict(strategy="fixed", orf="ATGStop", frames=3, remove_ref_gaps=True, all_scores=True)),
     ("12flies", "tal-AA.fa", ["--strategy=omega", "--frames=3", "--allScores", "--debug"], dict(strategy="omega", frames=3, all_scores=True, debug=True)),
+    ("29mammals", "Aldh2.mRNA.fa", ["--strategy=fixed", "--removeRefGaps", "--frames=6", "--bls", "--allScores", "--ancComp"],
+     dict(strategy="fixed", remove_ref_gaps=True, frames=6, bls=True, all_scores=True, anc_comp=True)),
     # fixed + ORF search on both strands: scored from per-column terms of whole frames (frame mode)
     ("29mammals", "Aldh2.mRNA.fa", ["--strategy=fixed", "--orf=StopStop3", "--frames=6", "--removeRefGaps", "--allScores", "--ancComp", "--debug", "--minCodons=30"],
      dict(strategy="fixed", orf="StopStop3", frames=6, remove_ref_gaps=True, all_scores=True, anc_comp=True, debug=True, min_codons=30)),
