@@ -1141,8 +1141,11 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
                 const int p_ = pp[k], q_ = pq[k];
                 const double c = rc[k], s = rs[k];
                 const double apk = A[p_ * 65 + col], aqk = A[q_ * 65 + col];
-                A[p_ * 65 + col] = c * apk - s * aqk;
-                A[q_ * 65 + col] = s * apk + c * aqk;
+                // the rotated pair itself ends up exactly zero (annihilated, or flushed when it no longer registers
+                // against the diagonal), as in the host's Jacobi: without this the off-diagonal norm stalls at
+                // rounding level above the stopping threshold and every matrix runs all 40 sweeps instead of ~9
+                A[p_ * 65 + col] = col == q_ ? 0.0 : c * apk - s * aqk;
+                A[q_ * 65 + col] = col == p_ ? 0.0 : s * apk + c * aqk;
             }
             __syncthreads();
         }

@@ -55,7 +55,8 @@ open(lst, "w").write(("\n".join(names) + "\n") * REPEAT)
 N *= REPEAT
 env = dict(os.environ, PHYLOCSF_BASE=base)
 t0 = time.perf_counter()
-r = subprocess.run([os.path.join(ROOT, "phylocsf_b200", "bin", "PhyloCSF"), pset, lst, "--files"] + flags, env=env, capture_output=True, text=True)
+wrap = os.environ.get("PCSF_NCU_WRAP", "").split()  # e.g. an ncu command line, for per-kernel time splits
+r = subprocess.run(wrap + [os.path.join(ROOT, "phylocsf_b200", "bin", "PhyloCSF"), pset, lst, "--files"] + flags, env=env, capture_output=True, text=True)
 dt = time.perf_counter() - t0
 lines = r.stdout.splitlines()
 print(json.dumps({"paramset": pset, "alignments": N, "codons": ncod, "flags": flags, "rc": r.returncode, "seconds": dt,
