@@ -274,8 +274,13 @@ int main(int argc, char** argv) {
                 stop = true;
             }
             cv_space.notify_all();
-            for (auto& t : pool) t.join();
+            for (auto& t : pool)
+                if (t.joinable()) t.join();
         };
+        struct PoolGuard {  // an exception on the way (a scoring context that failed, a CUDA error) must not leave joinable threads behind
+            std::function<void()> f;
+            ~PoolGuard() { f(); }
+        } pool_guard{shut};
         const bool host_profile = std::getenv("PCSF_HOST_PROFILE") != nullptr;  // where the appender's time goes, on stderr
         double t_wait = 0, t_append = 0;
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
