@@ -546,8 +546,7 @@ class Driver {
         if (devices.empty()) devices.push_back(o.device);
         if (o.strategy == STRAT_NOP) devices.resize(1);
         // The scoring contexts (CUDA initialisation, tree and model upload, P(t) tables) come up in parallel, one
-        // thread each, and are all up before reading starts. (Letting them come up while the readers already run
-        // saves ~0.2 s at best and was bimodal on the test box: 3.4 s or 5.0 s for the same 300 k alignments.)
+        // thread each, and are all up before reading starts.
         for (int d : devices)
             dev_init.push_back(std::async(std::launch::async, [this, d]() { return std::unique_ptr<DeviceScorer>(new DeviceScorer(opt, ps, d)); }));
         devices_ready();
