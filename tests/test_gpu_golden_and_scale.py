@@ -181,3 +181,55 @@ def test_full_size_properties(params_base):
         assert abs(H.DB * (lpr[0, r] - lo_[0, 0])) < 1e-6 and abs(H.DB * (lpr[1, r] - lo_[1, 0])) < 1e-6
         assert abs(H.DB * (elpr[0, r] - eo_[0, 0])) < 1e-6
     ctx.close()
+
+
+def test_mle_batch_properties_120mammals(params_base):
+    """BASELINE.json configs[2] at a size the oracle cannot follow (2,000 alignments x 100 codons, 120mammals,
+    mle): properties instead. (1) The maximised log-likelihood of every (region, model) is at least the one at
+    the starting point rho = 1 (what --strategy=fixed evaluates). (2) A region's result does not depend on what
+    else is in the batch: the first 300 regions alone give bit-identical rho and lpr. (3) Duplicated regions give
+    bit-identical results. (4) Simulated-coding regions outscore simulated-noncoding ones, and the estimated rho
+    follows the scale the region was simulated at."""
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host, simulate
+
+    N, NC = 2000, 100
+    ps = host.ParamSet(os.path.join(params_base, "PhyloCSF_Parameters", "120mammals"))
+    ctx = pb.Context(0)
+    ps.install(ctx)
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    parents = simulate.parents_from_children(ps.n_leaves, ps.children)
+    nbr = 2 * ps.n_leaves - 2
+    scales = [0.5, 1.6]
+    parts = []
+    per = (N - 100) // 4
+    for w in (0, 1):
+        ctx.pt_build(w, scales)
+        for si in range(2):
+            P = np.stack([ctx.pt_get(w, si, br) for br in range(nbr)])
+            parts.append(simulate.simulate_codes(P, ps.qdiag(w)["prior"], parents, ps.n_leaves, per * NC, gen, dev))
+    codes = torch.cat(parts).cpu().numpy()
+    codes = np.concatenate([codes, codes[: (N - 4 * per) * NC]])  # the tail repeats the head
+    off = np.arange(N + 1, dtype=np.int64) * NC
+    ctx.batch_upload(off, codes)
+    rho, lpr, elpr, st, ne = ctx.maximize_lpr_multi([0, 1])
+    assert ((st & ~64) == 0).all() and np.isfinite(lpr).all()
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    l1, _, _ = ctx.lpr_all([0, 1])
+    assert (lpr >= l1 - 1e-9 * np.abs(l1)).all()                      # (1)
+    dup = N - 4 * per
+    assert (rho[:, :dup] == rho[:, 4 * per:]).all() and (lpr[:, :dup] == lpr[:, 4 * per:]).all()   # (3)
+    score = H.DB * (lpr[0] - lpr[1])
+    assert score[: 2 * per].mean() > 300 and score[2 * per: 4 * per].mean() < -50               # (4)
+    for blk, s in ((0, 0.5), (1, 1.6)):
+        est = np.median(rho[0, blk * per:(blk + 1) * per])
+        assert 0.8 * s < est < 1.25 * s, (s, est)
+    ctx.batch_upload(off[:301], codes[: 300 * NC])
+    r2, l2, e2, st2, ne2 = ctx.maximize_lpr_multi([0, 1])
+    assert (r2 == rho[:, :300]).all() and (l2 == lpr[:, :300]).all() and (ne2 == ne[:, :300]).all()  # (2)
+    ctx.close()
