@@ -74,6 +74,14 @@ int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
  * for every new context.
  */
 #define PCSF_OPT_PRUNE_FORM 2
+/*
+ * PCSF_OPT_CHERRY_TABLES: memoise, per P set, the partial likelihood above every cherry of the tree over the
+ * 65 x 65 code pairs of its two leaves (computed with the pruning kernel's own instruction sequence, so a lookup
+ * is bit-identical to the computation it replaces). 0 (default) = built when a P set scores >= 50,000 columns in
+ * pcsf_lpr_all / pcsf_score_alignments and the wide form runs; 1 = never; 2 = always. PCSF_CHERRY_TABLES in the
+ * environment sets it for every new context.
+ */
+#define PCSF_OPT_CHERRY_TABLES 3
 int pcsf_option_set(pcsf_ctx *ctx, int option, int64_t value);
 
 /*

@@ -48,7 +48,7 @@ class Context:
     def stream_set(self, cuda_stream_ptr):
         self._check(self._L.pcsf_stream_set(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
 
-    OPT_RESCALE, OPT_PRUNE_FORM = 1, 2
+    OPT_RESCALE, OPT_PRUNE_FORM, OPT_CHERRY_TABLES = 1, 2, 3
     FORM_AUTO, FORM_NARROW, FORM_WIDE = 0, 1, 2
 
     def option_set(self, option, value):

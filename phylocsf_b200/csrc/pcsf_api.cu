@@ -33,6 +33,8 @@ struct Model {
     DevBuf d_scales, d_status;
     int nscales = 0;
     std::vector<int32_t> status;
+    DevBuf cherry;                  // [nscales][n_cherries][CHERRY_TABLE], built on demand (fixed strategy)
+    std::vector<char> cherry_built; // per scale
     const double* prior() const { return d_params + 8192 + 64; }
     const double* logprior() const { return d_params + 8192 + 128; }
 };
@@ -75,6 +77,14 @@ struct pcsf_ctx {
     int64_t launches = 0;
     int prune_smem_optin = 0;
     int skew_ns = 1500;
+    // cherry-table program: the tree program with every (cherry, edge above it) pair folded into one lookup
+    std::vector<Op> ops_t;
+    std::vector<Item> items_t;
+    std::vector<Cherry> cherries;
+    Op* d_ops_t = nullptr;
+    Item* d_items_t = nullptr;
+    Cherry* d_cherries = nullptr;
+    int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 when a P set scores enough columns, 1 never, 2 always
     int wide = -1;  // pruning kernel form: 0 narrow (128-column tiles), 1 wide (192), -1 chosen per launch (PCSF_WIDE overrides)
     int rescale = 0;  // PCSF_OPT_RESCALE
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
@@ -214,12 +224,17 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         CU(cudaMemcpyAsync(ctx->d_psets.p, psets.data(), sizeof(PSet) * psets.size(), cudaMemcpyHostToDevice, ctx->stream));
         const int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
         if (ctx->max_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * ctx->max_levels * level_bytes));
+        // the cherry-table program runs when the wide form does and every P set of the launch carries its tables
+        bool tabled = wide && !ctx->cherries.empty();
+        for (const PSet& q : psets) tabled = tabled && q.cherry != nullptr;
+        const std::vector<Op>& prog_ops = tabled ? ctx->ops_t : ctx->ops;
+        const std::vector<Item>& prog_items = tabled ? ctx->items_t : ctx->items;
         PruneParams p;
         memset(&p, 0, sizeof(p));
-        p.ops = ctx->d_ops;
-        p.n_ops = (int)ctx->ops.size();
-        p.items = ctx->d_items;
-        p.n_items = (int)ctx->items.size();
+        p.ops = tabled ? ctx->d_ops_t : ctx->d_ops;
+        p.n_ops = (int)prog_ops.size();
+        p.items = tabled ? ctx->d_items_t : ctx->d_items;
+        p.n_items = (int)prog_items.size();
         p.n_leaves = ctx->n_leaves;
         p.spans = (const Span*)ctx->d_spans.p;
         p.n_spans = (int)spans.size();
@@ -230,8 +245,8 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         p.out_anc = (double*)ctx->d_out_anc.p;
         p.global_stack = (uint8_t*)ctx->d_gstack.p;
         p.n_levels = ctx->max_levels;
-        p.ops_bytes = r16((int)(ctx->ops.size() * sizeof(Op)));
-        p.items_bytes = r16((int)(ctx->items.size() * sizeof(Item)));
+        p.ops_bytes = r16((int)(prog_ops.size() * sizeof(Op)));
+        p.items_bytes = r16((int)(prog_items.size() * sizeof(Item)));
         p.timeline = (long long*)ctx->timeline;
         p.timeline_cap = ctx->timeline_cap;
         p.skew_ns = ctx->skew_ns;
@@ -310,7 +325,37 @@ PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
     ps.tables = (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT;
     ps.prior = m.prior();
     ps.logprior = m.logprior();
+    ps.cherry = (scale < (int)m.cherry_built.size() && m.cherry_built[scale])
+                    ? (const double*)m.cherry.p + (size_t)scale * ctx->cherries.size() * CHERRY_TABLE
+                    : nullptr;
     return ps;
+}
+
+// Cherry tables pay for themselves when a P set scores many more columns than the 4225 code pairs per cherry.
+bool want_cherry_tables(const pcsf_ctx* ctx, int64_t cols_per_pset) {
+    if (ctx->cherry_mode == 1 || ctx->wide == 0) return false;
+    return ctx->cherry_mode == 2 || cols_per_pset >= 50000;
+}
+
+// Build (once) the cherry tables of model `m` at scale index `scale`. Only for models with a handful of scales
+// (the fixed strategy's): per-candidate P sets of mle / omega score too few columns to pay for 4225 lookups rows.
+int ensure_cherry_tables(pcsf_ctx* ctx, Model& m, int scale) {
+    if (ctx->cherries.empty() || m.nscales > 8) return PCSF_OK;
+    if ((int)m.cherry_built.size() != m.nscales) m.cherry_built.assign(m.nscales, 0);
+    if (m.cherry_built[scale]) return PCSF_OK;
+    const size_t per = ctx->cherries.size() * (size_t)CHERRY_TABLE;
+    if (m.cherry.cap < sizeof(double) * per * m.nscales) {
+        std::fill(m.cherry_built.begin(), m.cherry_built.end(), 0);
+        TRY(reserve(ctx, m.cherry, sizeof(double) * per * m.nscales));
+    }
+    const long long warps = (long long)ctx->cherries.size() * ((CHERRY_ROWS + 15) / 16);
+    cherry_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(
+        (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT, ctx->d_cherries, (int)ctx->cherries.size(),
+        (double*)m.cherry.p + (size_t)scale * per);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    m.cherry_built[scale] = 1;
+    return PCSF_OK;
 }
 
 // K1 over a list of jobs: tables[job][branch][PT_SLOT], status[job]
@@ -345,6 +390,7 @@ int pt_build_device(pcsf_ctx* ctx, Model& m, int nscales, const double* scales) 
     for (int i = 0; i < nscales; i++) jobs[i] = PtJob{m.d_params, scales[i]};
     TRY(pt_build_jobs(ctx, jobs, m.tables, m.d_status, m.status));
     m.nscales = nscales;
+    m.cherry_built.assign(nscales, 0);  // the cherry tables belonged to the previous P(t)
     return PCSF_OK;
 }
 
@@ -409,6 +455,7 @@ int pcsf_create(int device_id, pcsf_ctx** out) {
     ctx->prune_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("PCSF_SKEW_NS")) ctx->skew_ns = atoi(e);  // tuning knob, see prune_kernel
     if (const char* e = getenv("PCSF_WIDE")) ctx->wide = atoi(e);
+    if (const char* e = getenv("PCSF_CHERRY_TABLES")) ctx->cherry_mode = atoi(e);
     if (const char* e = getenv("PCSF_RESCALE")) ctx->rescale = atoi(e) ? 1 : 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->stream = ctx->own_stream;
@@ -442,6 +489,9 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
     if (ctx->d_items) cudaFree(ctx->d_items);
+    if (ctx->d_ops_t) cudaFree(ctx->d_ops_t);
+    if (ctx->d_items_t) cudaFree(ctx->d_items_t);
+    if (ctx->d_cherries) cudaFree(ctx->d_cherries);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -471,6 +521,11 @@ int pcsf_option_set(pcsf_ctx* ctx, int option, int64_t value) {
     if (option == PCSF_OPT_PRUNE_FORM) {
         if (value < 0 || value > 2) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_PRUNE_FORM takes 0, 1 or 2");
         ctx->wide = value == 0 ? -1 : (int)value - 1;
+        return PCSF_OK;
+    }
+    if (option == PCSF_OPT_CHERRY_TABLES) {
+        if (value < 0 || value > 2) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_CHERRY_TABLES takes 0, 1 or 2");
+        ctx->cherry_mode = (int)value;
         return PCSF_OK;
     }
     return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: unknown option");
@@ -512,17 +567,47 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         else if (op.kind == OP_GEMM_PUSH) ctx->items.push_back({ITEM_P, op.a});
         else if (op.kind == OP_GEMM_POP) { ctx->items.push_back({ITEM_P, op.a}); ctx->items.push_back({ITEM_POP, op.c}); }
     }
+    // the cherry-table program: (OP_CHERRY, the contraction that follows it) -> one table op
+    ctx->ops_t.clear();
+    ctx->items_t.clear();
+    ctx->cherries.clear();
+    for (size_t i = 0; i < ctx->ops.size(); i++) {
+        const Op& op = ctx->ops[i];
+        if (op.kind == OP_CHERRY && i + 1 < ctx->ops.size() && ctx->ops[i + 1].kind != OP_ROOT) {
+            const Op& g = ctx->ops[i + 1];  // the edge above the cherry's node: g.a
+            const int ti = (int)ctx->cherries.size();
+            ctx->cherries.push_back(Cherry{op.a, op.b, g.a});
+            const int kind = (g.kind == OP_GEMM_LEAF ? OP_TAB_LEAF : g.kind == OP_GEMM_PUSH ? OP_TAB_PUSH : OP_TAB_POP) | (ti << 8);
+            ctx->ops_t.push_back(Op{kind, op.a, op.b, g.kind == OP_GEMM_LEAF ? g.b : g.c});
+            if (g.kind == OP_GEMM_LEAF) ctx->items_t.push_back({ITEM_LEAF, g.b});
+            i++;
+            continue;
+        }
+        ctx->ops_t.push_back(op);
+        if (op.kind == OP_CHERRY) { ctx->items_t.push_back({ITEM_LEAF, op.a}); ctx->items_t.push_back({ITEM_LEAF, op.b}); }
+        else if (op.kind == OP_GEMM_LEAF) { ctx->items_t.push_back({ITEM_P, op.a}); ctx->items_t.push_back({ITEM_LEAF, op.b}); }
+        else if (op.kind == OP_GEMM_PUSH || op.kind == OP_GEMM_POP) ctx->items_t.push_back({ITEM_P, op.a});
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_branch_len) CU(cudaFree(ctx->d_branch_len));
     if (ctx->d_ops) CU(cudaFree(ctx->d_ops));
     if (ctx->d_items) CU(cudaFree(ctx->d_items));
+    if (ctx->d_ops_t) CU(cudaFree(ctx->d_ops_t));
+    if (ctx->d_items_t) CU(cudaFree(ctx->d_items_t));
+    if (ctx->d_cherries) CU(cudaFree(ctx->d_cherries));
+    CU(cudaMalloc(&ctx->d_ops_t, sizeof(Op) * std::max<size_t>(1, ctx->ops_t.size())));
+    CU(cudaMalloc(&ctx->d_items_t, sizeof(Item) * std::max<size_t>(1, ctx->items_t.size())));
+    CU(cudaMalloc(&ctx->d_cherries, sizeof(Cherry) * std::max<size_t>(1, ctx->cherries.size())));
+    CU(cudaMemcpy(ctx->d_ops_t, ctx->ops_t.data(), sizeof(Op) * ctx->ops_t.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_items_t, ctx->items_t.data(), sizeof(Item) * ctx->items_t.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_cherries, ctx->cherries.data(), sizeof(Cherry) * ctx->cherries.size(), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&ctx->d_branch_len, sizeof(double) * (n - 1)));
     CU(cudaMalloc(&ctx->d_ops, sizeof(Op) * ctx->ops.size()));
     CU(cudaMalloc(&ctx->d_items, sizeof(Item) * std::max<size_t>(1, ctx->items.size())));
     CU(cudaMemcpy(ctx->d_items, ctx->items.data(), sizeof(Item) * ctx->items.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_branch_len, branch_len, sizeof(double) * (n - 1), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_ops, ctx->ops.data(), sizeof(Op) * ctx->ops.size(), cudaMemcpyHostToDevice));
-    for (auto& m : ctx->models) m.nscales = 0;  // tables belong to the previous tree
+    for (auto& m : ctx->models) { m.nscales = 0; m.cherry_built.clear(); }  // tables belong to the previous tree
     return PCSF_OK;
 }
 
@@ -690,6 +775,7 @@ int pcsf_lpr_all(pcsf_ctx* ctx, int n_models, const int32_t* model_ids, const in
     for (int m = 0; m < n_models; m++) {
         const int sc = scale_idx ? scale_idx[m] : 0;
         TRY(check_model(ctx, model_ids[m], sc));
+        if (want_cherry_tables(ctx, ctx->total_cols)) TRY(ensure_cherry_tables(ctx, ctx->models[model_ids[m]], sc));
         psets.push_back(make_pset(ctx, model_ids[m], sc));
         spans.push_back(Span{0, (int64_t)m * ctx->total_cols, 0, (int32_t)0, m});
         spans.back().ncols = (int32_t)ctx->total_cols;
@@ -736,9 +822,12 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
         return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_score_alignments: bad argument");
     CU(cudaSetDevice(ctx->device));
     std::vector<PSet> psets;
+    int64_t est_cols = 0;
+    for (int64_t a = 0; a < nalign; a++) est_cols += (int64_t)(aln_len[a] > 0 ? aln_len[a] / 3 : 0) * frames;
     for (int m = 0; m < n_models; m++) {
         const int sc = scale_idx ? scale_idx[m] : 0;
         TRY(check_model(ctx, model_ids[m], sc));
+        if (want_cherry_tables(ctx, est_cols)) TRY(ensure_cherry_tables(ctx, ctx->models[model_ids[m]], sc));
         psets.push_back(make_pset(ctx, model_ids[m], sc));
     }
     if (!ctx->copy_stream) {
@@ -1029,6 +1118,7 @@ int pcsf_lpr_pairs(pcsf_ctx* ctx, int64_t n_evals, const int64_t* eval_pair, con
             ps.tables = (const double*)ctx->d_pair_tables.p + (size_t)pr * ctx->n_branches * PT_SLOT;
             ps.prior = m.prior();
             ps.logprior = m.logprior();
+            ps.cherry = nullptr;
             psets.push_back(ps);
             prev_pair = pr;
         }

@@ -32,7 +32,18 @@ enum OpKind : int32_t {
     OP_GEMM_LEAF = 1,  // cur = (P_a x cur) * G(b)                a internal child, b sibling leaf
     OP_GEMM_PUSH = 2,  // stack[c] = P_a x cur                    sibling subtree still to come
     OP_GEMM_POP = 3,   // cur = (P_a x cur) * stack[c]
-    OP_ROOT = 4        // z = cur . prior, log z, root posterior . log prior
+    OP_ROOT = 4,       // z = cur . prior, log z, root posterior . log prior
+    // cherry-table program (wide form, P sets that carry cherry tables): a cherry (leaves a, b) and the contraction
+    // over the edge above it are one lookup, W[table][code_a][code_b][.] = P_v x (G(a) * G(b)); `kind` carries the
+    // table index in its bits 8.., `c` the operand of the usual epilogue (sibling leaf / stack level)
+    OP_TAB_LEAF = 5,   // cur = W * G(c)
+    OP_TAB_PUSH = 6,   // stack[c] = W
+    OP_TAB_POP = 7     // cur = W * stack[c]
+};
+constexpr int CHERRY_ROWS = 65 * 65;              // code pairs, 64 = marginalise
+constexpr int CHERRY_TABLE = CHERRY_ROWS * 64;    // doubles per cherry table (2.16 MB)
+struct Cherry {
+    int32_t la, lb, v;  // the two leaves and their parent node (= the branch above it)
 };
 struct Op {
     int32_t kind, a, b, c;
@@ -52,6 +63,7 @@ struct PSet {
     const double* tables;    // [n_branches][PT_SLOT]
     const double* prior;     // [64]
     const double* logprior;  // [64]
+    const double* cherry;    // [n_cherries][CHERRY_TABLE], or null when not built for this P set
 };
 
 // ---- small PTX wrappers ------------------------------------------------------------------------
@@ -751,7 +763,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t lring0 = smem0 + W_P_STAGES * FRAG_BYTES + t * 16;
     const uint32_t codes00 = smem_u32(codes_s) + (cw * WARP_COLS + g) * p.n_leaves;  // this lane's first column in buffer 0
-    int64_t* const scratch = reinterpret_cast<int64_t*>(codes_s + 2 * cbytes) + cw * 4;  // {out index of column 0 of the tile, pset}
+    int64_t* const scratch = reinterpret_cast<int64_t*>(codes_s + 2 * cbytes) + cw * 4;  // {out index of column 0 of the tile, pset, cherry tables}
     // No start-up offsets and no barrier among the warps of a sub-partition: left alone they spread out over
     // the edge by themselves (timeline: thousands of clocks apart). Both were measured: offsets of 0.8-3 us
     // change nothing, re-aligning the three warps after every contraction costs 6 points (83.3 %).
@@ -771,6 +783,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
             if (lane == 0) {
                 scratch[0] = sp.out0 + tcol0;
                 scratch[1] = sp.pset;
+                scratch[2] = (int64_t)p.psets[sp.pset].cherry;
             }
             __syncwarp();
         }
@@ -863,12 +876,31 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                 }
                 continue;
             }
+            double acc[2][8][2];
+            int ekind = op.kind;
+            if ((op.kind & 0xff) >= OP_TAB_LEAF) {
+                // -------------------- cherry + the edge above it: one 512-byte row of the cherry's table per column --------------------
+                ekind = (op.kind & 0xff) - OP_TAB_LEAF + OP_GEMM_LEAF;  // LEAF / PUSH / POP epilogue as after a contraction
+                if (warp_active) {
+                    const double* W = reinterpret_cast<const double*>(scratch[2]) + (size_t)(op.kind >> 8) * CHERRY_TABLE + 2 * t;
+                    uint32_t a0 = lds_u8(codes0 + op.a), a1 = lds_u8(codes0 + 8 * p.n_leaves + op.a);
+                    uint32_t b0 = lds_u8(codes0 + op.b), b1 = lds_u8(codes0 + 8 * p.n_leaves + op.b);
+                    a0 = a0 > 64 ? 64 : a0; a1 = a1 > 64 ? 64 : a1; b0 = b0 > 64 ? 64 : b0; b1 = b1 > 64 ? 64 : b1;
+                    const double2* r0 = reinterpret_cast<const double2*>(W + (size_t)(a0 * 65 + b0) * 64);
+                    const double2* r1 = reinterpret_cast<const double2*>(W + (size_t)(a1 * 65 + b1) * 64);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double2 v0 = __ldg(r0 + 4 * j), v1 = __ldg(r1 + 4 * j);
+                        acc[0][j][0] = v0.x; acc[0][j][1] = v0.y;
+                        acc[1][j][0] = v1.x; acc[1][j][1] = v1.y;
+                    }
+                }
+            } else {
             // ------------------------------ K3: contraction over one internal edge ------------------------------
             TL_MARK(oi * 8 + 0);
             const uint32_t pst = pq % W_P_STAGES;
             mbar_wait(&pfull[pst], (pq / W_P_STAGES) & 1);
             TL_MARK(oi * 8 + 1);
-            double acc[2][8][2];
             if (warp_active) {
                 const double* Pb = reinterpret_cast<const double*>(Pring + pst * FRAG_BYTES) + lane;
 #pragma unroll
@@ -888,8 +920,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
             release_stage(&pempty[pst], lane);
             pq++;
             TL_MARK(oi * 8 + 2);
+            }
             // ------------------------------ epilogue ------------------------------
-            if (op.kind == OP_GEMM_PUSH) {  // park the message; only this thread ever touches these addresses
+            if (ekind == OP_GEMM_PUSH) {  // park the message; only this thread ever touches these addresses
                 if (warp_active) {
                     double2* slot = reinterpret_cast<double2*>(park(op.c));
 #pragma unroll
@@ -906,7 +939,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                         }
                     }
                 }
-            } else if (op.kind == OP_GEMM_POP) {
+            } else if (ekind == OP_GEMM_POP) {
                 if (warp_active) {
                     const double2* slot = reinterpret_cast<const double2*>(park(op.c));
 #pragma unroll
@@ -930,7 +963,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                 TL_MARK(oi * 8 + 3);
                 if (warp_active) {
                     uint32_t a0, a1;
-                    leaf_rows(st, op.b, a0, a1);
+                    leaf_rows(st, ekind == op.kind ? op.b : op.c, a0, a1);  // the sibling leaf
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const double2 v0 = lds_f64x2(a0 + j * 64), v1 = lds_f64x2(a1 + j * 64);
@@ -948,6 +981,59 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&cempty[k & 1]);  // this warp is done with the tile's codes
+    }
+}
+
+// =================================================================================================
+// Cherry tables: W[cherry][code_a][code_b][y] = sum_x P_v[y][x] (G_a[code_a][x] G_b[code_b][x]) for every cherry of the
+// tree - what the pruning kernels compute for a column whose two leaves carry (code_a, code_b), memoised over the
+// 65 x 65 code pairs. Built with the very instruction sequence of the pruning kernels (same products, same DMMA
+// accumulation order), 16 code pairs per warp as if they were 16 columns, so a lookup is bit-identical to the
+// computation it replaces. Worth building when a P set scores many columns (fixed strategy): 17 of the 56
+// contractions per column of the 58mammals tree become 512-byte gathers.
+// =================================================================================================
+__global__ void __launch_bounds__(128) cherry_table_kernel(const double* __restrict__ tables, const Cherry* __restrict__ cherries,
+                                                           int n_cherries, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int warps_per_cherry = (CHERRY_ROWS + 15) / 16;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (long long)n_cherries * warps_per_cherry) return;
+    const int ci = (int)(wid / warps_per_cherry), q0 = (int)(wid % warps_per_cherry) * 16;
+    const Cherry ch = cherries[ci];
+    const double* ta = tables + (size_t)ch.la * PT_SLOT;
+    const double* tb = tables + (size_t)ch.lb * PT_SLOT;
+    const double* Pb = tables + (size_t)ch.v * PT_SLOT + lane;
+    double cur[2][8][2], acc[2][8][2];
+#pragma unroll
+    for (int T = 0; T < 2; T++) {
+        const int q = min(q0 + 8 * T + g, CHERRY_ROWS - 1);  // padding pairs repeat the last one (never stored)
+        const double2* ra = reinterpret_cast<const double2*>(ta + (q / 65) * 64 + 2 * t);
+        const double2* rb = reinterpret_cast<const double2*>(tb + (q % 65) * 64 + 2 * t);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double2 u = ra[4 * j], v = rb[4 * j];
+            cur[T][j][0] = u.x * v.x;  // the cherry's product, as in the pruning kernels
+            cur[T][j][1] = u.y * v.y;
+            acc[T][j][0] = acc[T][j][1] = 0.0;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double bf = Pb[(j * 16 + s) * 32];
+#pragma unroll
+            for (int T = 0; T < 2; T++) dmma(acc[T][j][0], acc[T][j][1], cur[T][s >> 1][s & 1], bf);
+        }
+    }
+#pragma unroll
+    for (int T = 0; T < 2; T++) {
+        const int q = q0 + 8 * T + g;
+        if (q < CHERRY_ROWS) {
+            double2* w = reinterpret_cast<double2*>(out + (size_t)ci * CHERRY_TABLE + (size_t)q * 64 + 2 * t);
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[4 * j] = make_double2(acc[T][j][0], acc[T][j][1]);
+        }
     }
 }
 

@@ -127,8 +127,11 @@ def test_both_kernel_forms_match_oracle_and_each_other(params_base, pset):
     off, codes = H.regions_to_batch(regs)
     ctx.batch_upload(off, codes)
     got = {}
-    for form in (pb.Context.FORM_NARROW, pb.Context.FORM_WIDE):
-        ctx.option_set(pb.Context.OPT_PRUNE_FORM, form)
+    # the third variant: the wide form running the cherry-table program (a cherry and the contraction above it as
+    # one lookup in a table built with the kernel's own instruction sequence)
+    for form, cherry in ((pb.Context.FORM_NARROW, 1), (pb.Context.FORM_WIDE, 1), ("tabled", 2)):
+        ctx.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_WIDE if form == "tabled" else form)
+        ctx.option_set(pb.Context.OPT_CHERRY_TABLES, cherry)
         for rep in range(2):
             lpr, elpr, st = ctx.lpr_all([0, 1])
             cols = [ctx.column_terms(m) for m in (0, 1)]
@@ -145,10 +148,13 @@ def test_both_kernel_forms_match_oracle_and_each_other(params_base, pset):
         er = np.tile(np.arange(len(regs)), 2)
         l2, e2, _ = ctx.lpr(em, np.zeros_like(em), er)
         assert (l2.reshape(2, -1) == got[form][0]).all() and (e2.reshape(2, -1) == got[form][1]).all()
-    a, b = got[pb.Context.FORM_NARROW], got[pb.Context.FORM_WIDE]
-    assert all((x == y).all() for x, y in zip(a[2], b[2])) and all((x == y).all() for x, y in zip(a[3], b[3]))  # per column
-    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    a = got[pb.Context.FORM_NARROW]
+    for other in (pb.Context.FORM_WIDE, "tabled"):
+        b = got[other]
+        assert all((x == y).all() for x, y in zip(a[2], b[2])) and all((x == y).all() for x, y in zip(a[3], b[3])), other  # per column
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), other
     ctx.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_AUTO)
+    ctx.option_set(pb.Context.OPT_CHERRY_TABLES, 0)
     with pytest.raises(Exception):
         ctx.option_set(pb.Context.OPT_PRUNE_FORM, 3)
     ctx.close()
