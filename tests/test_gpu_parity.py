@@ -432,7 +432,7 @@ def _lpr_extended_precision(model, codes):
     return float(np.log(z).sum())
 
 
-@pytest.mark.parametrize("form", [1, 2])
+@pytest.mark.parametrize("form", [1, 2, 3])
 def test_rescale_option_rescues_underflow(params_base, form):
     """(in both forms of the pruning kernel) PCSF_OPT_RESCALE: uniform-random columns on the 120-leaf tree underflow to -inf without it (the
     reference's behaviour); with it the score is finite and equals an extended-precision evaluation.
@@ -449,7 +449,8 @@ def test_rescale_option_rescues_underflow(params_base, form):
     ctx.pt_build(1, [1.0])
     off, codes = H.regions_to_batch(regs)
     ctx.batch_upload(off, codes)
-    ctx.option_set(2, form)
+    ctx.option_set(2, min(form, 2))
+    ctx.option_set(3, 2 if form == 3 else 1)  # form 3: the wide form with cherry tables
     lpr0, elpr0, st0 = ctx.lpr_all([0, 1])
     assert np.isneginf(lpr0[:, 0]).all() and np.isfinite(lpr0[:, 1]).all()
     ctx.option_set(1, 1)
