@@ -33,8 +33,9 @@ struct Model {
     DevBuf d_scales, d_status;
     int nscales = 0;
     std::vector<int32_t> status;
-    DevBuf cherry;                  // [nscales][n_cherries][CHERRY_TABLE], built on demand (fixed strategy)
-    std::vector<char> cherry_built; // per scale
+    DevBuf cherry;                  // [nscales][subtree tables of one P set], built on demand (fixed strategy)
+    std::vector<char> cherry_built; // per scale: 0, or the level built (2 cherries, 3 cherries + cherry-and-leaf subtrees)
+    int cherry_level = 0;           // level the buffer's per-scale stride was sized for
     const double* prior() const { return d_params + 8192 + 64; }
     const double* logprior() const { return d_params + 8192 + 128; }
 };
@@ -78,13 +79,15 @@ struct pcsf_ctx {
     int prune_smem_optin = 0;
     int skew_ns = 1500;
     // cherry-table program: the tree program with every (cherry, edge above it) pair folded into one lookup
-    std::vector<Op> ops_t;
-    std::vector<Item> items_t;
-    std::vector<Cherry> cherries;
-    Op* d_ops_t = nullptr;
-    Item* d_items_t = nullptr;
-    Cherry* d_cherries = nullptr;
-    int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 when a P set scores enough columns, 1 never, 2 always
+    std::vector<Op> ops_t, ops_t3;      // level 2 (cherries) and level 3 (+ cherry-and-leaf subtrees) programs
+    std::vector<Item> items_t, items_t3;
+    std::vector<SubTab> subtabs;        // cherries first (n_tab2), then the 3-leaf subtrees (n_tab3)
+    int n_tab2 = 0, n_tab3 = 0;
+    Op *d_ops_t = nullptr, *d_ops_t3 = nullptr;
+    Item *d_items_t = nullptr, *d_items_t3 = nullptr;
+    SubTab* d_subtabs = nullptr;
+    long long* d_tab_off = nullptr;
+    int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 by the number of columns a P set scores, 1 never, 2 always (deepest), 3 always, cherries only
     int wide = -1;  // pruning kernel form: 0 narrow (128-column tiles), 1 wide (192), -1 chosen per launch (PCSF_WIDE overrides)
     int rescale = 0;  // PCSF_OPT_RESCALE
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
@@ -225,16 +228,18 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         const int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
         if (ctx->max_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * ctx->max_levels * level_bytes));
         // the cherry-table program runs when the wide form does and every P set of the launch carries its tables
-        bool tabled = wide && !ctx->cherries.empty();
-        for (const PSet& q : psets) tabled = tabled && q.cherry != nullptr;
-        const std::vector<Op>& prog_ops = tabled ? ctx->ops_t : ctx->ops;
-        const std::vector<Item>& prog_items = tabled ? ctx->items_t : ctx->items;
+        long long level = (wide && ctx->n_tab2 > 0) ? 3 : 0;
+        for (const PSet& q : psets) level = std::min(level, q.cherry ? q.tab_level : 0LL);
+        if (level == 3 && ctx->n_tab3 == 0) level = 2;
+        const std::vector<Op>& prog_ops = level == 3 ? ctx->ops_t3 : level == 2 ? ctx->ops_t : ctx->ops;
+        const std::vector<Item>& prog_items = level == 3 ? ctx->items_t3 : level == 2 ? ctx->items_t : ctx->items;
         PruneParams p;
         memset(&p, 0, sizeof(p));
-        p.ops = tabled ? ctx->d_ops_t : ctx->d_ops;
+        p.ops = level == 3 ? ctx->d_ops_t3 : level == 2 ? ctx->d_ops_t : ctx->d_ops;
         p.n_ops = (int)prog_ops.size();
-        p.items = tabled ? ctx->d_items_t : ctx->d_items;
+        p.items = level == 3 ? ctx->d_items_t3 : level == 2 ? ctx->d_items_t : ctx->d_items;
         p.n_items = (int)prog_items.size();
+        p.tab_off = ctx->d_tab_off;
         p.n_leaves = ctx->n_leaves;
         p.spans = (const Span*)ctx->d_spans.p;
         p.n_spans = (int)spans.size();
@@ -319,42 +324,69 @@ int check_model(pcsf_ctx* ctx, int model_id, int scale) {
     return PCSF_OK;
 }
 
+size_t table_block_doubles(const pcsf_ctx* ctx, int level) {  // subtree tables of one P set
+    return (size_t)ctx->n_tab2 * CHERRY_TABLE + (level >= 3 ? (size_t)ctx->n_tab3 * (size_t)TRIPLE_TABLE : 0);
+}
+
 PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
     const Model& m = ctx->models[model_id];
     PSet ps;
     ps.tables = (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT;
     ps.prior = m.prior();
     ps.logprior = m.logprior();
-    ps.cherry = (scale < (int)m.cherry_built.size() && m.cherry_built[scale])
-                    ? (const double*)m.cherry.p + (size_t)scale * ctx->cherries.size() * CHERRY_TABLE
-                    : nullptr;
+    ps.cherry = nullptr;
+    ps.tab_level = 0;
+    if (scale < (int)m.cherry_built.size() && m.cherry_built[scale]) {
+        ps.cherry = (const double*)m.cherry.p + (size_t)scale * table_block_doubles(ctx, m.cherry_level);
+        ps.tab_level = m.cherry_built[scale];
+    }
     return ps;
 }
 
-// Cherry tables pay for themselves when a P set scores many more columns than the 4225 code pairs per cherry.
-bool want_cherry_tables(const pcsf_ctx* ctx, int64_t cols_per_pset) {
-    if (ctx->cherry_mode == 1 || ctx->wide == 0) return false;
-    return ctx->cherry_mode == 2 || cols_per_pset >= 50000;
+// Which subtree tables a P set that scores `cols_per_pset` columns should carry: cherries (2.16 MB each, built in
+// well under a millisecond) pay from a few ten thousand columns; the 140.6 MB tables of cherry-and-leaf subtrees
+// from about a million, and only while they fit comfortably in device memory.
+int want_table_level(pcsf_ctx* ctx, int64_t cols_per_pset) {
+    if (ctx->cherry_mode == 1 || ctx->wide == 0 || ctx->n_tab2 == 0) return 0;
+    return ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : cols_per_pset >= 1000000 ? 3 : cols_per_pset >= 50000 ? 2 : 0;
 }
 
-// Build (once) the cherry tables of model `m` at scale index `scale`. Only for models with a handful of scales
-// (the fixed strategy's): per-candidate P sets of mle / omega score too few columns to pay for 4225 lookups rows.
-int ensure_cherry_tables(pcsf_ctx* ctx, Model& m, int scale) {
-    if (ctx->cherries.empty() || m.nscales > 8) return PCSF_OK;
+// Build (once) the subtree tables of model `m` at scale index `scale` up to `level`. Only for models with a handful
+// of scales (the fixed strategy's): per-candidate P sets of mle / omega score too few columns to pay for them.
+int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
+    if (level == 0 || ctx->n_tab2 == 0 || m.nscales > 8) return PCSF_OK;
+    if (ctx->n_tab3 == 0) level = 2;
     if ((int)m.cherry_built.size() != m.nscales) m.cherry_built.assign(m.nscales, 0);
-    if (m.cherry_built[scale]) return PCSF_OK;
-    const size_t per = ctx->cherries.size() * (size_t)CHERRY_TABLE;
-    if (m.cherry.cap < sizeof(double) * per * m.nscales) {
-        std::fill(m.cherry_built.begin(), m.cherry_built.end(), 0);
-        TRY(reserve(ctx, m.cherry, sizeof(double) * per * m.nscales));
+    if (m.cherry_built[scale] >= level) return PCSF_OK;
+    if (level == 3 && m.cherry_level < 3) {  // about to allocate the large tables: only while they fit comfortably
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        if ((double)free_b < 6.0 * sizeof(double) * (double)table_block_doubles(ctx, 3) * m.nscales) {
+            level = 2;  // no room for a few such blocks and the batch: stay with the cherries
+            if (m.cherry_built[scale] >= level) return PCSF_OK;
+        }
     }
-    const long long warps = (long long)ctx->cherries.size() * ((CHERRY_ROWS + 15) / 16);
-    cherry_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(
-        (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT, ctx->d_cherries, (int)ctx->cherries.size(),
-        (double*)m.cherry.p + (size_t)scale * per);
-    CU(cudaGetLastError());
-    ctx->launches++;
-    m.cherry_built[scale] = 1;
+    if (m.cherry_level < level || m.cherry.cap < sizeof(double) * table_block_doubles(ctx, level) * m.nscales) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::fill(m.cherry_built.begin(), m.cherry_built.end(), 0);
+        m.cherry_level = level;
+        TRY(reserve(ctx, m.cherry, sizeof(double) * table_block_doubles(ctx, level) * m.nscales));
+    }
+    const double* tables = (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT;
+    double* base = (double*)m.cherry.p + (size_t)scale * table_block_doubles(ctx, m.cherry_level);
+    if (m.cherry_built[scale] < 2) {
+        const long long warps = (long long)ctx->n_tab2 * ((CHERRY_ROWS + 15) / 16);
+        subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, 0, ctx->n_tab2, CHERRY_ROWS, base);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (level == 3) {
+        const long long warps = (long long)ctx->n_tab3 * ((TRIPLE_ROWS + 15) / 16);
+        subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, ctx->n_tab2, ctx->n_tab3, TRIPLE_ROWS, base);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    m.cherry_built[scale] = (char)level;
     return PCSF_OK;
 }
 
@@ -489,9 +521,8 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
     if (ctx->d_items) cudaFree(ctx->d_items);
-    if (ctx->d_ops_t) cudaFree(ctx->d_ops_t);
-    if (ctx->d_items_t) cudaFree(ctx->d_items_t);
-    if (ctx->d_cherries) cudaFree(ctx->d_cherries);
+    for (void* q : {(void*)ctx->d_ops_t, (void*)ctx->d_items_t, (void*)ctx->d_ops_t3, (void*)ctx->d_items_t3, (void*)ctx->d_subtabs, (void*)ctx->d_tab_off})
+        if (q) cudaFree(q);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -524,7 +555,7 @@ int pcsf_option_set(pcsf_ctx* ctx, int option, int64_t value) {
         return PCSF_OK;
     }
     if (option == PCSF_OPT_CHERRY_TABLES) {
-        if (value < 0 || value > 2) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_CHERRY_TABLES takes 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_CHERRY_TABLES takes 0 .. 3");
         ctx->cherry_mode = (int)value;
         return PCSF_OK;
     }
@@ -567,40 +598,90 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         else if (op.kind == OP_GEMM_PUSH) ctx->items.push_back({ITEM_P, op.a});
         else if (op.kind == OP_GEMM_POP) { ctx->items.push_back({ITEM_P, op.a}); ctx->items.push_back({ITEM_POP, op.c}); }
     }
-    // the cherry-table program: (OP_CHERRY, the contraction that follows it) -> one table op
+    // The table programs. Level 2: (OP_CHERRY, the contraction over the edge above the cherry) -> one lookup in the
+    // cherry's table. Level 3: when the cherry's sibling is a leaf and the node above them has an edge of its own,
+    // (OP_CHERRY, OP_GEMM_LEAF, the contraction over that edge) -> one lookup in the 3-leaf table.
+    auto is_gemm = [](const Op& o) { return o.kind == OP_GEMM_LEAF || o.kind == OP_GEMM_PUSH || o.kind == OP_GEMM_POP; };
+    auto plain_items = [](const Op& op, std::vector<Item>& items) {
+        if (op.kind == OP_CHERRY) { items.push_back({ITEM_LEAF, op.a}); items.push_back({ITEM_LEAF, op.b}); }
+        else if (op.kind == OP_GEMM_LEAF) { items.push_back({ITEM_P, op.a}); items.push_back({ITEM_LEAF, op.b}); }
+        else if (op.kind == OP_GEMM_PUSH || op.kind == OP_GEMM_POP) items.push_back({ITEM_P, op.a});
+    };
+    auto table_op = [](const Op& g, int table, int la, int lb, int lc) {  // g: the contraction the lookup replaces last
+        const int kind = (g.kind == OP_GEMM_LEAF ? OP_TAB_LEAF : g.kind == OP_GEMM_PUSH ? OP_TAB_PUSH : OP_TAB_POP) | (table << 8);
+        return Op{kind, la | (lb << 16), lc, g.kind == OP_GEMM_LEAF ? g.b : g.c};
+    };
     ctx->ops_t.clear();
     ctx->items_t.clear();
-    ctx->cherries.clear();
-    for (size_t i = 0; i < ctx->ops.size(); i++) {
+    ctx->ops_t3.clear();
+    ctx->items_t3.clear();
+    ctx->subtabs.clear();
+    std::vector<SubTab> triples;
+    std::vector<int> cherry_table_at(ctx->ops.size(), -1);
+    for (size_t i = 0; i + 1 < ctx->ops.size(); i++)
+        if (ctx->ops[i].kind == OP_CHERRY && is_gemm(ctx->ops[i + 1])) {
+            cherry_table_at[i] = (int)ctx->subtabs.size();
+            ctx->subtabs.push_back(SubTab{ctx->ops[i].a, ctx->ops[i].b, -1, ctx->ops[i + 1].a, -1, 0, 0});
+        }
+    ctx->n_tab2 = (int)ctx->subtabs.size();
+    for (size_t i = 0; i < ctx->ops.size(); i++) {  // level 2
         const Op& op = ctx->ops[i];
-        if (op.kind == OP_CHERRY && i + 1 < ctx->ops.size() && ctx->ops[i + 1].kind != OP_ROOT) {
-            const Op& g = ctx->ops[i + 1];  // the edge above the cherry's node: g.a
-            const int ti = (int)ctx->cherries.size();
-            ctx->cherries.push_back(Cherry{op.a, op.b, g.a});
-            const int kind = (g.kind == OP_GEMM_LEAF ? OP_TAB_LEAF : g.kind == OP_GEMM_PUSH ? OP_TAB_PUSH : OP_TAB_POP) | (ti << 8);
-            ctx->ops_t.push_back(Op{kind, op.a, op.b, g.kind == OP_GEMM_LEAF ? g.b : g.c});
+        if (cherry_table_at[i] >= 0) {
+            const Op& g = ctx->ops[i + 1];
+            ctx->ops_t.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1));
             if (g.kind == OP_GEMM_LEAF) ctx->items_t.push_back({ITEM_LEAF, g.b});
             i++;
             continue;
         }
         ctx->ops_t.push_back(op);
-        if (op.kind == OP_CHERRY) { ctx->items_t.push_back({ITEM_LEAF, op.a}); ctx->items_t.push_back({ITEM_LEAF, op.b}); }
-        else if (op.kind == OP_GEMM_LEAF) { ctx->items_t.push_back({ITEM_P, op.a}); ctx->items_t.push_back({ITEM_LEAF, op.b}); }
-        else if (op.kind == OP_GEMM_PUSH || op.kind == OP_GEMM_POP) ctx->items_t.push_back({ITEM_P, op.a});
+        plain_items(op, ctx->items_t);
     }
+    for (size_t i = 0; i < ctx->ops.size(); i++) {  // level 3
+        const Op& op = ctx->ops[i];
+        if (cherry_table_at[i] >= 0) {
+            const Op& g = ctx->ops[i + 1];
+            if (g.kind == OP_GEMM_LEAF && i + 2 < ctx->ops.size() && is_gemm(ctx->ops[i + 2])) {
+                const Op& g2 = ctx->ops[i + 2];  // the edge above the node that joins the cherry and the leaf g.b
+                const int ti = ctx->n_tab2 + (int)triples.size();
+                triples.push_back(SubTab{op.a, op.b, g.b, g2.a, cherry_table_at[i], 0, 0});
+                ctx->ops_t3.push_back(table_op(g2, ti, op.a, op.b, g.b));
+                if (g2.kind == OP_GEMM_LEAF) ctx->items_t3.push_back({ITEM_LEAF, g2.b});
+                i += 2;
+                continue;
+            }
+            ctx->ops_t3.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1));
+            if (g.kind == OP_GEMM_LEAF) ctx->items_t3.push_back({ITEM_LEAF, g.b});
+            i++;
+            continue;
+        }
+        ctx->ops_t3.push_back(op);
+        plain_items(op, ctx->items_t3);
+    }
+    ctx->n_tab3 = (int)triples.size();
+    ctx->subtabs.insert(ctx->subtabs.end(), triples.begin(), triples.end());
+    std::vector<long long> tab_off(ctx->subtabs.size());
+    for (size_t k = 0; k < ctx->subtabs.size(); k++) {
+        tab_off[k] = (int)k < ctx->n_tab2 ? (long long)k * CHERRY_TABLE : (long long)ctx->n_tab2 * CHERRY_TABLE + (long long)(k - ctx->n_tab2) * TRIPLE_TABLE;
+        ctx->subtabs[k].off = tab_off[k];
+    }
+    if (n_leaves > 0xffff) { ctx->n_tab2 = ctx->n_tab3 = 0; }  // leaf ids are packed into 16 bits
     CU(cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_branch_len) CU(cudaFree(ctx->d_branch_len));
-    if (ctx->d_ops) CU(cudaFree(ctx->d_ops));
-    if (ctx->d_items) CU(cudaFree(ctx->d_items));
-    if (ctx->d_ops_t) CU(cudaFree(ctx->d_ops_t));
-    if (ctx->d_items_t) CU(cudaFree(ctx->d_items_t));
-    if (ctx->d_cherries) CU(cudaFree(ctx->d_cherries));
-    CU(cudaMalloc(&ctx->d_ops_t, sizeof(Op) * std::max<size_t>(1, ctx->ops_t.size())));
-    CU(cudaMalloc(&ctx->d_items_t, sizeof(Item) * std::max<size_t>(1, ctx->items_t.size())));
-    CU(cudaMalloc(&ctx->d_cherries, sizeof(Cherry) * std::max<size_t>(1, ctx->cherries.size())));
-    CU(cudaMemcpy(ctx->d_ops_t, ctx->ops_t.data(), sizeof(Op) * ctx->ops_t.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_items_t, ctx->items_t.data(), sizeof(Item) * ctx->items_t.size(), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_cherries, ctx->cherries.data(), sizeof(Cherry) * ctx->cherries.size(), cudaMemcpyHostToDevice));
+    for (void** q : {(void**)&ctx->d_branch_len, (void**)&ctx->d_ops, (void**)&ctx->d_items, (void**)&ctx->d_ops_t, (void**)&ctx->d_items_t,
+                     (void**)&ctx->d_ops_t3, (void**)&ctx->d_items_t3, (void**)&ctx->d_subtabs, (void**)&ctx->d_tab_off}) {
+        if (*q) CU(cudaFree(*q));
+        *q = nullptr;
+    }
+    auto upload = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess || bytes == 0) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CU(upload((void**)&ctx->d_ops_t, ctx->ops_t.data(), sizeof(Op) * ctx->ops_t.size()));
+    CU(upload((void**)&ctx->d_items_t, ctx->items_t.data(), sizeof(Item) * ctx->items_t.size()));
+    CU(upload((void**)&ctx->d_ops_t3, ctx->ops_t3.data(), sizeof(Op) * ctx->ops_t3.size()));
+    CU(upload((void**)&ctx->d_items_t3, ctx->items_t3.data(), sizeof(Item) * ctx->items_t3.size()));
+    CU(upload((void**)&ctx->d_subtabs, ctx->subtabs.data(), sizeof(SubTab) * ctx->subtabs.size()));
+    CU(upload((void**)&ctx->d_tab_off, tab_off.data(), sizeof(long long) * tab_off.size()));
     CU(cudaMalloc(&ctx->d_branch_len, sizeof(double) * (n - 1)));
     CU(cudaMalloc(&ctx->d_ops, sizeof(Op) * ctx->ops.size()));
     CU(cudaMalloc(&ctx->d_items, sizeof(Item) * std::max<size_t>(1, ctx->items.size())));
@@ -775,7 +856,7 @@ int pcsf_lpr_all(pcsf_ctx* ctx, int n_models, const int32_t* model_ids, const in
     for (int m = 0; m < n_models; m++) {
         const int sc = scale_idx ? scale_idx[m] : 0;
         TRY(check_model(ctx, model_ids[m], sc));
-        if (want_cherry_tables(ctx, ctx->total_cols)) TRY(ensure_cherry_tables(ctx, ctx->models[model_ids[m]], sc));
+        TRY(ensure_tables(ctx, ctx->models[model_ids[m]], sc, want_table_level(ctx, ctx->total_cols)));
         psets.push_back(make_pset(ctx, model_ids[m], sc));
         spans.push_back(Span{0, (int64_t)m * ctx->total_cols, 0, (int32_t)0, m});
         spans.back().ncols = (int32_t)ctx->total_cols;
@@ -827,7 +908,7 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
     for (int m = 0; m < n_models; m++) {
         const int sc = scale_idx ? scale_idx[m] : 0;
         TRY(check_model(ctx, model_ids[m], sc));
-        if (want_cherry_tables(ctx, est_cols)) TRY(ensure_cherry_tables(ctx, ctx->models[model_ids[m]], sc));
+        TRY(ensure_tables(ctx, ctx->models[model_ids[m]], sc, want_table_level(ctx, est_cols)));
         psets.push_back(make_pset(ctx, model_ids[m], sc));
     }
     if (!ctx->copy_stream) {
@@ -1119,6 +1200,7 @@ int pcsf_lpr_pairs(pcsf_ctx* ctx, int64_t n_evals, const int64_t* eval_pair, con
             ps.prior = m.prior();
             ps.logprior = m.logprior();
             ps.cherry = nullptr;
+            ps.tab_level = 0;
             psets.push_back(ps);
             prev_pair = pr;
         }

@@ -33,20 +33,28 @@ enum OpKind : int32_t {
     OP_GEMM_PUSH = 2,  // stack[c] = P_a x cur                    sibling subtree still to come
     OP_GEMM_POP = 3,   // cur = (P_a x cur) * stack[c]
     OP_ROOT = 4,       // z = cur . prior, log z, root posterior . log prior
-    // cherry-table program (wide form, P sets that carry cherry tables): a cherry (leaves a, b) and the contraction
-    // over the edge above it are one lookup, W[table][code_a][code_b][.] = P_v x (G(a) * G(b)); `kind` carries the
-    // table index in its bits 8.., `c` the operand of the usual epilogue (sibling leaf / stack level)
+    // table program (wide form, P sets that carry subtree tables): a cherry (leaves a, b) - or a cherry plus the
+    // leaf c next to it - and the contractions up to and including the edge above that subtree are one lookup,
+    //   W2[code_a][code_b][.]         = P_v x (G(a) * G(b))
+    //   W3[code_a][code_b][code_c][.] = P_u x (W2[code_a][code_b] * G(c))
+    // Encoding: kind | table << 8, a = leaf a | leaf b << 16, b = leaf c (or -1), c = operand of the usual epilogue
     OP_TAB_LEAF = 5,   // cur = W * G(c)
     OP_TAB_PUSH = 6,   // stack[c] = W
     OP_TAB_POP = 7     // cur = W * stack[c]
 };
-constexpr int CHERRY_ROWS = 65 * 65;              // code pairs, 64 = marginalise
-constexpr int CHERRY_TABLE = CHERRY_ROWS * 64;    // doubles per cherry table (2.16 MB)
-struct Cherry {
-    int32_t la, lb, v;  // the two leaves and their parent node (= the branch above it)
-};
 struct Op {
     int32_t kind, a, b, c;
+};
+constexpr int CHERRY_ROWS = 65 * 65;              // code pairs, 64 = marginalise
+constexpr int CHERRY_TABLE = CHERRY_ROWS * 64;    // doubles per cherry table (2.16 MB)
+constexpr int TRIPLE_ROWS = 65 * 65 * 65;         // code triples
+constexpr long long TRIPLE_TABLE = (long long)TRIPLE_ROWS * 64;  // doubles per 3-leaf table (140.6 MB)
+struct SubTab {          // one memoised subtree
+    int32_t la, lb, lc;  // its leaves (lc = -1: a cherry)
+    int32_t edge;        // the node whose upward edge the table includes (the cherry's node v, or its parent u)
+    int32_t src;         // 3-leaf tables: index of the cherry table they are built from
+    int32_t pad;
+    long long off;       // offset of the table (doubles) in the P set's table block
 };
 
 // ---- work description --------------------------------------------------------------------------
@@ -63,7 +71,8 @@ struct PSet {
     const double* tables;    // [n_branches][PT_SLOT]
     const double* prior;     // [64]
     const double* logprior;  // [64]
-    const double* cherry;    // [n_cherries][CHERRY_TABLE], or null when not built for this P set
+    const double* cherry;    // subtree tables of this P set (SubTab::off), or null when not built
+    long long tab_level;     // 0 none, 2 cherries, 3 cherries and cherry+leaf subtrees
 };
 
 // ---- small PTX wrappers ------------------------------------------------------------------------
@@ -270,6 +279,7 @@ struct PruneParams {
     int items_bytes;         // n_items * sizeof(Item) rounded up to 16
     int skew_ns;             // start-up offset of the second compute warp of every SM sub-partition
     int32_t* global_exp;     // [gridDim.x][n_levels][TILE_COLS] exponents of parked partials (rescale only)
+    const long long* tab_off;  // table program: offset of every table in a P set's table block
     long long* timeline;     // PCSF_TIMELINE builds only: [warp][event][2] = (code, clock64) of CTA 0
     int timeline_cap;
 };
@@ -882,12 +892,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                 // -------------------- cherry + the edge above it: one 512-byte row of the cherry's table per column --------------------
                 ekind = (op.kind & 0xff) - OP_TAB_LEAF + OP_GEMM_LEAF;  // LEAF / PUSH / POP epilogue as after a contraction
                 if (warp_active) {
-                    const double* W = reinterpret_cast<const double*>(scratch[2]) + (size_t)(op.kind >> 8) * CHERRY_TABLE + 2 * t;
-                    uint32_t a0 = lds_u8(codes0 + op.a), a1 = lds_u8(codes0 + 8 * p.n_leaves + op.a);
-                    uint32_t b0 = lds_u8(codes0 + op.b), b1 = lds_u8(codes0 + 8 * p.n_leaves + op.b);
-                    a0 = a0 > 64 ? 64 : a0; a1 = a1 > 64 ? 64 : a1; b0 = b0 > 64 ? 64 : b0; b1 = b1 > 64 ? 64 : b1;
-                    const double2* r0 = reinterpret_cast<const double2*>(W + (size_t)(a0 * 65 + b0) * 64);
-                    const double2* r1 = reinterpret_cast<const double2*>(W + (size_t)(a1 * 65 + b1) * 64);
+                    const double* W = reinterpret_cast<const double*>(scratch[2]) + p.tab_off[op.kind >> 8] + 2 * t;
+                    auto code = [&](uint32_t leaf, int col8) {
+                        const uint32_t c = lds_u8(codes0 + col8 * p.n_leaves + leaf);
+                        return c > 64 ? 64u : c;
+                    };
+                    const uint32_t la = op.a & 0xffff, lb = (uint32_t)op.a >> 16;
+                    uint32_t row0 = code(la, 0) * 65 + code(lb, 0), row1 = code(la, 8) * 65 + code(lb, 8);
+                    if (op.b >= 0) {
+                        row0 = row0 * 65 + code(op.b, 0);
+                        row1 = row1 * 65 + code(op.b, 8);
+                    }
+                    const double2* r0 = reinterpret_cast<const double2*>(W + (size_t)row0 * 64);
+                    const double2* r1 = reinterpret_cast<const double2*>(W + (size_t)row1 * 64);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const double2 v0 = __ldg(r0 + 4 * j), v1 = __ldg(r1 + 4 * j);
@@ -985,37 +1002,47 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
 }
 
 // =================================================================================================
-// Cherry tables: W[cherry][code_a][code_b][y] = sum_x P_v[y][x] (G_a[code_a][x] G_b[code_b][x]) for every cherry of the
-// tree - what the pruning kernels compute for a column whose two leaves carry (code_a, code_b), memoised over the
-// 65 x 65 code pairs. Built with the very instruction sequence of the pruning kernels (same products, same DMMA
-// accumulation order), 16 code pairs per warp as if they were 16 columns, so a lookup is bit-identical to the
-// computation it replaces. Worth building when a P set scores many columns (fixed strategy): 17 of the 56
-// contractions per column of the 58mammals tree become 512-byte gathers.
+// Subtree tables. For a cherry (leaves a, b under node v) the partial likelihood that leaves the edge above v,
+// W2[code_a][code_b][y] = sum_x P_v[y][x] (G_a[code_a][x] G_b[code_b][x]), depends on the column only through the code
+// pair; if the cherry's sibling is a leaf c (parent u), W3[code_a][code_b][code_c] = P_u x (W2[code_a][code_b] * G_c[code_c])
+// only through the triple. Both are memoised over all 65^2 / 65^3 code tuples with the very instruction sequence of
+// the pruning kernels (same products, same fragment-ordered image, same DMMA accumulation order), 16 tuples per warp as
+// if they were 16 columns, so a lookup is bit-identical to the computation it replaces.
 // =================================================================================================
-__global__ void __launch_bounds__(128) cherry_table_kernel(const double* __restrict__ tables, const Cherry* __restrict__ cherries,
-                                                           int n_cherries, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) subtree_table_kernel(const double* __restrict__ tables, const SubTab* __restrict__ tabs,
+                                                            int first, int count, int rows, double* __restrict__ base) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int warps_per_cherry = (CHERRY_ROWS + 15) / 16;
+    const int warps_per_table = (rows + 15) / 16;
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (wid >= (long long)n_cherries * warps_per_cherry) return;
-    const int ci = (int)(wid / warps_per_cherry), q0 = (int)(wid % warps_per_cherry) * 16;
-    const Cherry ch = cherries[ci];
-    const double* ta = tables + (size_t)ch.la * PT_SLOT;
-    const double* tb = tables + (size_t)ch.lb * PT_SLOT;
-    const double* Pb = tables + (size_t)ch.v * PT_SLOT + lane;
+    if (wid >= (long long)count * warps_per_table) return;
+    const SubTab tb = tabs[first + (int)(wid / warps_per_table)];
+    const int q0 = (int)(wid % warps_per_table) * 16;
+    const double* Pb = tables + (size_t)tb.edge * PT_SLOT + lane;
     double cur[2][8][2], acc[2][8][2];
 #pragma unroll
     for (int T = 0; T < 2; T++) {
-        const int q = min(q0 + 8 * T + g, CHERRY_ROWS - 1);  // padding pairs repeat the last one (never stored)
-        const double2* ra = reinterpret_cast<const double2*>(ta + (q / 65) * 64 + 2 * t);
-        const double2* rb = reinterpret_cast<const double2*>(tb + (q % 65) * 64 + 2 * t);
+        const int q = min(q0 + 8 * T + g, rows - 1);  // padding tuples repeat the last one (never stored)
+        if (tb.lc < 0) {  // cherry: the product of the two leaf messages, as in the pruning kernels
+            const double2* ra = reinterpret_cast<const double2*>(tables + (size_t)tb.la * PT_SLOT + (q / 65) * 64 + 2 * t);
+            const double2* rb = reinterpret_cast<const double2*>(tables + (size_t)tb.lb * PT_SLOT + (q % 65) * 64 + 2 * t);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double2 u = ra[4 * j], v = rb[4 * j];
-            cur[T][j][0] = u.x * v.x;  // the cherry's product, as in the pruning kernels
-            cur[T][j][1] = u.y * v.y;
-            acc[T][j][0] = acc[T][j][1] = 0.0;
+            for (int j = 0; j < 8; j++) {
+                const double2 u = ra[4 * j], v = rb[4 * j];
+                cur[T][j][0] = u.x * v.x;
+                cur[T][j][1] = u.y * v.y;
+            }
+        } else {  // cherry + leaf: the cherry's table row times the leaf message, as in the GEMM_LEAF epilogue
+            const double2* rw = reinterpret_cast<const double2*>(base + tabs[tb.src].off + (size_t)(q / 65) * 64 + 2 * t);
+            const double2* rc = reinterpret_cast<const double2*>(tables + (size_t)tb.lc * PT_SLOT + (q % 65) * 64 + 2 * t);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double2 w = rw[4 * j], v = rc[4 * j];
+                cur[T][j][0] = w.x * v.x;
+                cur[T][j][1] = w.y * v.y;
+            }
         }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[T][j][0] = acc[T][j][1] = 0.0;
     }
 #pragma unroll
     for (int s = 0; s < 16; s++) {
@@ -1029,8 +1056,8 @@ __global__ void __launch_bounds__(128) cherry_table_kernel(const double* __restr
 #pragma unroll
     for (int T = 0; T < 2; T++) {
         const int q = q0 + 8 * T + g;
-        if (q < CHERRY_ROWS) {
-            double2* w = reinterpret_cast<double2*>(out + (size_t)ci * CHERRY_TABLE + (size_t)q * 64 + 2 * t);
+        if (q < rows) {
+            double2* w = reinterpret_cast<double2*>(base + tb.off + (size_t)q * 64 + 2 * t);
 #pragma unroll
             for (int j = 0; j < 8; j++) w[4 * j] = make_double2(acc[T][j][0], acc[T][j][1]);
         }

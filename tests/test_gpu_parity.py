@@ -127,10 +127,10 @@ def test_both_kernel_forms_match_oracle_and_each_other(params_base, pset):
     off, codes = H.regions_to_batch(regs)
     ctx.batch_upload(off, codes)
     got = {}
-    # the third variant: the wide form running the cherry-table program (a cherry and the contraction above it as
-    # one lookup in a table built with the kernel's own instruction sequence)
-    for form, cherry in ((pb.Context.FORM_NARROW, 1), (pb.Context.FORM_WIDE, 1), ("tabled", 2)):
-        ctx.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_WIDE if form == "tabled" else form)
+    # further variants: the wide form running the table programs (a cherry - or a cherry and the leaf next to it - and
+    # the contractions above them as one lookup in a table built with the kernel's own instruction sequence)
+    for form, cherry in ((pb.Context.FORM_NARROW, 1), (pb.Context.FORM_WIDE, 1), ("pairs", 3), ("triples", 2)):
+        ctx.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_WIDE if isinstance(form, str) else form)
         ctx.option_set(pb.Context.OPT_CHERRY_TABLES, cherry)
         for rep in range(2):
             lpr, elpr, st = ctx.lpr_all([0, 1])
@@ -149,7 +149,7 @@ def test_both_kernel_forms_match_oracle_and_each_other(params_base, pset):
         l2, e2, _ = ctx.lpr(em, np.zeros_like(em), er)
         assert (l2.reshape(2, -1) == got[form][0]).all() and (e2.reshape(2, -1) == got[form][1]).all()
     a = got[pb.Context.FORM_NARROW]
-    for other in (pb.Context.FORM_WIDE, "tabled"):
+    for other in (pb.Context.FORM_WIDE, "pairs", "triples"):
         b = got[other]
         assert all((x == y).all() for x, y in zip(a[2], b[2])) and all((x == y).all() for x, y in zip(a[3], b[3])), other  # per column
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), other
@@ -432,7 +432,7 @@ def _lpr_extended_precision(model, codes):
     return float(np.log(z).sum())
 
 
-@pytest.mark.parametrize("form", [1, 2, 3])
+@pytest.mark.parametrize("form", [1, 2, 3, 4])
 def test_rescale_option_rescues_underflow(params_base, form):
     """(in both forms of the pruning kernel) PCSF_OPT_RESCALE: uniform-random columns on the 120-leaf tree underflow to -inf without it (the
     reference's behaviour); with it the score is finite and equals an extended-precision evaluation.
@@ -450,7 +450,7 @@ def test_rescale_option_rescues_underflow(params_base, form):
     off, codes = H.regions_to_batch(regs)
     ctx.batch_upload(off, codes)
     ctx.option_set(2, min(form, 2))
-    ctx.option_set(3, 2 if form == 3 else 1)  # form 3: the wide form with cherry tables
+    ctx.option_set(3, {3: 3, 4: 2}.get(form, 1))  # forms 3, 4: the wide form with cherry tables / + 3-leaf tables
     lpr0, elpr0, st0 = ctx.lpr_all([0, 1])
     assert np.isneginf(lpr0[:, 0]).all() and np.isfinite(lpr0[:, 1]).all()
     ctx.option_set(1, 1)
