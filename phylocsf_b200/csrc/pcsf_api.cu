@@ -65,7 +65,7 @@ struct pcsf_ctx {
     DevBuf d_region_off, d_codes, d_nt, d_aln_off, d_aln_len;
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
-    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs, d_gexp;
+    DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs, d_gexp, d_pair_cherry;
     // pcsf_score_alignments: double-buffered chunk staging on a second stream
     DevBuf pipe_nt[2], pipe_aln_off[2], pipe_aln_len[2], pipe_codes[2], pipe_roff[2];
     cudaStream_t copy_stream = nullptr;
@@ -510,11 +510,12 @@ void pcsf_destroy(pcsf_ctx* ctx) {
         fr(m.tables);
         fr(m.d_scales);
         fr(m.d_status);
+        fr(m.cherry);
     }
     DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
                       &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
-                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
+                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp, &ctx->d_pair_cherry, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
                       &ctx->pipe_aln_off[1], &ctx->pipe_aln_len[0], &ctx->pipe_aln_len[1], &ctx->pipe_codes[0], &ctx->pipe_codes[1],
                       &ctx->pipe_roff[0], &ctx->pipe_roff[1]};
     for (auto* b : bufs) fr(*b);
@@ -1214,6 +1215,28 @@ int pcsf_lpr_pairs(pcsf_ctx* ctx, int64_t n_evals, const int64_t* eval_pair, con
             spans.push_back(Span{c0, out, 0, (int32_t)nc, (int32_t)psets.size() - 1});
         }
         out += nc;
+    }
+    // A round of candidates that all regions share (the bracket ends, the starting point, Brent's first golden-section
+    // point, find_init's fixed random stream) scores the whole batch under a handful of P sets: worth their cherry
+    // tables, built into a scratch block that lives until the next call.
+    if (!psets.empty() && psets.size() <= 8 && ctx->cherry_mode != 1 && ctx->wide != 0 && ctx->n_tab2 > 0) {
+        std::vector<int64_t> cols(psets.size(), 0);
+        for (const Span& sp : spans) cols[sp.pset] += sp.ncols;
+        bool all_long = true;
+        for (int64_t c : cols) all_long = all_long && (ctx->cherry_mode >= 2 || c >= 50000);
+        if (all_long) {
+            const size_t block = table_block_doubles(ctx, 2);
+            TRY(reserve(ctx, ctx->d_pair_cherry, sizeof(double) * block * psets.size()));
+            const long long warps = (long long)ctx->n_tab2 * ((CHERRY_ROWS + 15) / 16);
+            for (size_t i = 0; i < psets.size(); i++) {
+                double* base = (double*)ctx->d_pair_cherry.p + i * block;
+                subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(psets[i].tables, ctx->d_subtabs, 0, ctx->n_tab2, CHERRY_ROWS, base);
+                CU(cudaGetLastError());
+                ctx->launches++;
+                psets[i].cherry = base;
+                psets[i].tab_level = 2;
+            }
+        }
     }
     TRY(eval_spans(ctx, spans, psets, out, seg_b, seg_e, out_lpr, out_elpr_anc));
     if (out_status)
