@@ -258,6 +258,20 @@ def test_scores_match_oracle_lines(params_base, pset, fn, flags, kw):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_fixed_with_subtree_tables_forced(params_base, monkeypatch, mode):
+    """The command line with the memoised subtree tables forced on (they are built only for big batches otherwise) and
+    the wide form of the pruning kernel: the same lines as the oracle, 6 frames, ancestral composition included."""
+    monkeypatch.setenv("PCSF_CHERRY_TABLES", mode)
+    monkeypatch.setenv("PCSF_WIDE", "1")
+    path = ex(params_base, "ALDH2.exon5.fa")
+    flags = ["--strategy=fixed", "--frames=6", "--allScores", "--ancComp"]
+    got = run_cli(params_base, "29mammals", [path] * 2, *flags)
+    want = run_oracle(params_base, "29mammals", path, gp.example_lines("ALDH2.exon5.fa"), strategy="fixed", frames=6, all_scores=True, anc_comp=True)
+    same_lines(got, want * 2)
+
+
+@pytest.mark.gpu
 def test_many_alignments_one_batch_keep_order(params_base, tmp_path):
     """Several alignments are staged as one GPU batch; output order and values equal one-by-one runs."""
     files = [ex(params_base, "ALDH2.exon5.fa")] * 3
