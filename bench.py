@@ -230,6 +230,8 @@ def main():
 
     ctx.batch_upload_alignments(aln_off, aln_len, nt_np, FRAMES)
     R, total_cols = ctx.nregions, ctx.ncols
+    # one-time work per P set, outside the timed region like the reference's memoised P(t): K1 and the subtree tables
+    setup = {"pt_build_ms_per_model": ctx.last_ms(2)}
     out_lpr = torch.empty((2, R), dtype=torch.float64, pin_memory=True)
     out_elpr = torch.empty((2, R), dtype=torch.float64, pin_memory=True)
     outs = (out_lpr.numpy(), out_elpr.numpy())
@@ -250,7 +252,9 @@ def main():
     sampler = ClockSampler(uuid)
 
     # ---- device-resident: value ----
-    for _ in range(args.warmup):
+    step_resident()
+    setup["subtree_tables_ms_per_model"] = ctx.last_ms(5)  # built by the first pass that scores enough columns
+    for _ in range(args.warmup - 1):
         step_resident()
     barrier()
     sampler.start()
@@ -325,6 +329,7 @@ def main():
                     "d2h_bytes_per_step": int(outs[0].nbytes + outs[1].nbytes), "ms_per_step": ms_e2e / args.steps,
                     "path": "pcsf_score_alignments: pinned host nucleotide rows -> chunked H2D overlapped with on-device pleaves + pruning + reduction -> D2H"},
             "gpu_launches": int(launches),
+            "setup": setup,
             "clocks": clocks,
             "roofline": {"kernel": "pcsf::prune_wide_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms,

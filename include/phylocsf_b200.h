@@ -217,7 +217,8 @@ int pcsf_maximize_lpr_multi(pcsf_ctx *ctx, int n_models, const int32_t *model_id
 
 /* Timing of the most recent call, measured with CUDA events on the context's stream:
  * which = 0 pruning kernel (K2+K3 fused), 1 region reduction (K4), 2 P(t) build (K1),
- * 3 H2D copies, 4 D2H copies. Returns milliseconds, or a negative value if not recorded. */
+ * 3 H2D copies, 4 D2H copies; 5 = the most recent build of subtree tables (PCSF_OPT_CHERRY_TABLES; once per
+ * P set). Returns milliseconds, or a negative value if not recorded. */
 double pcsf_last_ms(const pcsf_ctx *ctx, int which);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t pcsf_launch_count(const pcsf_ctx *ctx);

@@ -73,8 +73,8 @@ struct pcsf_ctx {
     std::vector<int32_t> pair_model, pair_status;  // P sets built by pcsf_pt_build_pairs
     int last_all_models = 0;
     // timing
-    cudaEvent_t ev[10];
-    double ms[5] = {-1, -1, -1, -1, -1};
+    cudaEvent_t ev[12];
+    double ms[6] = {-1, -1, -1, -1, -1, -1};  // [5]: the most recent build of subtree tables
     int64_t launches = 0;
     int prune_smem_optin = 0;
     int skew_ns = 1500;
@@ -374,6 +374,7 @@ int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
     }
     const double* tables = (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT;
     double* base = (double*)m.cherry.p + (size_t)scale * table_block_doubles(ctx, m.cherry_level);
+    CU(cudaEventRecord(ctx->ev[10], ctx->stream));
     if (m.cherry_built[scale] < 2) {
         const long long warps = (long long)ctx->n_tab2 * ((CHERRY_ROWS + 15) / 16);
         subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, 0, ctx->n_tab2, CHERRY_ROWS, base);
@@ -386,6 +387,11 @@ int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
         CU(cudaGetLastError());
         ctx->launches++;
     }
+    CU(cudaEventRecord(ctx->ev[11], ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev[11]));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]));
+    ctx->ms[5] = t;
     m.cherry_built[scale] = (char)level;
     return PCSF_OK;
 }
@@ -1367,7 +1373,7 @@ int pcsf_debug_timeline(pcsf_ctx* ctx, int cap, long long* out) {
 #endif
 
 double pcsf_last_ms(const pcsf_ctx* ctx, int which) {
-    if (!ctx || which < 0 || which > 4) return -1.0;
+    if (!ctx || which < 0 || which > 5) return -1.0;
     return ctx->ms[which];
 }
 
