@@ -311,9 +311,14 @@ def main():
         cherries = [nl + i for i, pair in enumerate(ch) if (pair < nl).all() and nl + i != root]
         # a cherry whose sibling is a leaf, under a node that has an edge of its own: one lookup replaces two contractions
         triples = [v for v in cherries if parent[v] != root and min(int(c) for c in ch[parent[v] - nl] if int(c) != v) < nl]
+        def sibling(v):
+            return [int(c) for c in ch[parent[v] - nl] if int(c) != v][0]
+        # ... and a further leaf next to that (a caterpillar of four)
+        quads = [parent[v] for v in triples if parent[parent[v]] != root and sibling(parent[v]) < nl]
         mode = os.environ.get("PCSF_CHERRY_TABLES", "0")
         tabled = mode != "1" and os.environ.get("PCSF_WIDE", "-1") != "0"
-        n_lookup_edges = 0 if not tabled else len(cherries) + (len(triples) if mode in ("0", "2") and total_cols >= 1000000 or mode == "2" else 0)
+        level = 0 if not tabled else {"2": 3, "3": 2, "4": 4}.get(mode, 4 if total_cols >= 5000000 else 3 if total_cols >= 1000000 else 2 if total_cols >= 50000 else 0)
+        n_lookup_edges = (len(cherries) if level >= 2 else 0) + (len(triples) if level >= 3 else 0) + (len(quads) if level >= 4 else 0)
         executed_share = (nl - 2 - n_lookup_edges) / (nl - 2)
         traffic = None  # dram__bytes_read+write of one launch: ncu-measured bytes per codon column x columns
         try:

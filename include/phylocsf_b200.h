@@ -76,12 +76,13 @@ int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
 #define PCSF_OPT_PRUNE_FORM 2
 /*
  * PCSF_OPT_CHERRY_TABLES: memoise, per P set, the partial likelihood above every cherry of the tree over the
- * 65 x 65 code pairs of its two leaves (2.16 MB per cherry) and, one level up, above every cherry-and-leaf subtree over
- * the 65^3 code triples (140.6 MB each). The tables are computed with the pruning kernel's own instruction sequence, so
- * a lookup is bit-identical to the computation it replaces. 0 (default) = built by pcsf_lpr_all / pcsf_score_alignments
- * when the wide form runs and a P set scores >= 50,000 columns (cherries) / >= 1,000,000 columns and memory allows
- * (3-leaf subtrees); 1 = never; 2 = always, both levels; 3 = always, cherries only. PCSF_CHERRY_TABLES in the
- * environment sets it for every new context.
+ * 65 x 65 code pairs of its two leaves (2.16 MB per cherry); one level up, above every cherry-and-leaf subtree over
+ * the 65^3 code triples (140.6 MB each); and above every caterpillar of four leaves over the 65^4 quadruples (9.14 GB
+ * each). The tables are computed with the pruning kernel's own instruction sequence, so a lookup is bit-identical
+ * to the computation it replaces. 0 (default) = built by pcsf_lpr_all / pcsf_score_alignments when the wide form runs
+ * and a P set scores >= 50,000 columns (cherries) / >= 1,000,000 (3 leaves) / >= 5,000,000 (4 leaves), the larger
+ * ones only while device memory allows; 1 = never; 2 = always, up to 3 leaves; 3 = always, cherries only;
+ * 4 = always, up to 4 leaves. PCSF_CHERRY_TABLES in the environment sets it for every new context.
  */
 #define PCSF_OPT_CHERRY_TABLES 3
 int pcsf_option_set(pcsf_ctx *ctx, int option, int64_t value);

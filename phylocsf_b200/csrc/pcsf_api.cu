@@ -79,15 +79,15 @@ struct pcsf_ctx {
     int prune_smem_optin = 0;
     int skew_ns = 1500;
     // cherry-table program: the tree program with every (cherry, edge above it) pair folded into one lookup
-    std::vector<Op> ops_t, ops_t3;      // level 2 (cherries) and level 3 (+ cherry-and-leaf subtrees) programs
-    std::vector<Item> items_t, items_t3;
-    std::vector<SubTab> subtabs;        // cherries first (n_tab2), then the 3-leaf subtrees (n_tab3)
-    int n_tab2 = 0, n_tab3 = 0;
-    Op *d_ops_t = nullptr, *d_ops_t3 = nullptr;
-    Item *d_items_t = nullptr, *d_items_t3 = nullptr;
+    std::vector<Op> ops_t, ops_t3, ops_t4;  // level 2 (cherries), 3 (+ cherry-and-leaf subtrees), 4 (+ caterpillars of four) programs
+    std::vector<Item> items_t, items_t3, items_t4;
+    std::vector<SubTab> subtabs;        // cherries first (n_tab2), then the 3-leaf (n_tab3) and the 4-leaf subtrees (n_tab4)
+    int n_tab2 = 0, n_tab3 = 0, n_tab4 = 0;
+    Op *d_ops_t = nullptr, *d_ops_t3 = nullptr, *d_ops_t4 = nullptr;
+    Item *d_items_t = nullptr, *d_items_t3 = nullptr, *d_items_t4 = nullptr;
     SubTab* d_subtabs = nullptr;
     long long* d_tab_off = nullptr;
-    int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 by the number of columns a P set scores, 1 never, 2 always (deepest), 3 always, cherries only
+    int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 by the number of columns a P set scores, 1 never, 2 always levels 2-3, 3 always cherries only, 4 always levels 2-4
     int wide = -1;  // pruning kernel form: 0 narrow (128-column tiles), 1 wide (192), -1 chosen per launch (PCSF_WIDE overrides)
     int rescale = 0;  // PCSF_OPT_RESCALE
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
@@ -228,16 +228,17 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         const int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
         if (ctx->max_levels > 0) TRY(reserve(ctx, ctx->d_gstack, (size_t)grid * ctx->max_levels * level_bytes));
         // the cherry-table program runs when the wide form does and every P set of the launch carries its tables
-        long long level = (wide && ctx->n_tab2 > 0) ? 3 : 0;
+        long long level = (wide && ctx->n_tab2 > 0) ? 4 : 0;
         for (const PSet& q : psets) level = std::min(level, q.cherry ? q.tab_level : 0LL);
+        if (level == 4 && ctx->n_tab4 == 0) level = 3;
         if (level == 3 && ctx->n_tab3 == 0) level = 2;
-        const std::vector<Op>& prog_ops = level == 3 ? ctx->ops_t3 : level == 2 ? ctx->ops_t : ctx->ops;
-        const std::vector<Item>& prog_items = level == 3 ? ctx->items_t3 : level == 2 ? ctx->items_t : ctx->items;
+        const std::vector<Op>& prog_ops = level == 4 ? ctx->ops_t4 : level == 3 ? ctx->ops_t3 : level == 2 ? ctx->ops_t : ctx->ops;
+        const std::vector<Item>& prog_items = level == 4 ? ctx->items_t4 : level == 3 ? ctx->items_t3 : level == 2 ? ctx->items_t : ctx->items;
         PruneParams p;
         memset(&p, 0, sizeof(p));
-        p.ops = level == 3 ? ctx->d_ops_t3 : level == 2 ? ctx->d_ops_t : ctx->d_ops;
+        p.ops = level == 4 ? ctx->d_ops_t4 : level == 3 ? ctx->d_ops_t3 : level == 2 ? ctx->d_ops_t : ctx->d_ops;
         p.n_ops = (int)prog_ops.size();
-        p.items = level == 3 ? ctx->d_items_t3 : level == 2 ? ctx->d_items_t : ctx->d_items;
+        p.items = level == 4 ? ctx->d_items_t4 : level == 3 ? ctx->d_items_t3 : level == 2 ? ctx->d_items_t : ctx->d_items;
         p.n_items = (int)prog_items.size();
         p.tab_off = ctx->d_tab_off;
         p.n_leaves = ctx->n_leaves;
@@ -325,7 +326,8 @@ int check_model(pcsf_ctx* ctx, int model_id, int scale) {
 }
 
 size_t table_block_doubles(const pcsf_ctx* ctx, int level) {  // subtree tables of one P set
-    return (size_t)ctx->n_tab2 * CHERRY_TABLE + (level >= 3 ? (size_t)ctx->n_tab3 * (size_t)TRIPLE_TABLE : 0);
+    return (size_t)ctx->n_tab2 * CHERRY_TABLE + (level >= 3 ? (size_t)ctx->n_tab3 * (size_t)TRIPLE_TABLE : 0) +
+           (level >= 4 ? (size_t)ctx->n_tab4 * (size_t)QUAD_TABLE : 0);
 }
 
 PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
@@ -348,23 +350,28 @@ PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
 // from about a million, and only while they fit comfortably in device memory.
 int want_table_level(pcsf_ctx* ctx, int64_t cols_per_pset) {
     if (ctx->cherry_mode == 1 || ctx->wide == 0 || ctx->n_tab2 == 0) return 0;
-    return ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : cols_per_pset >= 1000000 ? 3 : cols_per_pset >= 50000 ? 2 : 0;
+    if (ctx->cherry_mode >= 2) return ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : 4;
+    return cols_per_pset >= 5000000 ? 4 : cols_per_pset >= 1000000 ? 3 : cols_per_pset >= 50000 ? 2 : 0;
 }
 
 // Build (once) the subtree tables of model `m` at scale index `scale` up to `level`. Only for models with a handful
 // of scales (the fixed strategy's): per-candidate P sets of mle / omega score too few columns to pay for them.
 int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
     if (level == 0 || ctx->n_tab2 == 0 || m.nscales > 8) return PCSF_OK;
-    if (ctx->n_tab3 == 0) level = 2;
+    if (level == 4 && ctx->n_tab4 == 0) level = 3;
+    if (level == 3 && ctx->n_tab3 == 0) level = 2;
     if ((int)m.cherry_built.size() != m.nscales) m.cherry_built.assign(m.nscales, 0);
     if (m.cherry_built[scale] >= level) return PCSF_OK;
-    if (level == 3 && m.cherry_level < 3) {  // about to allocate the large tables: only while they fit comfortably
+    while (level >= 3 && m.cherry_level < level) {  // about to allocate large tables: only while they fit comfortably
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
-        if ((double)free_b < 6.0 * sizeof(double) * (double)table_block_doubles(ctx, 3) * m.nscales) {
-            level = 2;  // no room for a few such blocks and the batch: stay with the cherries
-            if (m.cherry_built[scale] >= level) return PCSF_OK;
-        }
+        const double need = sizeof(double) * (double)table_block_doubles(ctx, level) * m.nscales;
+        // level 3 (a GB or so): room for a few such blocks and the batch; level 4 (tens of GB): room for the other
+        // model's block too and 16 GB to spare
+        if ((double)free_b + (double)m.cherry.cap >= (level == 3 ? 6.0 * need : 2.0 * need + 16e9)) break;
+        level--;
+        if (level == 3 && ctx->n_tab3 == 0) level = 2;
+        if (m.cherry_built[scale] >= level) return PCSF_OK;
     }
     if (m.cherry_level < level || m.cherry.cap < sizeof(double) * table_block_doubles(ctx, level) * m.nscales) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -381,9 +388,15 @@ int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
         CU(cudaGetLastError());
         ctx->launches++;
     }
-    if (level == 3) {
+    if (level >= 3 && m.cherry_built[scale] < 3 && ctx->n_tab3 > 0) {
         const long long warps = (long long)ctx->n_tab3 * ((TRIPLE_ROWS + 15) / 16);
         subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, ctx->n_tab2, ctx->n_tab3, TRIPLE_ROWS, base);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (level >= 4 && ctx->n_tab4 > 0) {
+        const long long warps = (long long)ctx->n_tab4 * ((QUAD_ROWS + 15) / 16);
+        subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, ctx->n_tab2 + ctx->n_tab3, ctx->n_tab4, QUAD_ROWS, base);
         CU(cudaGetLastError());
         ctx->launches++;
     }
@@ -528,7 +541,8 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     if (ctx->d_branch_len) cudaFree(ctx->d_branch_len);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
     if (ctx->d_items) cudaFree(ctx->d_items);
-    for (void* q : {(void*)ctx->d_ops_t, (void*)ctx->d_items_t, (void*)ctx->d_ops_t3, (void*)ctx->d_items_t3, (void*)ctx->d_subtabs, (void*)ctx->d_tab_off})
+    for (void* q : {(void*)ctx->d_ops_t, (void*)ctx->d_items_t, (void*)ctx->d_ops_t3, (void*)ctx->d_items_t3, (void*)ctx->d_ops_t4,
+                    (void*)ctx->d_items_t4, (void*)ctx->d_subtabs, (void*)ctx->d_tab_off})
         if (q) cudaFree(q);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; i++) {
@@ -562,7 +576,7 @@ int pcsf_option_set(pcsf_ctx* ctx, int option, int64_t value) {
         return PCSF_OK;
     }
     if (option == PCSF_OPT_CHERRY_TABLES) {
-        if (value < 0 || value > 3) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_CHERRY_TABLES takes 0 .. 3");
+        if (value < 0 || value > 4) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_option_set: PCSF_OPT_CHERRY_TABLES takes 0 .. 4");
         ctx->cherry_mode = (int)value;
         return PCSF_OK;
     }
@@ -614,17 +628,20 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         else if (op.kind == OP_GEMM_LEAF) { items.push_back({ITEM_P, op.a}); items.push_back({ITEM_LEAF, op.b}); }
         else if (op.kind == OP_GEMM_PUSH || op.kind == OP_GEMM_POP) items.push_back({ITEM_P, op.a});
     };
-    auto table_op = [](const Op& g, int table, int la, int lb, int lc) {  // g: the contraction the lookup replaces last
+    auto table_op = [](const Op& g, int table, int la, int lb, int lc, int ld) {  // g: the contraction the lookup replaces last
         const int kind = (g.kind == OP_GEMM_LEAF ? OP_TAB_LEAF : g.kind == OP_GEMM_PUSH ? OP_TAB_PUSH : OP_TAB_POP) | (table << 8);
-        return Op{kind, la | (lb << 16), lc, g.kind == OP_GEMM_LEAF ? g.b : g.c};
+        const uint32_t b = (uint32_t)(lc < 0 ? 0xffff : lc) | ((uint32_t)(ld < 0 ? 0xffff : ld) << 16);
+        return Op{kind, la | (lb << 16), (int32_t)b, g.kind == OP_GEMM_LEAF ? g.b : g.c};
     };
     ctx->ops_t.clear();
     ctx->items_t.clear();
     ctx->ops_t3.clear();
     ctx->items_t3.clear();
     ctx->subtabs.clear();
-    std::vector<SubTab> triples;
-    std::vector<int> cherry_table_at(ctx->ops.size(), -1);
+    std::vector<SubTab> triples, quads;
+    std::vector<int> cherry_table_at(ctx->ops.size(), -1), triple_table_at(ctx->ops.size(), -1);
+    ctx->ops_t4.clear();
+    ctx->items_t4.clear();
     for (size_t i = 0; i + 1 < ctx->ops.size(); i++)
         if (ctx->ops[i].kind == OP_CHERRY && is_gemm(ctx->ops[i + 1])) {
             cherry_table_at[i] = (int)ctx->subtabs.size();
@@ -635,7 +652,7 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         const Op& op = ctx->ops[i];
         if (cherry_table_at[i] >= 0) {
             const Op& g = ctx->ops[i + 1];
-            ctx->ops_t.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1));
+            ctx->ops_t.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1, -1));
             if (g.kind == OP_GEMM_LEAF) ctx->items_t.push_back({ITEM_LEAF, g.b});
             i++;
             continue;
@@ -650,13 +667,14 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
             if (g.kind == OP_GEMM_LEAF && i + 2 < ctx->ops.size() && is_gemm(ctx->ops[i + 2])) {
                 const Op& g2 = ctx->ops[i + 2];  // the edge above the node that joins the cherry and the leaf g.b
                 const int ti = ctx->n_tab2 + (int)triples.size();
+                triple_table_at[i] = ti;
                 triples.push_back(SubTab{op.a, op.b, g.b, g2.a, cherry_table_at[i], 0, 0});
-                ctx->ops_t3.push_back(table_op(g2, ti, op.a, op.b, g.b));
+                ctx->ops_t3.push_back(table_op(g2, ti, op.a, op.b, g.b, -1));
                 if (g2.kind == OP_GEMM_LEAF) ctx->items_t3.push_back({ITEM_LEAF, g2.b});
                 i += 2;
                 continue;
             }
-            ctx->ops_t3.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1));
+            ctx->ops_t3.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1, -1));
             if (g.kind == OP_GEMM_LEAF) ctx->items_t3.push_back({ITEM_LEAF, g.b});
             i++;
             continue;
@@ -665,16 +683,49 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         plain_items(op, ctx->items_t3);
     }
     ctx->n_tab3 = (int)triples.size();
+    for (size_t i = 0; i < ctx->ops.size(); i++) {  // level 4: a further leaf d joins the 3-leaf subtree
+        const Op& op = ctx->ops[i];
+        if (cherry_table_at[i] >= 0) {
+            const Op& g = ctx->ops[i + 1];
+            if (triple_table_at[i] >= 0) {
+                const Op& g2 = ctx->ops[i + 2];
+                if (g2.kind == OP_GEMM_LEAF && i + 3 < ctx->ops.size() && is_gemm(ctx->ops[i + 3])) {
+                    const Op& g3 = ctx->ops[i + 3];  // the edge above the node that joins the 3-leaf subtree and the leaf g2.b
+                    const int ti = ctx->n_tab2 + ctx->n_tab3 + (int)quads.size();
+                    quads.push_back(SubTab{op.a, op.b, g2.b, g3.a, triple_table_at[i], 0, 0});
+                    ctx->ops_t4.push_back(table_op(g3, ti, op.a, op.b, g.b, g2.b));
+                    if (g3.kind == OP_GEMM_LEAF) ctx->items_t4.push_back({ITEM_LEAF, g3.b});
+                    i += 3;
+                    continue;
+                }
+                ctx->ops_t4.push_back(table_op(g2, triple_table_at[i], op.a, op.b, g.b, -1));
+                if (g2.kind == OP_GEMM_LEAF) ctx->items_t4.push_back({ITEM_LEAF, g2.b});
+                i += 2;
+                continue;
+            }
+            ctx->ops_t4.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1, -1));
+            if (g.kind == OP_GEMM_LEAF) ctx->items_t4.push_back({ITEM_LEAF, g.b});
+            i++;
+            continue;
+        }
+        ctx->ops_t4.push_back(op);
+        plain_items(op, ctx->items_t4);
+    }
+    ctx->n_tab4 = (int)quads.size();
     ctx->subtabs.insert(ctx->subtabs.end(), triples.begin(), triples.end());
+    ctx->subtabs.insert(ctx->subtabs.end(), quads.begin(), quads.end());
     std::vector<long long> tab_off(ctx->subtabs.size());
     for (size_t k = 0; k < ctx->subtabs.size(); k++) {
-        tab_off[k] = (int)k < ctx->n_tab2 ? (long long)k * CHERRY_TABLE : (long long)ctx->n_tab2 * CHERRY_TABLE + (long long)(k - ctx->n_tab2) * TRIPLE_TABLE;
+        const long long k2 = std::min<long long>(k, ctx->n_tab2), k3 = std::min<long long>(std::max<long long>((long long)k - ctx->n_tab2, 0), ctx->n_tab3),
+                        k4 = std::max<long long>((long long)k - ctx->n_tab2 - ctx->n_tab3, 0);
+        tab_off[k] = k2 * CHERRY_TABLE + k3 * TRIPLE_TABLE + k4 * QUAD_TABLE;
         ctx->subtabs[k].off = tab_off[k];
     }
-    if (n_leaves > 0xffff) { ctx->n_tab2 = ctx->n_tab3 = 0; }  // leaf ids are packed into 16 bits
+    if (n_leaves > 0xfffe) { ctx->n_tab2 = ctx->n_tab3 = ctx->n_tab4 = 0; }  // leaf ids are packed into 16 bits, 0xffff = none
     CU(cudaStreamSynchronize(ctx->stream));
     for (void** q : {(void**)&ctx->d_branch_len, (void**)&ctx->d_ops, (void**)&ctx->d_items, (void**)&ctx->d_ops_t, (void**)&ctx->d_items_t,
-                     (void**)&ctx->d_ops_t3, (void**)&ctx->d_items_t3, (void**)&ctx->d_subtabs, (void**)&ctx->d_tab_off}) {
+                     (void**)&ctx->d_ops_t3, (void**)&ctx->d_items_t3, (void**)&ctx->d_ops_t4, (void**)&ctx->d_items_t4, (void**)&ctx->d_subtabs,
+                     (void**)&ctx->d_tab_off}) {
         if (*q) CU(cudaFree(*q));
         *q = nullptr;
     }
@@ -687,6 +738,8 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
     CU(upload((void**)&ctx->d_items_t, ctx->items_t.data(), sizeof(Item) * ctx->items_t.size()));
     CU(upload((void**)&ctx->d_ops_t3, ctx->ops_t3.data(), sizeof(Op) * ctx->ops_t3.size()));
     CU(upload((void**)&ctx->d_items_t3, ctx->items_t3.data(), sizeof(Item) * ctx->items_t3.size()));
+    CU(upload((void**)&ctx->d_ops_t4, ctx->ops_t4.data(), sizeof(Op) * ctx->ops_t4.size()));
+    CU(upload((void**)&ctx->d_items_t4, ctx->items_t4.data(), sizeof(Item) * ctx->items_t4.size()));
     CU(upload((void**)&ctx->d_subtabs, ctx->subtabs.data(), sizeof(SubTab) * ctx->subtabs.size()));
     CU(upload((void**)&ctx->d_tab_off, tab_off.data(), sizeof(long long) * tab_off.size()));
     CU(cudaMalloc(&ctx->d_branch_len, sizeof(double) * (n - 1)));

@@ -37,7 +37,9 @@ enum OpKind : int32_t {
     // leaf c next to it - and the contractions up to and including the edge above that subtree are one lookup,
     //   W2[code_a][code_b][.]         = P_v x (G(a) * G(b))
     //   W3[code_a][code_b][code_c][.] = P_u x (W2[code_a][code_b] * G(c))
-    // Encoding: kind | table << 8, a = leaf a | leaf b << 16, b = leaf c (or -1), c = operand of the usual epilogue
+    //   W4[code_a][code_b][code_c][code_d] = P_w x (W3[code_a][code_b][code_c] * G(d))     (caterpillar of four)
+    // Encoding: kind | table << 8, a = leaf a | leaf b << 16, b = leaf c | leaf d << 16 (0xffff = none), c = operand
+    // of the usual epilogue
     OP_TAB_LEAF = 5,   // cur = W * G(c)
     OP_TAB_PUSH = 6,   // stack[c] = W
     OP_TAB_POP = 7     // cur = W * stack[c]
@@ -49,10 +51,13 @@ constexpr int CHERRY_ROWS = 65 * 65;              // code pairs, 64 = marginalis
 constexpr int CHERRY_TABLE = CHERRY_ROWS * 64;    // doubles per cherry table (2.16 MB)
 constexpr int TRIPLE_ROWS = 65 * 65 * 65;         // code triples
 constexpr long long TRIPLE_TABLE = (long long)TRIPLE_ROWS * 64;  // doubles per 3-leaf table (140.6 MB)
-struct SubTab {          // one memoised subtree
-    int32_t la, lb, lc;  // its leaves (lc = -1: a cherry)
-    int32_t edge;        // the node whose upward edge the table includes (the cherry's node v, or its parent u)
-    int32_t src;         // 3-leaf tables: index of the cherry table they are built from
+constexpr int QUAD_ROWS = 65 * 65 * 65 * 65;      // code quadruples
+constexpr long long QUAD_TABLE = (long long)QUAD_ROWS * 64;      // doubles per 4-leaf table (9.14 GB)
+struct SubTab {          // one memoised subtree: a cherry, or the subtree of table `src` plus one more leaf
+    int32_t la, lb;      // cherries: the two leaves
+    int32_t lnew;        // deeper tables: the leaf that joins the subtree of table `src` (-1 for a cherry)
+    int32_t edge;        // the node whose upward edge the table includes
+    int32_t src;         // deeper tables: index of the table they are built from
     int32_t pad;
     long long off;       // offset of the table (doubles) in the P set's table block
 };
@@ -72,7 +77,7 @@ struct PSet {
     const double* prior;     // [64]
     const double* logprior;  // [64]
     const double* cherry;    // subtree tables of this P set (SubTab::off), or null when not built
-    long long tab_level;     // 0 none, 2 cherries, 3 cherries and cherry+leaf subtrees
+    long long tab_level;     // 0 none, 2 cherries, 3 + cherry-and-leaf subtrees, 4 + caterpillars of four
 };
 
 // ---- small PTX wrappers ------------------------------------------------------------------------
@@ -899,9 +904,14 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                     };
                     const uint32_t la = op.a & 0xffff, lb = (uint32_t)op.a >> 16;
                     uint32_t row0 = code(la, 0) * 65 + code(lb, 0), row1 = code(la, 8) * 65 + code(lb, 8);
-                    if (op.b >= 0) {
-                        row0 = row0 * 65 + code(op.b, 0);
-                        row1 = row1 * 65 + code(op.b, 8);
+                    const uint32_t lc = op.b & 0xffff, ld = (uint32_t)op.b >> 16;
+                    if (lc != 0xffff) {
+                        row0 = row0 * 65 + code(lc, 0);
+                        row1 = row1 * 65 + code(lc, 8);
+                        if (ld != 0xffff) {
+                            row0 = row0 * 65 + code(ld, 0);
+                            row1 = row1 * 65 + code(ld, 8);
+                        }
                     }
                     const double2* r0 = reinterpret_cast<const double2*>(W + (size_t)row0 * 64);
                     const double2* r1 = reinterpret_cast<const double2*>(W + (size_t)row1 * 64);
@@ -1005,7 +1015,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
 // Subtree tables. For a cherry (leaves a, b under node v) the partial likelihood that leaves the edge above v,
 // W2[code_a][code_b][y] = sum_x P_v[y][x] (G_a[code_a][x] G_b[code_b][x]), depends on the column only through the code
 // pair; if the cherry's sibling is a leaf c (parent u), W3[code_a][code_b][code_c] = P_u x (W2[code_a][code_b] * G_c[code_c])
-// only through the triple. Both are memoised over all 65^2 / 65^3 code tuples with the very instruction sequence of
+// only through the triple, and so on for a further leaf d. They are memoised over all 65^k code tuples with the very instruction sequence of
 // the pruning kernels (same products, same fragment-ordered image, same DMMA accumulation order), 16 tuples per warp as
 // if they were 16 columns, so a lookup is bit-identical to the computation it replaces.
 // =================================================================================================
@@ -1022,7 +1032,7 @@ __global__ void __launch_bounds__(128) subtree_table_kernel(const double* __rest
 #pragma unroll
     for (int T = 0; T < 2; T++) {
         const int q = min(q0 + 8 * T + g, rows - 1);  // padding tuples repeat the last one (never stored)
-        if (tb.lc < 0) {  // cherry: the product of the two leaf messages, as in the pruning kernels
+        if (tb.lnew < 0) {  // cherry: the product of the two leaf messages, as in the pruning kernels
             const double2* ra = reinterpret_cast<const double2*>(tables + (size_t)tb.la * PT_SLOT + (q / 65) * 64 + 2 * t);
             const double2* rb = reinterpret_cast<const double2*>(tables + (size_t)tb.lb * PT_SLOT + (q % 65) * 64 + 2 * t);
 #pragma unroll
@@ -1031,9 +1041,9 @@ __global__ void __launch_bounds__(128) subtree_table_kernel(const double* __rest
                 cur[T][j][0] = u.x * v.x;
                 cur[T][j][1] = u.y * v.y;
             }
-        } else {  // cherry + leaf: the cherry's table row times the leaf message, as in the GEMM_LEAF epilogue
+        } else {  // subtree + leaf: the source table's row times the leaf message, as in the GEMM_LEAF epilogue
             const double2* rw = reinterpret_cast<const double2*>(base + tabs[tb.src].off + (size_t)(q / 65) * 64 + 2 * t);
-            const double2* rc = reinterpret_cast<const double2*>(tables + (size_t)tb.lc * PT_SLOT + (q % 65) * 64 + 2 * t);
+            const double2* rc = reinterpret_cast<const double2*>(tables + (size_t)tb.lnew * PT_SLOT + (q % 65) * 64 + 2 * t);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const double2 w = rw[4 * j], v = rc[4 * j];

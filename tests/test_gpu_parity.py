@@ -160,6 +160,40 @@ def test_both_kernel_forms_match_oracle_and_each_other(params_base, pset):
     ctx.close()
 
 
+@pytest.mark.parametrize("pset", ["7yeast", "29mammals"])
+def test_level4_subtree_tables_bit_identical(params_base, pset):
+    """Level 4 of the subtree tables (a caterpillar of four leaves memoised over the 65^4 code quadruples, 9.1 GB per
+    subtree and P set - forced here; by default only for P sets that score >= 5 M columns and while memory allows):
+    bit-identical to the plain wide form and within 1e-7 dB of the oracle, with gaps and marginalised species."""
+    import phylocsf_b200 as pb
+
+    ps = H.oracle_paramset(params_base, pset)
+    n = ps.tree.n_leaves
+    rng = np.random.default_rng(29)
+    mc, mn = ps.model.coding_model.model(1.0), ps.model.noncoding_model.model(1.0)
+    regs = [o.simulate_columns(mc, 300, rng), o.simulate_columns(mn, 193, rng), o.simulate_columns(mc, 7, rng)]
+    regs[0][::7, :] = rng.integers(0, 65, size=regs[0][::7, :].shape)  # unrelated codes and gaps: rows far from the diagonal
+    regs[1][5, :] = 64
+    lo, eo = H.oracle_fixed(ps, regs)
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    ctx.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_WIDE)
+    out = {}
+    for mode in (1, 4):
+        ctx.option_set(pb.Context.OPT_CHERRY_TABLES, mode)
+        lpr, elpr, st = ctx.lpr_all([0, 1])
+        out[mode] = (lpr.copy(), elpr.copy(), [ctx.column_terms(m)[0].copy() for m in (0, 1)])
+        finite = np.isfinite(lo)
+        assert np.abs(H.DB * (lpr - lo))[finite].max() < TOL_DB and (np.isfinite(lpr) == finite).all()
+    assert (out[1][0] == out[4][0]).all() or np.array_equal(out[1][0], out[4][0], equal_nan=True)
+    assert np.array_equal(out[1][1], out[4][1], equal_nan=True)
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(out[1][2], out[4][2]))
+    ctx.close()
+
+
 @pytest.mark.parametrize("pset", ["120mammals", "100vertebrates", "29mammals", "7yeast"])
 def test_fixed_other_trees(params_base, pset):
     ps = H.oracle_paramset(params_base, pset)
