@@ -541,3 +541,66 @@ def test_tiny_trees(params_base, species):
         lo, eo = H.oracle_fixed(ps, regs, rho=rho)
         assert np.abs(H.DB * (lpr - lo)).max() < TOL_DB and np.abs(H.DB * (elpr - eo)).max() < TOL_DB
     ctx.close()
+
+
+def _random_tree(rng, n_leaves, shape):
+    """children[2*(i-n)+k] in T numbering (leaves left to right, internal nodes in post-order) and branch lengths."""
+    def build(leaves):
+        if len(leaves) == 1:
+            return leaves[0]
+        if shape == "caterpillar":
+            cut = len(leaves) - 1
+        elif shape == "balanced":
+            cut = len(leaves) // 2
+        else:
+            cut = int(rng.integers(1, len(leaves)))
+        return (build(leaves[:cut]), build(leaves[cut:]))
+    nested = build(list(range(n_leaves)))
+    children = []
+    def number(t):
+        if not isinstance(t, tuple):
+            return t
+        l, r = number(t[0]), number(t[1])
+        children.append((l, r))
+        return n_leaves + len(children) - 1
+    root = number(nested)
+    assert root == 2 * n_leaves - 2
+    bl = rng.uniform(0.01, 0.6, size=2 * n_leaves - 2)
+    return np.array(children, dtype=np.int32).reshape(-1), bl
+
+
+@pytest.mark.parametrize("seed,n_leaves,shape", [(1, 5, "caterpillar"), (2, 6, "balanced"), (3, 8, "random"), (4, 9, "random"),
+                                                 (5, 4, "balanced"), (6, 3, "caterpillar"), (7, 11, "random"), (8, 7, "caterpillar")])
+def test_table_programs_on_random_trees(params_base, seed, n_leaves, shape):
+    """The table programs are derived from the plain tree program by pattern (cherry / + leaf / + leaf, then the edge
+    above). Random tree shapes exercise the corners: cherries right under the root, caterpillars that end at the root,
+    balanced trees with no leaf next to a cherry. Every table level must reproduce the narrow form bit for bit."""
+    import phylocsf_b200 as pb
+
+    ps = H.oracle_paramset(params_base, "12flies")  # rate matrices only; the tree is replaced
+    rng = np.random.default_rng(seed)
+    children, bl = _random_tree(rng, n_leaves, shape)
+    ctx = pb.Context(0)
+    ctx.tree_set(n_leaves, children, bl)
+    H.push_qdiag(ctx, 0, ps.model.coding_model.q)
+    H.push_qdiag(ctx, 1, ps.model.noncoding_model.q)
+    ctx.pt_build(0, [1.0, 0.3])
+    ctx.pt_build(1, [1.0, 0.3])
+    codes = rng.integers(0, 65, size=(450, n_leaves)).astype(np.uint8)
+    codes[:200] = codes[:200, :1]                 # conserved columns
+    codes[200:300, ::2] = codes[200:300, :1]      # half conserved
+    ctx.batch_upload(np.array([0, 193, 200, 450], dtype=np.int64), codes)
+    ref = None
+    for form, mode in ((pb.Context.FORM_NARROW, 1), (pb.Context.FORM_WIDE, 1), (pb.Context.FORM_WIDE, 3), (pb.Context.FORM_WIDE, 2),
+                       (pb.Context.FORM_WIDE, 4)):
+        ctx.option_set(pb.Context.OPT_PRUNE_FORM, form)
+        ctx.option_set(pb.Context.OPT_CHERRY_TABLES, mode)
+        res = [ctx.lpr_all([0, 1], scale_idx=[si, si]) for si in (0, 1)]
+        cols = [ctx.column_terms(m) for m in (0, 1)]
+        key = [r[0] for r in res] + [r[1] for r in res] + [c[0] for c in cols] + [c[1] for c in cols]
+        if ref is None:
+            ref = key
+            assert np.isfinite(res[0][0]).any()
+        else:
+            assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(ref, key)), (form, mode)
+    ctx.close()
