@@ -686,6 +686,9 @@ static_assert(PRUNE_T == 2, "the wide form is written for two 8-column tiles per
 
 __device__ __forceinline__ int w_codes_bytes(int n_leaves) { return (W_TILE_COLS * n_leaves + 15) & ~15; }
 
+#ifndef PCSF_TABLE_PREFETCH
+#define PCSF_TABLE_PREFETCH 1
+#endif
 template <bool RESCALE>
 __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PruneParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -821,6 +824,39 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
             a0 = base + c0 * 512;
             a1 = base + c1 * 512;
         };
+        // rows of this lane's two columns in the table of a table op: the codes of the subtree's leaves, base 65
+        auto table_rows = [&](const Op& op, uint32_t& row0, uint32_t& row1) {
+            auto code = [&](uint32_t leaf, int col8) {
+                const uint32_t c = lds_u8(codes0 + col8 * p.n_leaves + leaf);
+                return c > 64 ? 64u : c;
+            };
+            const uint32_t la = op.a & 0xffff, lb = (uint32_t)op.a >> 16;
+            row0 = code(la, 0) * 65 + code(lb, 0);
+            row1 = code(la, 8) * 65 + code(lb, 8);
+            const uint32_t lc = op.b & 0xffff, ld = (uint32_t)op.b >> 16;
+            if (lc != 0xffff) {
+                row0 = row0 * 65 + code(lc, 0);
+                row1 = row1 * 65 + code(lc, 8);
+                if (ld != 0xffff) {
+                    row0 = row0 * 65 + code(ld, 0);
+                    row1 = row1 * 65 + code(ld, 8);
+                }
+            }
+        };
+#if PCSF_TABLE_PREFETCH
+        // The large tables (3 and 4 leaves) do not stay in L2 as a whole: ask for this tile's rows now, thousands of
+        // clocks before the ops that gather them (lane t of a quad asks for the t-th 128-byte line of the row).
+        if (warp_active)
+            for (int oi = 0; oi < p.n_ops; oi++) {
+                const Op op = ops_s[oi];
+                if ((op.kind & 0xff) < OP_TAB_LEAF || (op.b & 0xffff) == 0xffff) continue;
+                const double* W = reinterpret_cast<const double*>(scratch[2]) + p.tab_off[op.kind >> 8] + 16 * t;
+                uint32_t row0, row1;
+                table_rows(op, row0, row1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(W + (size_t)row0 * 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(W + (size_t)row1 * 64));
+            }
+#endif
         auto park = [&](int level) {  // this thread's 256 bytes of stack level `level`
             return p.global_stack + ((size_t)blockIdx.x * p.n_levels + level) * W_LEVEL_BYTES + (size_t)cw * STACK_ENTRY_BYTES + lane * 16;
         };
@@ -898,21 +934,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
                 ekind = (op.kind & 0xff) - OP_TAB_LEAF + OP_GEMM_LEAF;  // LEAF / PUSH / POP epilogue as after a contraction
                 if (warp_active) {
                     const double* W = reinterpret_cast<const double*>(scratch[2]) + p.tab_off[op.kind >> 8] + 2 * t;
-                    auto code = [&](uint32_t leaf, int col8) {
-                        const uint32_t c = lds_u8(codes0 + col8 * p.n_leaves + leaf);
-                        return c > 64 ? 64u : c;
-                    };
-                    const uint32_t la = op.a & 0xffff, lb = (uint32_t)op.a >> 16;
-                    uint32_t row0 = code(la, 0) * 65 + code(lb, 0), row1 = code(la, 8) * 65 + code(lb, 8);
-                    const uint32_t lc = op.b & 0xffff, ld = (uint32_t)op.b >> 16;
-                    if (lc != 0xffff) {
-                        row0 = row0 * 65 + code(lc, 0);
-                        row1 = row1 * 65 + code(lc, 8);
-                        if (ld != 0xffff) {
-                            row0 = row0 * 65 + code(ld, 0);
-                            row1 = row1 * 65 + code(ld, 8);
-                        }
-                    }
+                    uint32_t row0, row1;
+                    table_rows(op, row0, row1);
                     const double2* r0 = reinterpret_cast<const double2*>(W + (size_t)row0 * 64);
                     const double2* r1 = reinterpret_cast<const double2*>(W + (size_t)row1 * 64);
 #pragma unroll
