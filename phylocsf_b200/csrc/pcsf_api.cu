@@ -113,7 +113,7 @@ int reserve(pcsf_ctx* ctx, DevBuf& b, size_t bytes) {
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
+    size_t want = bytes + std::min<size_t>(bytes / 8, (size_t)256 << 20) + 256;  // head room for slowly growing batches, capped
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -376,8 +376,17 @@ int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
     if (m.cherry_level < level || m.cherry.cap < sizeof(double) * table_block_doubles(ctx, level) * m.nscales) {
         CU(cudaStreamSynchronize(ctx->stream));
         std::fill(m.cherry_built.begin(), m.cherry_built.end(), 0);
-        m.cherry_level = level;
-        TRY(reserve(ctx, m.cherry, sizeof(double) * table_block_doubles(ctx, level) * m.nscales));
+        // the memory check above is only a snapshot (another scoring context of the process may allocate at the same
+        // moment): when the allocation fails after all, settle for the level below instead of failing the call
+        for (;;) {
+            m.cherry_level = level;
+            const int rc = reserve(ctx, m.cherry, sizeof(double) * table_block_doubles(ctx, level) * m.nscales);
+            if (rc == PCSF_OK) break;
+            m.cherry_level = 0;
+            if (rc != PCSF_ERR_NOMEM || level <= 2) return level <= 2 && rc == PCSF_ERR_NOMEM ? PCSF_OK : rc;  // no tables at all is fine too
+            level--;
+            if (level == 3 && ctx->n_tab3 == 0) level = 2;
+        }
     }
     const double* tables = (const double*)m.tables.p + (size_t)scale * ctx->n_branches * PT_SLOT;
     double* base = (double*)m.cherry.p + (size_t)scale * table_block_doubles(ctx, m.cherry_level);
