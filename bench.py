@@ -176,7 +176,9 @@ def main():
     config = {"workload": "58mammals fixed strategy, 3 frames, %d synthetic alignments x %d codons per GPU" % (args.alignments, N_CODONS),
               "paramset": PSET, "strategy": "fixed", "frames": FRAMES, "alignments_per_gpu": args.alignments,
               "codon_columns_per_gpu_per_step": args.alignments * (3 * N_CODONS // 3 + 2 * ((3 * N_CODONS - 1) // 3)),
-              "l2": "inputs larger than L2 (no flush needed)", "sharding": "alignments by rank, no collective on the data path"}
+              "l2": "inputs larger than L2 (no flush needed)", "sharding": "alignments by rank, no collective on the data path",
+              "subtree_tables": "PCSF_CHERRY_TABLES=%s (0 = by batch size: levels 2-4 for this workload; built once per P set outside the timed region, see setup)"
+                                % os.environ.get("PCSF_CHERRY_TABLES", "0")}
 
     if args.impl == "reference":
         if rank != 0:
