@@ -580,7 +580,7 @@ class Driver {
     // repeated species, ragged rows, a gapped reference - returns false WITHOUT judging it: the caller then
     // runs prepare(), which applies the reference's checks in the reference's order with its messages.
     bool prepare_fast(const std::string& name, const char* data, size_t n, Prepared& p, std::vector<uint8_t>& nt_buf) const {
-        if (opt.orf != AsIs || opt.strategy == STRAT_OMEGA) return false;
+        if (opt.orf != AsIs || opt.strategy == STRAT_OMEGA || no_fast_reader) return false;
         if (opt.bls && !bls_table.usable()) return false;
         if (n == 0 || data[0] != '>') return false;
         struct Seg { const char *b, *e; };
@@ -863,6 +863,7 @@ class Driver {
     std::unordered_map<std::string, int> leaf_index;  // species -> tree leaf
     BlsTable bls_table;
     uint8_t nt_lut[256];                              // alignment character -> staged character, 0 = not allowed
+    const bool no_fast_reader = std::getenv("PCSF_NO_FAST_READER") != nullptr;  // tests: everything through the general reader
     std::vector<std::unique_ptr<DeviceScorer>> dev;
     std::vector<std::future<std::unique_ptr<DeviceScorer>>> dev_init;
     Batch batch;

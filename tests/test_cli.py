@@ -322,3 +322,59 @@ def test_multi_device_dispatch_keeps_order(params_base, monkeypatch):
     if N.load().pcsf_device_count() >= 2:
         monkeypatch.setenv("PCSF_DEVICES", "all")
         assert run_cli(params_base, "29mammals", files, *flags) == one
+
+
+def test_fast_reader_equals_general_reader_on_random_alignments(params_base, tmp_path):
+    """Differential test without a GPU (--strategy=nop): random alignments in random shapes (wrapped lines, CRLF, lower
+    case, u for t, N and gaps, missing and shuffled species, |comments, a gapped reference, now and then a foreign
+    character or a ragged row) through the fast reader and, with PCSF_NO_FAST_READER, through the general reader: the
+    same lines for every option set, including --bls, --removeRefGaps, --dna, --aa and the abort messages."""
+    import random
+
+    rnd = random.Random(5)
+    species = ["dmel", "dsim", "dsec", "dyak", "dere", "dana", "dpse", "dper", "dwil", "dvir", "dmoj", "dgri"]
+    files = []
+    for k in range(60):
+        L = rnd.choice([3, 4, 30, 31, 32, 90, 200])
+        present = rnd.sample(species, rnd.randint(2, len(species)))
+        ref = "".join(rnd.choice("ACGT") for _ in range(L))
+        rows = []
+        for i, sp in enumerate(present):
+            row = list(ref)
+            for j in range(L):
+                r = rnd.random()
+                if r < 0.08:
+                    row[j] = rnd.choice("ACGT")
+                elif r < 0.12 and (i > 0 or k % 7 == 3):  # k % 7 == 3: a gapped reference now and then
+                    row[j] = rnd.choice("-N")
+            row = "".join(row)
+            if k % 5 == 1:
+                row = row.lower()
+            if k % 6 == 2:
+                row = row.replace("T", "U").replace("t", "u")
+            rows.append(row)
+        if k % 19 == 7:
+            rows[-1] = rows[-1][:-1] + "R"      # foreign character -> abort
+        if k % 23 == 11 and L > 3:
+            rows[-1] = rows[-1][:-1]            # ragged -> abort
+        text = ""
+        for sp, row in zip(present, rows):
+            hdr = ">" + sp + (" | chr2L:%d" % k if k % 4 == 0 else "")
+            body = row if k % 3 else "\n".join(row[i:i + 13] for i in range(0, len(row), 13))
+            text += hdr + "\n" + body + "\n"
+        if k % 8 == 5:
+            text = text.replace("\n", "\r\n")
+        p = tmp_path / ("r%02d.fa" % k)
+        p.write_bytes(text.encode())
+        files.append(str(p))
+    env_general = dict(os.environ, PHYLOCSF_BASE=params_base, PCSF_NO_FAST_READER="1")
+    env_fast = dict(os.environ, PHYLOCSF_BASE=params_base, PCSF_HOST_PROFILE="1")
+    took_fast = 0
+    for flags in (["--frames=6", "--bls", "--dna", "--aa"], ["--frames=3", "--removeRefGaps", "--bls"], ["--allowRefGaps", "--bls", "--allScores", "--frames=3"], []):
+        for f in files:  # one alignment per run: an abort ends a run
+            cmd = [CLI, "12flies", f, "--strategy=nop"] + flags
+            a = subprocess.run(cmd, env=env_fast, capture_output=True, text=True, timeout=60)
+            b = subprocess.run(cmd, env=env_general, capture_output=True, text=True, timeout=60)
+            assert (a.returncode, a.stdout) == (b.returncode, b.stdout), (f, flags, a.stdout, b.stdout)
+            took_fast += "fast reader took 1 alignments" in a.stderr
+    assert took_fast > 100  # the fast reader did take most of the well-formed ones
