@@ -86,6 +86,16 @@ int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
  */
 #define PCSF_OPT_CHERRY_TABLES 3
 int pcsf_option_set(pcsf_ctx *ctx, int option, int64_t value);
+/*
+ * What is actually in effect (no reference analogue; lets tests and bench.py state which kernel program produced a
+ * number instead of re-deriving the library's heuristics). pcsf_table_level: the subtree-table level (0 none, 2, 3, 4)
+ * the P set (model_id, scale_idx) carries right now - it can be lower than requested, because the large levels are
+ * skipped when device memory is short - or a negative PCSF_ERR_* for an unknown model / scale.
+ * pcsf_last_launch_info: the most recent pruning launch of the context: which = 0 kernel form (1 narrow, 2 wide),
+ * 1 table level of the tree program it ran (0, 2, 3, 4), 2 number of tiles, 3 grid size (CTAs).
+ */
+int pcsf_table_level(const pcsf_ctx *ctx, int model_id, int scale_idx);
+int64_t pcsf_last_launch_info(const pcsf_ctx *ctx, int which);
 
 /*
  * Tree shape = T.t (lib/CamlPaml/T.mli:3, T.ml:57-112): leaves are nodes 0..n_leaves-1 in
@@ -131,6 +141,8 @@ int pcsf_batch_upload(pcsf_ctx *ctx, int64_t nregions, const int64_t *region_off
  *   bytes each, at nt + aln_off[a]; bytes are the alignment characters after u->t.
  *   frames = 1, 3 or 6 (AsIs candidate_regions, src/PhyloCSF.ml:198-205). Regions are numbered
  *   alignment-major, then frame (+0,+1,+2,-0,-1,-2).
+ *   Preconditions checked: aln_off[a] >= 0, aln_len[a] >= 0. NOT checkable here: the buffer at nt must
+ *   extend to max_a(aln_off[a] + aln_len[a] * n_leaves) bytes (the _parts form takes explicit sizes and checks).
  */
 int pcsf_batch_upload_alignments(pcsf_ctx *ctx, int64_t nalign, const int64_t *aln_off, const int32_t *aln_len,
                                  const uint8_t *nt, int frames);

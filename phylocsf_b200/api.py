@@ -204,6 +204,19 @@ class Context:
                                                     N.ptr(elpr), N.ptr(st), N.ptr(ne)), ok_numeric=not check)
         return rho, lpr, elpr, st, ne
 
+    def table_level(self, model_id, scale_idx=0):
+        """Subtree-table level (0, 2, 3, 4) the P set carries right now (pcsf_table_level)."""
+        rc = int(self._L.pcsf_table_level(self._h, model_id, scale_idx))
+        if rc < 0:
+            raise PcsfError(rc, "pcsf_table_level: unknown model / scale")
+        return rc
+
+    def last_launch_info(self):
+        """{'form': 'narrow'|'wide', 'table_level', 'tiles', 'grid'} of the most recent pruning launch."""
+        f = int(self._L.pcsf_last_launch_info(self._h, 0))
+        return {"form": {1: "narrow", 2: "wide"}.get(f, "none"), "table_level": int(self._L.pcsf_last_launch_info(self._h, 1)),
+                "tiles": int(self._L.pcsf_last_launch_info(self._h, 2)), "grid": int(self._L.pcsf_last_launch_info(self._h, 3))}
+
     def last_ms(self, which):
         return float(self._L.pcsf_last_ms(self._h, which))
 

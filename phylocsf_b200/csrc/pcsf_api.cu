@@ -90,6 +90,8 @@ struct pcsf_ctx {
     int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 by the number of columns a P set scores, 1 never, 2 always levels 2-3, 3 always cherries only, 4 always levels 2-4
     int wide = -1;  // pruning kernel form: 0 narrow (128-column tiles), 1 wide (192), -1 chosen per launch (PCSF_WIDE overrides)
     int rescale = 0;  // PCSF_OPT_RESCALE
+    int last_form = 0, last_level = 0, last_grid = 0;  // what the most recent pruning launch ran (pcsf_last_launch_info)
+    int64_t last_tiles = 0;
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
     int timeline_cap = 0;
 };
@@ -278,6 +280,10 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         }
         CU(cudaGetLastError());
         ctx->launches++;
+        ctx->last_form = wide ? 2 : 1;
+        ctx->last_level = (int)level;
+        ctx->last_grid = grid;
+        ctx->last_tiles = tiles;
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     return PCSF_OK;
@@ -609,18 +615,21 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
     }
     if (prune_smem_for(n_leaves + 1, 3 * n_leaves, n_leaves) > ctx->prune_smem_optin)
         return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: too many leaves for the pruning kernel's shared memory");
-    ctx->n_leaves = n_leaves;
-    ctx->n_branches = n - 1;
-    ctx->children.assign(children, children + 2 * (n_leaves - 1));
-    ctx->branch_len.assign(branch_len, branch_len + (n - 1));
-    ProgramBuilder pb(n_leaves, ctx->children);
+    // every check comes before the context is touched: a call that fails leaves the previous tree in place
+    const std::vector<int32_t> new_children(children, children + 2 * (n_leaves - 1));
+    ProgramBuilder pb(n_leaves, new_children);
     pb.compute_need();
     pb.emit(n - 1);
     pb.ops.push_back({OP_ROOT, 0, 0, 0});
+    if (pb.max_height > MAX_STACK_LEVELS) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: tree needs more than 16 parked partials");
+    ctx->n_leaves = 0;  // from here to the last upload the context has no tree (check_ready fails if an upload does)
+    for (auto& m : ctx->models) { m.nscales = 0; m.cherry_built.clear(); }  // tables belong to the previous tree
+    ctx->n_branches = n - 1;
+    ctx->children = new_children;
+    ctx->branch_len.assign(branch_len, branch_len + (n - 1));
     ctx->ops = pb.ops;
     ctx->n_gemm = pb.n_gemm;
     ctx->max_levels = pb.max_height;
-    if (ctx->max_levels > MAX_STACK_LEVELS) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: tree needs more than 16 parked partials");
     ctx->items.clear();
     for (const Op& op : ctx->ops) {
         if (op.kind == OP_CHERRY) { ctx->items.push_back({ITEM_LEAF, op.a}); ctx->items.push_back({ITEM_LEAF, op.b}); }
@@ -757,7 +766,8 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
     CU(cudaMemcpy(ctx->d_items, ctx->items.data(), sizeof(Item) * ctx->items.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_branch_len, branch_len, sizeof(double) * (n - 1), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->d_ops, ctx->ops.data(), sizeof(Op) * ctx->ops.size(), cudaMemcpyHostToDevice));
-    for (auto& m : ctx->models) { m.nscales = 0; m.cherry_built.clear(); }  // tables belong to the previous tree
+    ctx->n_leaves = n_leaves;  // committed
+    ctx->nregions = -1;        // a staged batch belonged to the previous tree's leaf set
     return PCSF_OK;
 }
 
@@ -867,6 +877,7 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     int64_t nt_bytes = 0;
     for (int64_t a = 0; a < nalign; a++) {
         if (aln_len[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment length");
+        if (aln_off[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment offset");
         nt_bytes = std::max<int64_t>(nt_bytes, aln_off[a] + (int64_t)aln_len[a] * ctx->n_leaves);
         for (int f = 0; f < frames; f++) {
             const int rem = aln_len[a] - (f % 3);
@@ -875,6 +886,17 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     }
     const int64_t total = roff[nregions];
     if (nt_bytes > have) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload_alignments: an alignment lies outside the nucleotide buffer");
+    if (nparts > 1) {  // an alignment must lie inside one piece (the pieces are copied back to back, so it would still be read correctly, but the contract says so)
+        std::vector<int64_t> ends(nparts);
+        int64_t at = 0;
+        for (int64_t i = 0; i < nparts; i++) ends[i] = (at += part_bytes[i]);
+        for (int64_t a = 0; a < nalign; a++) {
+            const int64_t nb = (int64_t)aln_len[a] * ctx->n_leaves;
+            if (nb == 0) continue;
+            const int64_t i = std::upper_bound(ends.begin(), ends.end(), aln_off[a]) - ends.begin();
+            if (i >= nparts || aln_off[a] + nb > ends[i]) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_upload_alignments_parts: an alignment straddles two pieces");
+        }
+    }
     TRY(reserve(ctx, ctx->d_nt, std::max<int64_t>(nt_bytes, 1)));
     TRY(reserve(ctx, ctx->d_aln_off, sizeof(int64_t) * std::max<int64_t>(nalign, 1)));
     TRY(reserve(ctx, ctx->d_aln_len, sizeof(int32_t) * std::max<int64_t>(nalign, 1)));
@@ -996,6 +1018,7 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
         int64_t cols = 0;
         for (int64_t a = 0; a < nalign; a++) {
             if (aln_len[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment length");
+            if (aln_off[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment offset");
             int64_t c = 0;
             for (int f = 0; f < frames; f++) { const int rem = aln_len[a] - (f % 3); c += rem >= 3 ? rem / 3 : 0; }
             if (cols > 0 && cols + c > chunk_cols) { chunk_begin.push_back(a); cols = 0; }
@@ -1433,6 +1456,24 @@ int pcsf_debug_timeline(pcsf_ctx* ctx, int cap, long long* out) {
     return PCSF_OK;
 }
 #endif
+
+int pcsf_table_level(const pcsf_ctx* ctx, int model_id, int scale_idx) {
+    if (!ctx || model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set) return PCSF_ERR_INVALID_ARG;
+    const Model& m = ctx->models[model_id];
+    if (scale_idx < 0 || scale_idx >= m.nscales) return PCSF_ERR_INVALID_ARG;
+    return scale_idx < (int)m.cherry_built.size() ? (int)m.cherry_built[scale_idx] : 0;
+}
+
+int64_t pcsf_last_launch_info(const pcsf_ctx* ctx, int which) {
+    if (!ctx) return -1;
+    switch (which) {
+        case 0: return ctx->last_form;
+        case 1: return ctx->last_level;
+        case 2: return ctx->last_tiles;
+        case 3: return ctx->last_grid;
+        default: return -1;
+    }
+}
 
 double pcsf_last_ms(const pcsf_ctx* ctx, int which) {
     if (!ctx || which < 0 || which > 5) return -1.0;

@@ -26,7 +26,6 @@ class Model:
 
     def __init__(self, paramset, ctx):
         self.paramset, self.ctx = paramset, ctx
-        self._staged = None
 
     @classmethod
     def make(cls, paramset_prefix, species=None, device=0):
@@ -59,37 +58,43 @@ class Model:
         return out
 
     def _stage(self, leaves):
-        key = id(leaves)
-        if self._staged != key:
-            off = np.zeros(len(leaves) + 1, dtype=np.int64)
-            for i, c in enumerate(leaves):
-                off[i + 1] = off[i] + c.shape[0]
-            codes = np.concatenate(leaves, axis=0) if off[-1] else np.zeros((0, self.paramset.n_leaves), dtype=np.uint8)
-            self.ctx.batch_upload(off, codes)
-            self._staged = key
+        """Upload `leaves` as the context's batch. Always uploads: an identity-keyed cache would go stale when a
+        caller passes a fresh list that happens to reuse the address of a dead one, or mutates a list in place."""
+        off = np.zeros(len(leaves) + 1, dtype=np.int64)
+        for i, c in enumerate(leaves):
+            off[i + 1] = off[i] + c.shape[0]
+        codes = np.concatenate(leaves, axis=0) if off[-1] else np.zeros((0, self.paramset.n_leaves), dtype=np.uint8)
+        self.ctx.batch_upload(off, codes)
 
-    def lpr_leaves(self, which, leaves, t):
-        """-> list of {'lpr_leaves', 'elpr_anc'} for instance `which` (CODING / NONCODING) at tree scale t."""
-        self._stage(leaves)
+    def _lpr_staged(self, which, t):
         self.ctx.pt_build(which, [t])
         lpr, elpr, st = self.ctx.lpr_all([which])
         return [{"lpr_leaves": float(a), "elpr_anc": float(b)} for a, b in zip(lpr[0], elpr[0])]
 
-    def maximize_lpr(self, which, leaves, init=1.0, lo=1e-2, hi=10.0, accuracy=0.01):
-        """-> list of (rho, {'lpr_leaves', 'elpr_anc'})"""
-        self._stage(leaves)
+    def _maximize_staged(self, which, init, lo, hi, accuracy):
         rho, lpr, elpr, st, ne = self.ctx.maximize_lpr(which, init, lo, hi, accuracy)
         return [(float(r), {"lpr_leaves": float(a), "elpr_anc": float(b)}) for r, a, b in zip(rho, lpr, elpr)]
 
+    def lpr_leaves(self, which, leaves, t):
+        """-> list of {'lpr_leaves', 'elpr_anc'} for instance `which` (CODING / NONCODING) at tree scale t."""
+        self._stage(leaves)
+        return self._lpr_staged(which, t)
+
+    def maximize_lpr(self, which, leaves, init=1.0, lo=1e-2, hi=10.0, accuracy=0.01):
+        """-> list of (rho, {'lpr_leaves', 'elpr_anc'})"""
+        self._stage(leaves)
+        return self._maximize_staged(which, init, lo, hi, accuracy)
+
     def score(self, strategy, leaves):
         """strategy 'FixedLik' | 'MaxLik' -> list of {'score', 'anc_comp_score', 'diagnostics'} (decibans)."""
+        self._stage(leaves)  # once for both models
         if strategy == "FixedLik":
-            c = self.lpr_leaves(self.CODING, leaves, 1.0)
-            n = self.lpr_leaves(self.NONCODING, leaves, 1.0)
+            c = self._lpr_staged(self.CODING, 1.0)
+            n = self._lpr_staged(self.NONCODING, 1.0)
             rho = [(1.0, 1.0)] * len(leaves)
         elif strategy == "MaxLik":
-            mc = self.maximize_lpr(self.CODING, leaves)
-            mn = self.maximize_lpr(self.NONCODING, leaves)
+            mc = self._maximize_staged(self.CODING, 1.0, 1e-2, 10.0, 0.01)
+            mn = self._maximize_staged(self.NONCODING, 1.0, 1e-2, 10.0, 0.01)
             c, n = [x[1] for x in mc], [x[1] for x in mn]
             rho = [(a[0], b[0]) for a, b in zip(mc, mn)]
         else:

@@ -44,3 +44,23 @@ def test_aldh2_ex5_in_and_out_of_frame(params_base):
     assert 218.26 < ans[1]["score"] < 218.27
     assert max(range(3), key=lambda f: ans[f]["score"]) == 1
     m.close()
+
+
+def test_fresh_lists_are_never_served_from_a_stale_batch(params_base):
+    """Regression (round-1 advisor finding): back-to-back calls with temporary lists, which CPython may give the
+    same id(), and in-place mutation of a list must each score what was passed."""
+    from phylocsf_b200.model import Model
+
+    m = Model.make(os.path.join(params_base, "PhyloCSF_Parameters", "12flies"))
+    species, rows = _aln("tal-AA.fa")
+    a = m.pleaves(species, rows)
+    b = a[:20].copy()
+    sa = m.score("FixedLik", [a])[0]["score"]
+    sb = m.score("FixedLik", [b])[0]["score"]
+    assert abs(sa - 361.6876) < 1e-3 and abs(sb - sa) > 1.0
+    lst = [a]
+    s1 = m.lpr_leaves(m.CODING, lst, 1.0)[0]["lpr_leaves"]
+    lst[0] = b
+    s2 = m.lpr_leaves(m.CODING, lst, 1.0)[0]["lpr_leaves"]
+    assert s1 != s2 and s2 == m.lpr_leaves(m.CODING, [b], 1.0)[0]["lpr_leaves"]
+    m.close()
