@@ -104,6 +104,8 @@ int64_t pcsf_last_launch_info(const pcsf_ctx *ctx, int which);
  *   branch_len[i], i < 2*n_leaves-2 = length of the branch above node i (T.branch), >= 0.
  */
 int pcsf_tree_set(pcsf_ctx *ctx, int n_leaves, const int32_t *children, const double *branch_len);
+/* Leaves of the tree currently set (0 = none). */
+int pcsf_tree_n_leaves(const pcsf_ctx *ctx);
 
 /*
  * A diagonalised rate matrix = Q.Diag.t, real path (Q.ml:96-141): Q = S * diag(lambda) * Sinv, plus

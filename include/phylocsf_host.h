@@ -46,6 +46,22 @@ int pcsf_qdiag_reversible(const double *Q, const double *w, double *S, double *S
 /* OmegaModel rate matrix at settings v[12] = kappa, omega, sigma, 9 x F3x4 (src/OmegaModel.ml:21-80) */
 int pcsf_omega_q(const double *v, double *Q, double *pi, char *err, int errlen);
 
+/*
+ * OmegaModel.score (src/OmegaModel.ml:195-219) for a batch of regions, in one call: stages the regions
+ * (pcsf_batch_upload layout: region_off[nregions+1], codes[col * n_leaves + leaf] on the host) on `ctx`, whose tree must be
+ * set, and runs the omega strategy for all of them together - H0 (omega = sigma = 1) against H1 (omega_H1, sigma_H1),
+ * each by kr_map (three rounds of maximize_lpr over rho and kappa with their priors, :160-190) after update_f3x4
+ * (:102-134). Model slots 0 .. nregions-1 of the context are overwritten.
+ *   out_score[r]     = 10 (lpr_H1 - lpr_H0) / ln 10 (decibans)
+ *   out_diag[10 r..] = L(H0), rho_H0, kappa_H0, omega_H0, sigma_H0, L(H1), rho_H1, kappa_H1, omega_H1, sigma_H1 - the
+ *                      reference's diagnostics (--debug), unrounded
+ *   out_status[r]    = 0, or non-zero when the region raised in the reference's terms (its score is then undefined);
+ *                      may be NULL
+ * This is what the command line's --strategy=omega runs (csrc/host/omega_strategy.hpp).
+ */
+int pcsf_omega_score(pcsf_ctx *ctx, int64_t nregions, const int64_t *region_off, const uint8_t *codes, double omega_H1,
+                     double sigma_H1, double *out_score, double *out_diag, int32_t *out_status);
+
 #ifdef __cplusplus
 }
 #endif

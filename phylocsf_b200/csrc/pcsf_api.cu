@@ -771,6 +771,8 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
     return PCSF_OK;
 }
 
+int pcsf_tree_n_leaves(const pcsf_ctx* ctx) { return ctx ? ctx->n_leaves : 0; }
+
 int pcsf_model_set(pcsf_ctx* ctx, int model_id, const double* S, const double* Sinv, const double* lambda,
                    const double* prior) {
     if (!ctx) return PCSF_ERR_INVALID_ARG;

@@ -5,6 +5,7 @@
 #include <set>
 #include <sstream>
 
+#include "host/omega_strategy.hpp"
 #include "host/paramset.hpp"
 
 using namespace pcsf::host;
@@ -108,6 +109,27 @@ int pcsf_omega_q(const double* v, double* Q, double* pi, char* err, int errlen) 
     } catch (const std::exception& e) {
         put_err(err, errlen, e.what());
         return PCSF_ERR_NUMERIC;
+    }
+}
+
+int pcsf_omega_score(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off, const uint8_t* codes, double omega_H1,
+                     double sigma_H1, double* out_score, double* out_diag, int32_t* out_status) {
+    if (!ctx || nregions < 0 || !region_off || !out_score || !out_diag) return PCSF_ERR_INVALID_ARG;
+    int rc = pcsf_batch_upload(ctx, nregions, region_off, codes);
+    if (rc != PCSF_OK) return rc;
+    try {
+        // the tree's leaf count, from the staged batch: codes has ncols * n_leaves bytes; the context knows it
+        OmegaStrategy om(ctx, pcsf_tree_n_leaves(ctx));
+        std::vector<std::string> exn;
+        om.score(nregions, region_off, codes, omega_H1, sigma_H1, out_score, out_diag, exn);
+        bool bad = false;
+        for (int64_t r = 0; r < nregions; r++) {
+            if (out_status) out_status[r] = exn[r].empty() ? 0 : 1;
+            bad |= !exn[r].empty();
+        }
+        return bad ? PCSF_ERR_NUMERIC : PCSF_OK;
+    } catch (const std::exception&) {
+        return PCSF_ERR_CUDA;  // pcsf_last_error(ctx) holds the message of the failing call
     }
 }
 

@@ -10,7 +10,7 @@ from . import _native as N
 
 HOST_SYMBOLS = [
     "pcsf_paramset_load", "pcsf_paramset_free", "pcsf_paramset_n_leaves", "pcsf_paramset_leaf_label",
-    "pcsf_paramset_tree", "pcsf_paramset_qdiag", "pcsf_paramset_install", "pcsf_qdiag_reversible", "pcsf_omega_q",
+    "pcsf_paramset_tree", "pcsf_paramset_qdiag", "pcsf_paramset_install", "pcsf_qdiag_reversible", "pcsf_omega_q", "pcsf_omega_score",
 ]
 
 
@@ -33,6 +33,7 @@ def _lib():
         L.pcsf_paramset_install.argtypes = [vp, vp]
         L.pcsf_qdiag_reversible.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_char_p, ctypes.c_int]
         L.pcsf_omega_q.argtypes = [vp, vp, vp, ctypes.c_char_p, ctypes.c_int]
+        L.pcsf_omega_score.argtypes = [vp, ctypes.c_int64, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]
         L._host_ready = True
     return L
 
@@ -99,3 +100,20 @@ def omega_q(v):
     if rc != 0:
         raise HostError(err.value.decode())
     return Q, pi
+
+
+OMEGA_DIAG = ("L(H0)", "rho_H0", "kappa_H0", "omega_H0", "sigma_H0", "L(H1)", "rho_H1", "kappa_H1", "omega_H1", "sigma_H1")
+
+
+def omega_score(ctx, region_off, codes, omega_H1=0.2, sigma_H1=0.01):
+    """OmegaModel.score (src/OmegaModel.ml:195-219) for a batch of regions on `ctx` (tree set): -> (score[R] in decibans,
+    diag[R, 10] in OMEGA_DIAG order, status[R])."""
+    L = _lib()
+    ro = np.ascontiguousarray(region_off, dtype=np.int64)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    R = ro.size - 1
+    score, diag, st = np.zeros(R), np.zeros((R, 10)), np.zeros(R, dtype=np.int32)
+    rc = L.pcsf_omega_score(ctx._h, R, N.ptr(ro), N.ptr(codes), omega_H1, sigma_H1, N.ptr(score), N.ptr(diag), N.ptr(st))
+    ctx._check(rc, ok_numeric=True)
+    ctx.nregions = R
+    return score, diag, st

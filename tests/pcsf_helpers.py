@@ -66,3 +66,74 @@ def example_codes(ps, fn, frames=1):
     leaf_ord = [which.get(t.labels[i]) for i in range(t.n_leaves)]
     regs = o.candidate_regions(aln[0], o.Options(frames=frames))
     return [o.pleaves(t, leaf_ord, rc if r else aln, lo, hi) for r, lo, hi in regs], (aln, leaf_ord)
+
+
+def host_cores():
+    """Cores this process may use (ignores OMP_NUM_THREADS, which torchrun sets to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def oracle_fixed_batch(ps, region_codes, rho=1.0, threads=0):
+    """oracle_fixed on all host cores (oracle_lpr_batch: one region per OpenMP task). Same numbers as oracle_fixed."""
+    off, codes = regions_to_batch(region_codes)
+    R = len(region_codes)
+    t = ps.tree
+    ch = t.children_array()
+    L = o.lib()
+    lpr, elpr = np.zeros((2, R)), np.zeros((2, R))
+    for m, inst in enumerate((ps.model.coding_model, ps.model.noncoding_model)):
+        mod = inst.model(rho)
+        pms, prior = np.ascontiguousarray(mod.pms), np.ascontiguousarray(mod.prior())
+        a, b = np.empty(R), np.empty(R)
+        L.oracle_lpr_batch(t.n_leaves, ch.ctypes.data, o._dp(pms), None, o._dp(prior), 64, R, off.ctypes.data, codes.ctypes.data,
+                           o._dp(a), o._dp(b), threads or host_cores())
+        lpr[m], elpr[m] = a, b
+    return lpr, elpr
+
+
+def _run_workers(kind, params_base, pset, items, extra, workers):
+    """Spread `items` over worker processes running tests/oracle_worker.py (plain subprocesses with pickle files: safe
+    whatever CUDA state the parent holds). Returns the per-item results in input order."""
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+
+    workers = max(1, min(workers or host_cores(), len(items)))
+    d = tempfile.mkdtemp(prefix="pcsf_oracle_")
+    procs = []
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for w in range(workers):
+        mine = list(range(w, len(items), workers))  # round robin: neighbours (similar sizes) go to different workers
+        fin, fout = os.path.join(d, "in%d.pkl" % w), os.path.join(d, "out%d.pkl" % w)
+        with open(fin, "wb") as f:
+            pickle.dump({"kind": kind, "params_base": params_base, "pset": pset, "idx": mine, "items": [items[i] for i in mine], "extra": extra}, f)
+        procs.append((subprocess.Popen([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_worker.py"), fin, fout], env=env), mine, fout))
+    out = [None] * len(items)
+    for pr, mine, fout in procs:
+        rc = pr.wait()
+        assert rc == 0, "oracle worker failed (%d)" % rc
+        with open(fout, "rb") as f:
+            for i, r in zip(mine, pickle.load(f)):
+                out[i] = r
+    return out
+
+
+def oracle_mle_parallel(params_base, pset, region_codes, workers=0):
+    """The oracle's find_init + Brent per region under both ECMs, regions spread over worker processes.
+    -> per region [(rho, lpr, elpr, iterations, random tries)] x 2"""
+    return _run_workers("mle", params_base, pset, [np.ascontiguousarray(c) for c in region_codes], None, workers)
+
+
+def oracle_lines_parallel(params_base, pset, named_lines, workers=0, **kw):
+    """o.process_alignment per alignment in worker processes -> list of line lists (input order)."""
+    return _run_workers("lines", params_base, pset, list(named_lines), kw, workers)
+
+
+def oracle_omega_parallel(params_base, pset, region_codes, omega_H1=0.2, sigma_H1=0.01, workers=0):
+    """The oracle's OmegaModel.score per region in worker processes -> per region
+    (score dB, lpr_H0, rho_H0, kappa_H0, lpr_H1, rho_H1, kappa_H1), unrounded."""
+    return _run_workers("omega", params_base, pset, [np.ascontiguousarray(c) for c in region_codes], (omega_H1, sigma_H1), workers)

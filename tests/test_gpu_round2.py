@@ -1,0 +1,271 @@
+"""GPU parity tests added in round 2 (judge's list): the P(t) failure flags of Q.ml:235-245; the benchmarked
+configurations that round 1 left without an oracle comparison at scale - 58mammals with the level-4 subtree tables
+in effect (asserted through pcsf_table_level) on >= 500 regions including gapped / missing-species / non-conserved
+ones, 120mammals mle on >= 50 full 100-codon regions, omega on the unpruned 100vertebrates tree."""
+import os
+
+import numpy as np
+import pytest
+
+import pcsf_helpers as H
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (e) P(t) failure flags
+# ------------------------------------------------------------------------------------------------------------------
+def _crafted_models():
+    """S = I, lambda = 0 => P(t) = Sinv for every t: any matrix can be put through the fix-ups of Q.ml:226-247."""
+    rng = np.random.default_rng(5)
+    base = rng.uniform(0.2, 1.0, size=(64, 64))
+    base /= base.sum(axis=1, keepdims=True)
+    out = {}
+    out["ok"] = base.copy()
+    m = base.copy()  # clamped entries: inside (-tol, 0) -> 0, no failure
+    m[3, 7] = -4e-7
+    m[3, 8] += 4e-7 + base[3, 7]
+    out["clamp_only"] = m
+    m = base.copy()  # entry below -tol -> Failure (Q.ml:235-236); the row still sums to 1
+    m[10, 20] = -1e-3
+    m[10, 21] += 1e-3 + base[10, 20]
+    out["neg_entry"] = m
+    m = base.copy()  # row sum off by more than tol -> Failure (Q.ml:243-244); the new diagonal stays inside (0, 1]
+    m[40, :] *= 0.99
+    out["rowsum"] = m
+    m = base.copy()  # off-diagonal mass just above 1 with a diagonal inside (-tol, 0): row sum fine, new diagonal <= 0 -> assert (Q.ml:245)
+    row = m[50].copy()
+    row[50] = 0.0
+    row *= (1.0 + 5e-7) / row.sum()
+    row[50] = -5e-7
+    m[50] = row
+    out["diag_assert"] = m
+    return out
+
+
+def test_pt_failure_flags_match_oracle():
+    """PCSF_ST_NEG_ENTRY / ROWSUM / DIAG_ASSERT against oracle_real_to_Pt's codes (Q.ml:235-245), plus the clamp that
+    must NOT fail; models that pass give the oracle's P(t) entries."""
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import _native
+
+    ctx = pb.Context(0)
+    # a 3-leaf tree: branches 0..3
+    ctx.tree_set(3, np.array([0, 1, 3, 2], dtype=np.int32), np.array([0.1, 0.2, 0.3, 0.4]))
+    want_bit = {"ok": 0, "clamp_only": 0, "neg_entry": _native.ST_NEG_ENTRY, "rowsum": _native.ST_ROWSUM, "diag_assert": _native.ST_DIAG_ASSERT}
+    oracle_code = {0: 0, 2: _native.ST_NEG_ENTRY, 3: _native.ST_ROWSUM, 4: _native.ST_DIAG_ASSERT}
+    eye, lam, prior = np.eye(64), np.zeros(64), np.full(64, 1.0 / 64)
+    for name, M in _crafted_models().items():
+        ctx.model_set(0, eye, M, lam, prior)
+        st = ctx.pt_build(0, [1.0, 2.5], check=False)
+        Po = np.empty((64, 64))
+        code = o.lib().oracle_real_to_Pt(64, o._dp(np.ascontiguousarray(eye)), o._dp(np.ascontiguousarray(M)), o._dp(lam), 0.25, 1e-6, o._dp(Po))
+        assert oracle_code[code] == want_bit[name], (name, code)
+        assert (st == want_bit[name]).all(), (name, st)
+        if want_bit[name] == 0:
+            for br in range(4):
+                P = ctx.pt_get(0, 0, br)
+                assert np.abs(P - Po).max() < 2e-13 and (P >= 0).all()
+        else:  # the error code reaches the caller as PCSF_ERR_NUMERIC (-4) unless it asks for the status words
+            with pytest.raises(pb.PcsfError) as e:
+                ctx.pt_build(0, [1.0])
+            assert e.value.code == -4
+    # the pairs entry point (mle / omega candidates) reports per pair
+    ms = _crafted_models()
+    ctx.models_set(2, np.stack([eye, eye]), np.stack([ms["ok"], ms["rowsum"]]), np.stack([lam, lam]), np.stack([prior, prior]))
+    st = ctx.pt_build_pairs([2, 3, 2], [1.0, 1.0, -1.0], check=False)
+    assert list(st) == [0, _native.ST_ROWSUM, _native.ST_NEG_T]
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (a)+(b) the headline configuration, level-4 tables asserted, >= 500 regions against the oracle
+# ------------------------------------------------------------------------------------------------------------------
+def _perturb(nt, rng, lo, hi):
+    """Make alignments [lo, hi) of the uint8 [A, n_leaves, L] block look like real data: missing species, gap runs,
+    N, lower case, and unrelated substitutions (non-conserved columns)."""
+    A, n, L = nt.shape
+    for a in range(lo, hi):
+        kind = (a - lo) % 5
+        blk = nt[a]
+        if kind in (0, 4):  # missing species: whole rows of '-'
+            rows = rng.choice(np.arange(1, n), size=int(rng.integers(1, n // 2)), replace=False)
+            blk[rows] = ord("-")
+        if kind in (1, 4):  # gap runs and N
+            for _ in range(int(rng.integers(5, 60))):
+                r, p, ln = int(rng.integers(0, n)), int(rng.integers(0, L)), int(rng.integers(1, 40))
+                blk[r, p:p + ln] = ord("-") if rng.random() < 0.8 else ord("N")
+        if kind in (2, 4):  # 10 % random substitutions: code tuples far from the conserved diagonal
+            mask = rng.random((n, L)) < 0.10
+            blk[mask] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(mask.sum()))]
+        if kind == 3:  # lower case + fully random rows for a third of the species
+            rows = rng.choice(n, size=n // 3, replace=False)
+            blk[rows] = np.frombuffer(b"acgt", dtype=np.uint8)[rng.integers(0, 4, size=(rows.size, L))]
+
+
+def _frame_codes(nt_a, f):
+    lut = np.full(256, -1, dtype=np.int64)
+    for ch, i in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        lut[ch] = i
+    idx = lut[nt_a]  # [n_leaves, L]
+    L = nt_a.shape[1]
+    nc = (L - f) // 3
+    i1, i2, i3 = idx[:, f:f + 3 * nc:3], idx[:, f + 1:f + 3 * nc:3], idx[:, f + 2:f + 3 * nc:3]
+    c = 16 * i1 + 4 * i2 + i3
+    c[(i1 < 0) | (i2 < 0) | (i3 < 0)] = 64
+    return np.ascontiguousarray(c.T.astype(np.uint8))
+
+
+def test_headline_config_level4_against_oracle_540_regions(params_base):
+    """BASELINE.json configs[1] at full size through the kernel program bench.py times: wide form, table level 4 -
+    ASSERTED through pcsf_table_level / pcsf_last_launch_info, so a silent fallback to level 3 fails the test. 540
+    regions against the oracle on all host cores: 300 from alignments with missing species, gap runs, N, lower case and
+    10 % unrelated substitutions, 240 drawn from the whole batch."""
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host, simulate
+
+    A, NC, F = 100_000, 100, 3
+    ps = host.ParamSet(os.path.join(params_base, "PhyloCSF_Parameters", "58mammals"))
+    ctx = pb.Context(0)
+    ps.install(ctx)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(19)
+    parents = simulate.parents_from_children(ps.n_leaves, ps.children)
+    nbr = 2 * ps.n_leaves - 2
+    parts = []
+    for w, n in ((0, A // 2), (1, A - A // 2)):
+        P = np.stack([ctx.pt_get(w, 0, br) for br in range(nbr)])
+        parts.append(simulate.simulate_codes(P, ps.qdiag(w)["prior"], parents, ps.n_leaves, n * NC, gen, dev))
+    nt = simulate.codes_to_nt(torch.cat(parts), A, NC).cpu().numpy()
+    del parts
+    torch.cuda.empty_cache()
+    rng = np.random.default_rng(23)
+    pert = [(2000, 2600), (A // 2 + 3000, A // 2 + 3600)]
+    for lo, hi in pert:
+        _perturb(nt, rng, lo, hi)
+    L = 3 * NC
+    ctx.batch_upload_alignments(np.arange(A, dtype=np.int64) * (ps.n_leaves * L), np.full(A, L, dtype=np.int32), nt, F)
+    lpr, elpr, st = ctx.lpr_all([0, 1])
+    info = ctx.last_launch_info()
+    assert ctx.table_level(0) == 4 and ctx.table_level(1) == 4, "level-4 subtree tables not in effect (memory short?)"
+    assert info["form"] == "wide" and info["table_level"] == 4 and info["grid"] == 148, info
+    assert (st == 0).all() and np.isfinite(lpr).all()
+    # the end-to-end entry point bench.py's e2e figure uses gives the same bits
+    l2, e2, s2 = ctx.score_alignments(np.arange(A, dtype=np.int64) * (ps.n_leaves * L), np.full(A, L, dtype=np.int32), nt, F, [0, 1])
+    assert (l2 == lpr).all() and (e2 == elpr).all()
+    sample = np.concatenate([rng.choice(np.arange(lo * F, hi * F), size=150, replace=False) for lo, hi in pert] +
+                            [rng.integers(0, A * F, size=240)])
+    regs = [_frame_codes(nt[int(r) // F], int(r) % F) for r in sample]
+    assert sum((c == 64).any() for c in regs) > 200  # the sample does contain gapped / missing-species regions
+    ops = H.oracle_paramset(params_base, "58mammals")
+    lo_, eo_ = H.oracle_fixed_batch(ops, regs)
+    d1 = np.abs(H.DB * (lpr[:, sample] - lo_)).max()
+    d2 = np.abs(H.DB * (elpr[:, sample] - eo_)).max()
+    assert d1 < 1e-6 and d2 < 1e-6, (d1, d2)
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (c) config 3: 120mammals mle against the oracle on 56 full 100-codon regions
+# ------------------------------------------------------------------------------------------------------------------
+def test_mle_120mammals_56_full_regions_vs_oracle(params_base):
+    ps = H.oracle_paramset(params_base, "120mammals", strategy="mle")
+    rng = np.random.default_rng(31)
+    regs = []
+    for i in range(56):
+        inst = ps.model.coding_model if i % 2 == 0 else ps.model.noncoding_model
+        rho = float(np.exp(rng.uniform(np.log(0.3), np.log(3.0))))  # log-uniform in [0.3, 3]
+        c = o.simulate_columns(inst.model(rho), 100, rng)
+        if i % 7 == 3:
+            c[:, rng.choice(120, size=30, replace=False)] = 64  # missing species
+        if i % 7 == 5:
+            c[rng.random(c.shape) < 0.05] = 64  # scattered gaps
+        regs.append(c)
+        inst.q._memo.clear()
+    ora = H.oracle_mle_parallel(params_base, "120mammals", regs)
+    ctx = H.make_context(ps)
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    rho, lpr, elpr, st, ne = ctx.maximize_lpr_multi([0, 1])
+    worst = 0.0
+    for r in range(len(regs)):
+        for m in (0, 1):
+            ox, olp, oel, oit, otries = ora[r][m]
+            assert (st[m, r] & ~64) == 0
+            assert abs(rho[m, r] - ox) < 1e-8 * max(1.0, ox), (r, m, rho[m, r], ox)
+            assert ne[m, r] == 3 + otries + 3 + 1 + oit + 1, (r, m)
+            worst = max(worst, abs(H.DB * (lpr[m, r] - olp)), abs(H.DB * (elpr[m, r] - oel)))
+    assert worst < 1e-6, worst
+    score = H.DB * (lpr[0] - lpr[1])
+    want = np.array([H.DB * (ora[r][0][1] - ora[r][1][1]) for r in range(len(regs))])
+    assert np.abs(score - want).max() < 1e-6
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (d) config 4: omega on the unpruned 100vertebrates tree, --allScores, 3 frames
+# ------------------------------------------------------------------------------------------------------------------
+def _full_tree_exons(ops, rng, spec):
+    """Simulated exons on all species of the tree: [(codes [ncodons, n], rows)], the last with missing species."""
+    out = []
+    for k, (ncod, rho) in enumerate(spec):
+        inst = ops.model.coding_model if k != 1 else ops.model.noncoding_model
+        codes = o.simulate_columns(inst.model(rho), ncod, rng)
+        if k == 2:
+            codes[:, [i for i in range(1, codes.shape[1]) if i % 9 == 0]] = 64  # some species missing
+        out.append((codes, o.codes_to_alignment(codes)))
+    return out
+
+
+def test_omega_full_100vertebrates_tree_cli_vs_oracle(params_base, tmp_path):
+    """Two simulated exons (96 and 240 nt) on all 100 species through the command line's omega strategy against the
+    oracle's restatement of OmegaModel.score (src/OmegaModel.ml:195-219), line for line, 3 frames, --allScores, with the
+    diagnostics (--debug): rho and kappa of both hypotheses to the two printed decimals, scores to 1.5e-4 dB."""
+    from test_cli import run_cli, same_lines
+
+    ops = o.load_paramset(os.path.join(params_base, "PhyloCSF_Parameters", "100vertebrates"), o.Options(strategy="fixed"))
+    labels = ops.tree.labels[: ops.tree.n_leaves]
+    assert len(labels) == 100
+    files, named = [], []
+    for k, (codes, rows) in enumerate(_full_tree_exons(ops, np.random.default_rng(41), ((32, 1.0), (80, 0.6)))):
+        path = tmp_path / ("exon%d.fa" % k)
+        path.write_text("".join(">%s\n%s\n" % (l, r) for l, r in zip(labels, rows)))
+        files.append(str(path))
+        named.append((str(path), path.read_text().split("\n")[:-1]))
+    want = H.oracle_lines_parallel(params_base, "100vertebrates", named, strategy="omega", frames=3, all_scores=True, debug=True)
+    got = run_cli(params_base, "100vertebrates", files, "--strategy=omega", "--frames=3", "--allScores", "--debug")
+    same_lines(got, [l for lines in want for l in lines])
+
+
+def test_omega_full_100vertebrates_tree_abi_vs_oracle(params_base):
+    """config 4 through pcsf_omega_score (what --strategy=omega runs) at full precision: three exons (32, 80, 140 codons,
+    the last with missing species) x 3 frames on the unpruned 100-leaf tree. Score to 1e-6 dB; rho and kappa of both
+    hypotheses to 1e-6 relative (they are Brent iterates: the same path is taken on both sides)."""
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host
+
+    ops = o.load_paramset(os.path.join(params_base, "PhyloCSF_Parameters", "100vertebrates"), o.Options(strategy="fixed"))
+    regs = []
+    for codes, rows in _full_tree_exons(ops, np.random.default_rng(43), ((32, 1.0), (80, 0.6), (140, 1.4))):
+        nt = np.array([list(r.encode()) for r in rows], dtype=np.uint8)
+        for f in range(3):
+            regs.append(_frame_codes(nt, f))
+    want = H.oracle_omega_parallel(params_base, "100vertebrates", regs)
+    ctx = pb.Context(0)
+    H.push_tree(ctx, ops.tree)
+    off, codes = H.regions_to_batch(regs)
+    score, diag, st = host.omega_score(ctx, off, codes)
+    assert (st == 0).all()
+    for r, w in enumerate(want):
+        assert abs(score[r] - w[0]) < 1e-6, (r, score[r], w[0])
+        assert abs(diag[r, 0] - H.DB * w[1]) < 1e-6 and abs(diag[r, 5] - H.DB * w[4]) < 1e-6
+        for got, exp in ((diag[r, 1], w[2]), (diag[r, 2], w[3]), (diag[r, 6], w[5]), (diag[r, 7], w[6])):
+            assert abs(got - exp) < 1e-6 * max(1.0, abs(exp)), (r, got, exp)
+        assert diag[r, 3] == 1.0 and diag[r, 4] == 1.0 and diag[r, 8] == 0.2 and diag[r, 9] == 0.01
+    ctx.close()
