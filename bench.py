@@ -9,15 +9,24 @@ under the shipped 58mammals tree (half from the coding ECM, half from the noncod
 One step = one full pass of the hot path over that batch. Inputs are larger than L2 (1.7 GB of
 leaf codes per pass), so no L2 flush is needed between iterations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--only headline|cfg5|mle|omega]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 value   = device-resident throughput (leaf codes already in HBM), CUDA events, max over ranks
 e2e     = the same pass through the C ABI from pinned HOST buffers (pcsf_score_alignments): H2D of the
           nucleotide rows in chunks overlapped with on-device pleaves, pruning, region reduction, D2H
-roofline= the pruning kernel (wide form, prune_wide_kernel: the one this workload runs) against the FP64 tensor (DMMA) peak
+roofline= the pruning kernel this workload runs (form and table level QUERIED from the library, not re-derived)
+          against the FP64 tensor (DMMA) peak: `achieved` / `frac` count the flop the DMMA pipe EXECUTES;
+          `algorithmic` is SURVEY 8(d)'s figure (all n-2 contractions per column and model), which exceeds the peak
+          when memoised subtree tables serve part of them
 cpu_baseline / --impl reference = the CPU oracle (oracle/, a restatement of the reference's OCaml
-          path; the reference itself needs OCaml+GSL, absent here) on a bounded sample, all host threads
+          path; the reference itself needs OCaml+GSL, absent here) on a bounded sample, all host cores
+          (os.sched_getaffinity - torchrun's OMP_NUM_THREADS=1 is ignored on purpose)
+extra   = the other BASELINE.json configurations, measured in the same run so that they are driver-witnessed:
+          cfg5_strong_scaling (58mammals, fixed, 6 frames, 10 M codon columns in total split over the N ranks: strong
+          scaling, end to end from host buffers, subtree tables rebuilt once inside the timed region),
+          mle_cfg3 (120mammals, mle, 10,000 x 100 codons; N = 1 only), omega_cfg4 (100vertebrates, omega, 1,000 exon-length
+          alignments x 3 frames through pcsf_omega_score; N = 1 only)
 """
 import argparse
 import json
@@ -38,6 +47,15 @@ PSET = "58mammals"
 FLOP_PER_COLUMN = 2 * 56 * 2 * 64 * 64  # 2 ECMs x (n-2) internal edges x 2*64*64 = 917,504
 N_CODONS = 100
 FRAMES = 3
+
+
+def host_cores():
+    """Cores this process may run on. torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use
+    every core the box gives the process, so the affinity mask decides, not that variable."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def dmma_peak_tflops():
@@ -95,9 +113,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def materialize_params():
+def materialize_params(sets):
     from tools import golden_params as gp
-    return gp.materialize(tempfile.mkdtemp(prefix="pcsf_bench_"), sets=[PSET])
+    return gp.materialize(tempfile.mkdtemp(prefix="pcsf_bench_"), sets=sets)
 
 
 def frame_codes_numpy(nt, frames):
@@ -126,14 +144,12 @@ def frame_codes_numpy(nt, frames):
 def cpu_oracle_throughput(nt_sample, base, target_seconds, nthreads=0):
     """Time the CPU oracle (restatement of PhyloLik.ensure_alpha's dense ddot form) on a bounded
     sample, one region per OpenMP task, both ECMs. Returns (columns/s, cores, sample description)."""
-    import ctypes
-
     from oracle import oracle as o
 
     ps = o.load_paramset(os.path.join(base, "PhyloCSF_Parameters", PSET), o.Options(strategy="fixed"))
     t = ps.tree
     L = o.lib()
-    cores = L.oracle_max_threads() if nthreads <= 0 else nthreads
+    cores = host_cores() if nthreads <= 0 else nthreads
     ch = t.children_array()
     models = []
     for inst in (ps.model.coding_model, ps.model.noncoding_model):
@@ -156,75 +172,76 @@ def cpu_oracle_throughput(nt_sample, base, target_seconds, nthreads=0):
     nalign = int(min(nt_sample.shape[0], max(probe, target_seconds * rate / (cols / probe))))
     cols, dt = run(nalign)
     cpu_oracle_throughput.last_seconds = dt
-    return cols / dt, cores, "%d of the workload's alignments (%d codon columns, both ECMs), %.1f s" % (nalign, cols, dt)
+    return cols / dt, cores, "%d of the workload's alignments (%d codon columns, both ECMs), %.1f s on %d threads" % (nalign, cols, dt, cores)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--alignments", type=int, default=100000, help="alignments per GPU (workload default 100000)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+def lookup_edges(ps, level):
+    """How many of the n-2 contractions per column the table program of `level` serves by lookup (mirrors the
+    library's tree-program builder: cherries not under the root; + a leaf next to them; + a further leaf)."""
+    ch = np.asarray(ps.children).reshape(-1, 2)
+    nl = ps.n_leaves
+    root = 2 * nl - 2
+    parent = {int(c): nl + i for i, pair in enumerate(ch) for c in pair}
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "58mammals fixed strategy, 3 frames, %d synthetic alignments x %d codons per GPU" % (args.alignments, N_CODONS),
-              "paramset": PSET, "strategy": "fixed", "frames": FRAMES, "alignments_per_gpu": args.alignments,
-              "codon_columns_per_gpu_per_step": args.alignments * (3 * N_CODONS // 3 + 2 * ((3 * N_CODONS - 1) // 3)),
-              "l2": "inputs larger than L2 (no flush needed)", "sharding": "alignments by rank, no collective on the data path",
-              "subtree_tables": "PCSF_CHERRY_TABLES=%s (0 = by batch size: levels 2-4 for this workload; built once per P set outside the timed region, see setup)"
-                                % os.environ.get("PCSF_CHERRY_TABLES", "0")}
+    def sibling(v):
+        return [int(c) for c in ch[parent[v] - nl] if int(c) != v][0]
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        run_reference(args, config)
-        return
+    cherries = [nl + i for i, pair in enumerate(ch) if (pair < nl).all() and nl + i != root]
+    triples = [v for v in cherries if parent[v] != root and sibling(v) < nl]
+    quads = [parent[v] for v in triples if parent[parent[v]] != root and sibling(parent[v]) < nl]
+    return (len(cherries) if level >= 2 else 0) + (len(triples) if level >= 3 else 0) + (len(quads) if level >= 4 else 0)
 
+
+def simulate_nt(ctx, ps, n_align, n_codons, seed, dev, scales=(1.0,)):
+    """Synthetic alignments simulated under the context's two ECMs at the given tree scales (equal shares, coding
+    first): uint8 [n_align, n_leaves, 3 * n_codons] on the HOST (pinned)."""
     import torch
 
-    import phylocsf_b200 as pb
-    from phylocsf_b200 import host, simulate
+    from phylocsf_b200 import simulate
 
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-
-    base = materialize_params()
-    ps = host.ParamSet(os.path.join(base, "PhyloCSF_Parameters", PSET))
-    ctx = pb.Context(local_rank)
-    ps.install(ctx)
-    ctx.stream_set(torch.cuda.current_stream().cuda_stream)
-    ctx.pt_build(0, [1.0])
-    ctx.pt_build(1, [1.0])
-    nbr = 2 * ps.n_leaves - 2
-
-    # ---- synthetic alignments (not timed) ----
     gen = torch.Generator(device=dev)
-    gen.manual_seed(42 + rank)
+    gen.manual_seed(seed)
     parents = simulate.parents_from_children(ps.n_leaves, ps.children)
-    A = args.alignments
-    halves = [A // 2, A - A // 2]
+    nbr = 2 * ps.n_leaves - 2
+    groups = [(w, si) for w in (0, 1) for si in range(len(scales))]
+    per = [n_align // len(groups) + (1 if g < n_align % len(groups) else 0) for g in range(len(groups))]
     parts = []
     for w in (0, 1):
-        P = np.stack([ctx.pt_get(w, 0, br) for br in range(nbr)])
-        prior = ps.qdiag(w)["prior"]
-        parts.append(simulate.simulate_codes(P, prior, parents, ps.n_leaves, halves[w] * N_CODONS, gen, dev))
+        ctx.pt_build(w, list(scales))
+    for (w, si), n in zip(groups, per):
+        if n == 0:
+            continue
+        P = np.stack([ctx.pt_get(w, si, br) for br in range(nbr)])
+        parts.append(simulate.simulate_codes(P, ps.qdiag(w)["prior"], parents, ps.n_leaves, n * n_codons, gen, dev))
     codes0 = torch.cat(parts, dim=0)
-    nt_dev = simulate.codes_to_nt(codes0, A, N_CODONS)  # [A, n_leaves, 300]
+    nt_dev = simulate.codes_to_nt(codes0, n_align, n_codons)
     del codes0, parts
     nt_host = torch.empty(nt_dev.shape, dtype=torch.uint8, pin_memory=True)
     nt_host.copy_(nt_dev)
     del nt_dev
     torch.cuda.synchronize()
+    return nt_host
+
+
+# ======================================================================================================================
+# headline: configs[1]
+# ======================================================================================================================
+def run_headline(args, env):
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host
+
+    rank, world, local_rank, dev, dist = env["rank"], env["world"], env["local_rank"], env["dev"], env["dist"]
+    base = env["base"]
+    ps = host.ParamSet(os.path.join(base, "PhyloCSF_Parameters", PSET))
+    ctx = pb.Context(local_rank)
+    ps.install(ctx)
+    ctx.stream_set(torch.cuda.current_stream().cuda_stream)
+    A = args.alignments
+    nt_host = simulate_nt(ctx, ps, A, N_CODONS, 42 + rank, dev)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
     Lnt = 3 * N_CODONS
     aln_off = np.arange(A, dtype=np.int64) * (ps.n_leaves * Lnt)
     aln_len = np.full(A, Lnt, dtype=np.int32)
@@ -272,6 +289,8 @@ def main():
     launches = ctx.launch_count - launches0
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    info = ctx.last_launch_info()  # what actually ran: kernel form and table level of the tree program
+    level_models = [ctx.table_level(0), ctx.table_level(1)]
 
     # ---- end to end from pinned host buffers ----
     step_e2e()
@@ -285,6 +304,7 @@ def main():
     barrier()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     ms_e2e = max(e2.elapsed_time(e3), wall_e2e)  # host-side staging between launches counts too
+    info_e2e = ctx.last_launch_info()
 
     # sanity: the scores are finite and the two halves separate (coding half scores higher)
     score = (10.0 / np.log(10.0)) * (outs[0][0] - outs[0][1])
@@ -297,36 +317,31 @@ def main():
         tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(tt[0]), float(tt[1])
+    line = None
     if rank == 0:
         ms_step = ms_total / args.steps
         value = world * total_cols / (ms_step * 1e-3)
         e2e_value = world * total_cols / (ms_e2e / args.steps * 1e-3)
         peak, peak_note = dmma_peak_tflops()
         k_ms = float(np.mean(prune_ms))
-        achieved = FLOP_PER_COLUMN * total_cols / (k_ms * 1e-3) / 1e12
-        # cherry tables: the contraction above every cherry of the tree is served from a memoised table, so the kernel
-        # executes (n-2-cherries) of the (n-2) contractions the algorithmic figure counts
-        ch = np.asarray(ps.children).reshape(-1, 2)
-        nl = ps.n_leaves
-        root = 2 * nl - 2
-        parent = {int(c): nl + i for i, pair in enumerate(ch) for c in pair}
-        cherries = [nl + i for i, pair in enumerate(ch) if (pair < nl).all() and nl + i != root]
-        # a cherry whose sibling is a leaf, under a node that has an edge of its own: one lookup replaces two contractions
-        triples = [v for v in cherries if parent[v] != root and min(int(c) for c in ch[parent[v] - nl] if int(c) != v) < nl]
-        def sibling(v):
-            return [int(c) for c in ch[parent[v] - nl] if int(c) != v][0]
-        # ... and a further leaf next to that (a caterpillar of four)
-        quads = [parent[v] for v in triples if parent[parent[v]] != root and sibling(parent[v]) < nl]
-        mode = os.environ.get("PCSF_CHERRY_TABLES", "0")
-        tabled = mode != "1" and os.environ.get("PCSF_WIDE", "-1") != "0"
-        level = 0 if not tabled else {"2": 3, "3": 2, "4": 4}.get(mode, 4 if total_cols >= 5000000 else 3 if total_cols >= 1000000 else 2 if total_cols >= 50000 else 0)
-        n_lookup_edges = (len(cherries) if level >= 2 else 0) + (len(triples) if level >= 3 else 0) + (len(quads) if level >= 4 else 0)
-        executed_share = (nl - 2 - n_lookup_edges) / (nl - 2)
-        traffic = None  # dram__bytes_read+write of one launch: ncu-measured bytes per codon column x columns
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "prune_kernel_traffic.json")))["dram_bytes_per_codon_column"] * total_cols
-        except Exception:
-            pass
+        algorithmic = FLOP_PER_COLUMN * total_cols / (k_ms * 1e-3) / 1e12
+        level = info["table_level"]
+        n_lookup = lookup_edges(ps, level)
+        executed_share = (ps.n_leaves - 2 - n_lookup) / (ps.n_leaves - 2)
+        achieved = algorithmic * executed_share
+        traffic, traffic_source = None, None
+        for fn in ("r02_prune_wide_tabled_100k_ncu_summary.json", "prune_kernel_traffic.json"):
+            try:
+                j = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                traffic = j["dram_bytes_per_codon_column"] * total_cols
+                traffic_source = "ncu dram__bytes_read.sum + dram__bytes_write.sum per codon column (profiles/%s, %s) x the columns of one launch" % (fn, j.get("workload", "20k-alignment run"))
+                break
+            except Exception:
+                pass
+        kernel = "pcsf::prune_wide_kernel" if info["form"] == "wide" else "pcsf::prune_kernel"
+        config = dict(env["config"])
+        config["kernel_form"] = info["form"]
+        config["table_level"] = level
         line = {
             "metric": "codon_columns_per_sec", "value": value, "unit": "codon-columns/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -334,33 +349,296 @@ def main():
             "config": config,
             "e2e": {"value": e2e_value, "unit": "codon-columns/s", "h2d_bytes_per_step": int(nt_np.nbytes + aln_off.nbytes + aln_len.nbytes),
                     "d2h_bytes_per_step": int(outs[0].nbytes + outs[1].nbytes), "ms_per_step": ms_e2e / args.steps,
+                    "table_level": info_e2e["table_level"], "kernel_form": info_e2e["form"],
                     "path": "pcsf_score_alignments: pinned host nucleotide rows -> chunked H2D overlapped with on-device pleaves + pruning + reduction -> D2H"},
             "gpu_launches": int(launches),
             "setup": setup,
             "clocks": clocks,
-            "roofline": {"kernel": "pcsf::prune_wide_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel_ms": k_ms,
+            "roofline": {"kernel": kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "kernel_ms": k_ms,
+                         "executed_share": executed_share, "table_level": level, "table_level_per_model": level_models,
+                         "lookup_edges": n_lookup, "internal_edges": ps.n_leaves - 2,
+                         "algorithmic": algorithmic, "algorithmic_frac": algorithmic / peak,
                          "flop_per_codon_column": FLOP_PER_COLUMN, "peak_source": peak_note,
-                         "executed": {"share_of_algorithmic_flop": executed_share, "tflops": achieved * executed_share,
-                                      "frac_of_peak": achieved * executed_share / peak,
-                                      "note": "achieved/frac use the algorithmic flop of SURVEY 8(d); with the subtree tables %d of the %d contractions per column are "
-                                              "covered by 512-byte lookups of memoised results (bit-identical), so frac can exceed 1; 'executed' is what the DMMA pipe runs"
-                                              % (n_lookup_edges, nl - 2)}},
+                         "note": "achieved/frac = DMMA flop the kernel executes: (internal_edges - lookup_edges)/internal_edges of SURVEY 8(d)'s algorithmic flop; "
+                                 "the other contractions are 512-byte lookups of memoised, bit-identical results; 'algorithmic' charges all of them"},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_oracle_throughput(nt_np, base, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "codon-columns/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
     ctx.close()
+    del nt_host, out_lpr, out_elpr
+    return line
+
+
+# ======================================================================================================================
+# extra: configs[4] as a strong-scaling job (fixed total split over the ranks)
+# ======================================================================================================================
+def run_cfg5(args, env):
+    """58mammals, fixed, --frames=6, `--cfg5-alignments` contiguous alignments of 5,001 nt = 10 M codon columns IN TOTAL,
+    split over the ranks by phylocsf_b200.shard.shard_bounds; every step is end to end from pinned host buffers. A fresh
+    context, so the subtree-table level is the one a process scoring only this shard gets."""
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host, shard
+
+    rank, world, local_rank, dev, dist = env["rank"], env["world"], env["local_rank"], env["dev"], env["dist"]
+    ps = host.ParamSet(os.path.join(env["base"], "PhyloCSF_Parameters", PSET))
+    A_total, Lnt, F = args.cfg5_alignments, 5001, 6
+    cols_per_aln = 2 * sum((Lnt - f) // 3 for f in range(3))
+    lo, hi = shard.shard_bounds([cols_per_aln] * A_total, world)[rank]
+    A = hi - lo
+    ctx = pb.Context(local_rank)
+    ps.install(ctx)
+    ctx.stream_set(torch.cuda.current_stream().cuda_stream)
+    nt_host = simulate_nt(ctx, ps, max(A, 1), Lnt // 3, 1000 + rank, dev)
+    nt_np = nt_host.numpy()[:A]
+    aln_off = np.arange(A, dtype=np.int64) * (ps.n_leaves * Lnt)
+    aln_len = np.full(A, Lnt, dtype=np.int32)
+    R = A * F
+    out_lpr = torch.empty((2, max(R, 1)), dtype=torch.float64, pin_memory=True)
+    out_elpr = torch.empty((2, max(R, 1)), dtype=torch.float64, pin_memory=True)
+    outs = (out_lpr.numpy(), out_elpr.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if A:  # a rank without alignments (more ranks than alignments) only takes part in the barriers
+            ctx.score_alignments(aln_off, aln_len, nt_np, F, [0, 1], out=outs)
+
+    def timed(fn, n):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+        return ms
+
+    def cold():  # what a fresh process pays once: K1 for both models, the subtree tables, then the pass itself
+        ctx.pt_build(0, [1.0])
+        ctx.pt_build(1, [1.0])
+        step()
+
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    for _ in range(max(args.warmup, 1)):
+        step()
+    steady = timed(step, args.steps) / args.steps
+    cold_ms = timed(cold, 1)
+    info = ctx.last_launch_info() if A else {"form": "none", "table_level": 0}
+    tables_ms = ctx.last_ms(5)
+    total_cols = A_total * cols_per_aln
+    res = None
     if world > 1:
+        lv = torch.tensor([info["table_level"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(lv, op=dist.ReduceOp.MIN)
+        min_level = int(lv[0])
+    else:
+        min_level = info["table_level"]
+    if rank == 0:
+        res = {"workload": "58mammals fixed, 6 frames, %d alignments x %d nt = %d codon columns in total, split over %d rank(s)" % (A_total, Lnt, total_cols, world),
+               "scaling": "strong", "n_gpus": world, "codon_columns_total": total_cols, "codon_columns_per_gpu": A * cols_per_aln,
+               "value": total_cols / (steady * 1e-3), "unit": "codon-columns/s", "ms_per_step": steady,
+               "first_pass_ms_with_pt_build_and_tables": cold_ms, "value_first_pass": total_cols / (cold_ms * 1e-3),
+               "table_level_rank0": info["table_level"], "table_level_min_over_ranks": min_level, "kernel_form": info["form"],
+               "subtree_tables_ms_per_model": tables_ms,
+               "path": "pcsf_score_alignments from pinned host buffers (H2D + pleaves + pruning + reduction + D2H), wall clock with barriers, max over ranks"}
+    ctx.close()
+    return res
+
+
+# ======================================================================================================================
+# extra: configs[2], mle on 120mammals
+# ======================================================================================================================
+def run_mle(args, env):
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host
+
+    pset, N, NCOD = "120mammals", args.mle_alignments, 100
+    dev = env["dev"]
+    base = materialize_params([pset])
+    ps = host.ParamSet(os.path.join(base, "PhyloCSF_Parameters", pset))
+    ctx = pb.Context(env["local_rank"])
+    ps.install(ctx)
+    scales = np.exp(np.linspace(np.log(0.3), np.log(3.0), 8))  # SURVEY 8(d): rho log-uniform in [0.3, 3]
+    nt_host = simulate_nt(ctx, ps, N, NCOD, 4242, dev, scales=scales)
+    nt = nt_host.numpy()
+    aln_off = np.arange(N, dtype=np.int64) * (ps.n_leaves * 3 * NCOD)
+    aln_len = np.full(N, 3 * NCOD, dtype=np.int32)
+    best = None
+    for it in range(2):  # first pass warms up (allocations); second is reported
+        ctx.total_ms(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.batch_upload_alignments(aln_off, aln_len, nt, 1)  # host rows -> device pleaves (frames = 1)
+        rho, lpr, elpr, st, ne = ctx.maximize_lpr_multi([0, 1])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = (dt, ctx.total_ms(), int(ne.sum()), st, rho, lpr)
+    dt, ms, evals, st, rho, lpr = best
+    peak, _ = dmma_peak_tflops()
+    n = ps.n_leaves
+    res = {"workload": "120mammals mle (both ECMs maximised in the same rounds), %d alignments x %d codons, frames=1" % (N, NCOD),
+           "alignments_per_s": N / dt, "seconds": dt, "evaluations_per_alignment_model": evals / (2.0 * N),
+           "codon_column_evaluations_per_s": evals * NCOD / dt, "device_ms": ms,
+           "device_share_of_wall": (ms["prune"] + ms["reduce"] + ms["pt_build"] + ms["subtree_tables"]) / (dt * 1e3),
+           "failed_regions": int(((st[0] | st[1]) & ~64).astype(bool).sum()),
+           "median_rho_coding": float(np.median(rho[0])),
+           "pruning_algorithmic_tflops": evals * NCOD * (n - 2) * 8192 / (ms["prune"] * 1e-3) / 1e12 if ms["prune"] > 0 else None,
+           "dmma_peak_tflops": peak,
+           "path": "pcsf_batch_upload_alignments (host rows) + pcsf_maximize_lpr_multi, wall clock"}
+    res["pruning_algorithmic_frac"] = res["pruning_algorithmic_tflops"] / peak if res["pruning_algorithmic_tflops"] else None
+    ctx.close()
+    return res
+
+
+# ======================================================================================================================
+# extra: configs[3], omega on 100vertebrates
+# ======================================================================================================================
+def run_omega(args, env):
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host
+
+    pset, N = "100vertebrates", args.omega_alignments
+    dev = env["dev"]
+    base = materialize_params([pset])
+    ps = host.ParamSet(os.path.join(base, "PhyloCSF_Parameters", pset))
+    ctx = pb.Context(env["local_rank"])
+    ps.install(ctx)
+    rng = np.random.default_rng(77)
+    # exon-like lengths: log-normal, median 120 nt, clipped to 60..1500 nt, multiples of 3 (SURVEY 8(d) config 4)
+    lens = (np.clip(np.exp(rng.normal(np.log(120.0), 0.7, size=N)), 60, 1500) // 3).astype(np.int64)
+    nt_host = simulate_nt(ctx, ps, 1, int(lens.sum()), 777, dev)  # one long coding/noncoding stretch, cut into exons
+    nt_all = nt_host.numpy()[0]  # [n_leaves, 3 * sum(lens)]
+    lut = np.full(256, -1, dtype=np.int64)
+    for ch, i in zip(b"ACGT", range(4)):
+        lut[ch] = i
+    regs = []
+    pos = 0
+    for L3 in lens:
+        blk = lut[nt_all[:, 3 * pos:3 * (pos + L3)]]
+        pos += L3
+        for f in range(3):
+            nc = (3 * L3 - f) // 3
+            c = 16 * blk[:, f:f + 3 * nc:3] + 4 * blk[:, f + 1:f + 3 * nc:3] + blk[:, f + 2:f + 3 * nc:3]
+            regs.append(np.ascontiguousarray(c.T.astype(np.uint8)))
+    off = np.zeros(len(regs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([r.shape[0] for r in regs])
+    codes = np.concatenate(regs, axis=0)
+    # warm-up on a slice, then the timed pass over everything
+    w = min(len(regs), 90)
+    host.omega_score(ctx, off[: w + 1], codes[: off[w]])
+    ctx.total_ms(reset=True)
+    l0 = ctx.launch_count
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    score, diag, st = host.omega_score(ctx, off, codes)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ms = ctx.total_ms()
+    res = {"workload": "100vertebrates omega, --allScores --frames=3: %d exon-length alignments (median %d nt) = %d regions, %d codon columns"
+                       % (N, int(np.median(lens) * 3), len(regs), int(off[-1])),
+           "alignments_per_s": N / dt, "regions_per_s": len(regs) / dt, "seconds": dt, "device_ms": ms,
+           "device_share_of_wall": (ms["prune"] + ms["reduce"] + ms["pt_build"] + ms["omega_eig"]) / (dt * 1e3),
+           "gpu_launches": ctx.launch_count - l0, "failed_regions": int((st != 0).sum()),
+           "median_score_db": float(np.median(score)), "median_rho_H0": float(np.median(diag[:, 1])), "median_kappa_H0": float(np.median(diag[:, 2])),
+           "path": "pcsf_omega_score (stages the regions, then kr_map for H0 and H1 in batched Brent rounds: K5 + K1 + K2..K4 per round), wall clock"}
+    ctx.close()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--alignments", type=int, default=100000, help="alignments per GPU (workload default 100000)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline only")
+    ap.add_argument("--only", default="", choices=["", "headline", "cfg5", "mle", "omega"], help="run one part only (prints that part's JSON)")
+    ap.add_argument("--cfg5-alignments", type=int, default=1000, help="alignments of 5,001 nt in the strong-scaling job (1000 = 10 M codon columns)")
+    ap.add_argument("--mle-alignments", type=int, default=10000)
+    ap.add_argument("--omega-alignments", type=int, default=1000)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": "58mammals fixed strategy, 3 frames, %d synthetic alignments x %d codons per GPU" % (args.alignments, N_CODONS),
+              "paramset": PSET, "strategy": "fixed", "frames": FRAMES, "alignments_per_gpu": args.alignments,
+              "codon_columns_per_gpu_per_step": args.alignments * (3 * N_CODONS // 3 + 2 * ((3 * N_CODONS - 1) // 3)),
+              "l2": "inputs larger than L2 (no flush needed)", "sharding": "alignments by rank, no collective on the data path",
+              "subtree_tables": "PCSF_CHERRY_TABLES=%s (0 = by batch size; the level in effect is reported as table_level, queried from the library; "
+                                "built once per P set outside the timed region, see setup)" % os.environ.get("PCSF_CHERRY_TABLES", "0")}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        run_reference(args, config)
+        return
+
+    import torch
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    env = {"rank": rank, "world": world, "local_rank": local_rank, "dev": torch.device("cuda", local_rank), "dist": dist,
+           "base": materialize_params([PSET]), "config": config}
+
+    line = None
+    if args.only in ("", "headline"):
+        line = run_headline(args, env)
+    extra = {}
+
+    def guarded(name, fn):
+        try:
+            r = fn(args, env)
+            if r is not None:
+                extra[name] = r
+        except Exception as e:  # an extra must never take the headline line down with it
+            if rank == 0:
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    if not args.no_extra:
+        if args.only in ("", "cfg5"):
+            guarded("cfg5_strong_scaling", run_cfg5)
+        if world == 1 and args.only in ("", "mle"):
+            guarded("mle_cfg3", run_mle)
+        if world == 1 and args.only in ("", "omega"):
+            guarded("omega_cfg4", run_omega)
+    if rank == 0:
+        if line is None:
+            line = {"only": args.only, "n_gpus": world}
+        line["extra"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def run_reference(args, config):
     """The reference's own CPU algorithm (dense per-row ddot pruning) on this box's host cores. The
     OCaml+GSL reference cannot be built in this image, so this is the oracle port ("kind": "port"),
-    all OpenMP threads, each step a bounded sample of the same workload."""
-    base = materialize_params()
+    all cores of the affinity mask (under torchrun too), each step a bounded sample of the same workload."""
+    base = materialize_params([PSET])
     from oracle import oracle as o
 
     ps = o.load_paramset(os.path.join(base, "PhyloCSF_Parameters", PSET), o.Options(strategy="fixed"))
@@ -384,9 +662,10 @@ def run_reference(args, config):
     line = {"impl": "reference", "metric": "codon_columns_per_sec", "value": value, "unit": "codon-columns/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulated under the shipped 58mammals tree and ECMs)",
-            "config": config,
+            "config": config, "cores": cores,
             "cpu_baseline": {"value": value, "unit": "codon-columns/s", "cores": cores, "kind": "port",
-                             "sample": "per step: " + sample + "; OCaml+GSL reference not buildable here, CPU restatement timed instead"},
+                             "sample": "per step: " + sample + " (a bounded sample of the 100,000-alignment workload, same alignment shape); "
+                                       "OCaml+GSL reference not buildable here, CPU restatement (oracle port) timed instead"},
             "e2e": {"value": value, "unit": "codon-columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -235,6 +235,10 @@ int pcsf_maximize_lpr_multi(pcsf_ctx *ctx, int n_models, const int32_t *model_id
  * 3 H2D copies, 4 D2H copies; 5 = the most recent build of subtree tables (PCSF_OPT_CHERRY_TABLES; once per
  * P set). Returns milliseconds, or a negative value if not recorded. */
 double pcsf_last_ms(const pcsf_ctx *ctx, int which);
+/* Device time summed over every call since the context was created or last reset (which < 0 resets and returns 0):
+ * which = 0 pruning (K2+K3), 1 region reduction (K4), 2 P(t) build (K1), 5 subtree tables, 6 omega Q assembly +
+ * diagonalisation (K5). Lets a caller split a whole strategy run (mle, omega: hundreds of launch sequences) by kernel. */
+double pcsf_total_ms(pcsf_ctx *ctx, int which);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t pcsf_launch_count(const pcsf_ctx *ctx);
 

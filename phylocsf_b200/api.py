@@ -220,6 +220,14 @@ class Context:
     def last_ms(self, which):
         return float(self._L.pcsf_last_ms(self._h, which))
 
+    def total_ms(self, reset=False):
+        """Cumulative device time per kernel class since the last reset (pcsf_total_ms)."""
+        names = {0: "prune", 1: "reduce", 2: "pt_build", 5: "subtree_tables", 6: "omega_eig"}
+        out = {v: float(self._L.pcsf_total_ms(self._h, k)) for k, v in names.items()}
+        if reset:
+            self._L.pcsf_total_ms(self._h, -1)
+        return out
+
     @property
     def launch_count(self):
         return int(self._L.pcsf_launch_count(self._h))

@@ -75,6 +75,7 @@ struct pcsf_ctx {
     // timing
     cudaEvent_t ev[12];
     double ms[6] = {-1, -1, -1, -1, -1, -1};  // [5]: the most recent build of subtree tables
+    double ms_total[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cumulative device time per kernel class (pcsf_total_ms); [6] = K5
     int64_t launches = 0;
     int prune_smem_optin = 0;
     int skew_ns = 1500;
@@ -310,8 +311,10 @@ int finish_timing(pcsf_ctx* ctx) {
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
     ctx->ms[0] = t;
+    ctx->ms_total[0] += t;
     CU(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]));
     ctx->ms[1] = t;
+    ctx->ms_total[1] += t;
     return PCSF_OK;
 }
 
@@ -420,6 +423,7 @@ int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]));
     ctx->ms[5] = t;
+    ctx->ms_total[5] += t;
     m.cherry_built[scale] = (char)level;
     return PCSF_OK;
 }
@@ -448,6 +452,7 @@ int pt_build_jobs(pcsf_ctx* ctx, const std::vector<PtJob>& jobs, DevBuf& tables,
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
     ctx->ms[2] = t;
+    ctx->ms_total[2] += t;
     return PCSF_OK;
 }
 
@@ -1217,6 +1222,7 @@ int pcsf_omega_models_set(pcsf_ctx* ctx, int first_id, int n, const double* q_se
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
     ctx->ms[2] = t;
+    ctx->ms_total[6] += t;
     if ((int)ctx->models.size() < first_id + n) ctx->models.resize(first_id + n);
     bool bad = false;
     for (int i = 0; i < n; i++) {
@@ -1480,6 +1486,15 @@ int64_t pcsf_last_launch_info(const pcsf_ctx* ctx, int which) {
 double pcsf_last_ms(const pcsf_ctx* ctx, int which) {
     if (!ctx || which < 0 || which > 5) return -1.0;
     return ctx->ms[which];
+}
+
+double pcsf_total_ms(pcsf_ctx* ctx, int which) {
+    if (!ctx) return -1.0;
+    if (which < 0) {  // reset
+        for (double& v : ctx->ms_total) v = 0.0;
+        return 0.0;
+    }
+    return which < 8 ? ctx->ms_total[which] : -1.0;
 }
 
 int64_t pcsf_launch_count(const pcsf_ctx* ctx) { return ctx ? ctx->launches : 0; }
