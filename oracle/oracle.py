@@ -70,6 +70,8 @@ def lib():
                                        ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, dp, dp, ctypes.c_int]
         L.oracle_lpr_batch.restype = None
         L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_posteriors.argtypes = [ctypes.c_int, ctypes.c_void_p, dp, dp, ctypes.c_int, ctypes.c_void_p, ctypes.c_double, dp, dp]
+        L.oracle_posteriors.restype = ctypes.c_double
         _lib = L
     return _lib
 
@@ -465,6 +467,39 @@ def likelihood_column(model: PhyloModel, codes: Sequence[int]):
     alpha = np.empty((t.n_leaves - 1, k))
     z = lib().oracle_ensure_alpha(t.n_leaves, ch.ctypes.data, _dp(model.pms), _dp(pr), k, c.ctypes.data, _dp(alpha))
     return z, alpha
+
+
+def posteriors_column(n_leaves: int, children: np.ndarray, pms: np.ndarray, prior: np.ndarray, codes: Sequence[int],
+                      weight: float = 1.0, ecounts: Optional[np.ndarray] = None):
+    """PhyloLik.node_posterior for every node and (accumulating into `ecounts` when given) add_branch_posteriors for
+    every branch of one column (PhyloLik.ml:96-180). Returns (z, node_post [2n-1, k])."""
+    k = pms.shape[1]
+    ch = np.ascontiguousarray(children, dtype=np.int32)
+    pms = np.ascontiguousarray(pms, dtype=np.float64)
+    pr = np.ascontiguousarray(prior, dtype=np.float64)
+    c = np.ascontiguousarray(np.array(codes, dtype=np.uint8))
+    post = np.empty((2 * n_leaves - 1, k))
+    if ecounts is not None:
+        assert ecounts.shape == (2 * n_leaves - 2, k, k) and ecounts.flags["C_CONTIGUOUS"] and ecounts.dtype == np.float64
+    z = lib().oracle_posteriors(n_leaves, ch.ctypes.data, _dp(pms), _dp(pr), k, c.ctypes.data, weight, _dp(post),
+                                _dp(ecounts) if ecounts is not None else None)
+    return z, post
+
+
+def posteriors_columns(model: PhyloModel, codes: np.ndarray):
+    """All columns of a region: (z [ncols], node_post [ncols, 2n-1, k], ecounts [2n-2, k, k] summed over the columns in
+    column order with weight 1 - what PhyloEM's E step accumulates)."""
+    t = model.tree
+    k = model.pms.shape[1]
+    ch = t.children_array()
+    pr = model.prior()
+    ecounts = np.zeros((2 * t.n_leaves - 2, k, k))
+    zs, posts = [], []
+    for c in np.ascontiguousarray(codes, dtype=np.uint8):
+        z, post = posteriors_column(t.n_leaves, ch, model.pms, pr, c, 1.0, ecounts)
+        zs.append(z)
+        posts.append(post)
+    return np.array(zs), np.array(posts), ecounts
 
 
 def lpr_columns(model: PhyloModel, codes: np.ndarray):

@@ -195,3 +195,107 @@ int oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/*
+ * Outside algorithm and posteriors  <- lib/CamlPaml/PhyloLik.ml:96-180 (ensure_beta, node_posterior,
+ * add_branch_posteriors), for one column. Parent / sibling come from the children array (T.parent, T.sibling).
+ *   beta: (2*n_leaves-1) x k, row i = beta of node i; beta[root] = prior (PhyloLik.ml:62).
+ *   For i = root-1 downto 0 (PhyloLik.ml:103-119):
+ *     inter[a] = beta_p[a] * ddot(P_s[a,:], alpha_s)        p = parent(i), s = sibling(i)
+ *     beta_i[b] = ddot(inter, P_i[:,b])
+ * Pinned by the reference's own 2-state known answers (lib/CamlPaml/test.ml:8-54, eps 1e-3) in
+ * tests/test_oracle_golden.py.
+ */
+static void ensure_beta(int n_leaves, const int32_t *children, const double *pms, const double *prior, int k,
+                        const double *alpha, const double *leafvec, double *beta, double *inter) {
+    const int n = 2 * n_leaves - 1;
+    int *parent = (int *)malloc(sizeof(int) * n);
+    int *sibling = (int *)malloc(sizeof(int) * n);
+    for (int i = n_leaves; i < n; i++) {
+        const int lc = children[2 * (i - n_leaves)], rc = children[2 * (i - n_leaves) + 1];
+        parent[lc] = parent[rc] = i;
+        sibling[lc] = rc;
+        sibling[rc] = lc;
+    }
+    for (int a = 0; a < k; a++) beta[(size_t)(n - 1) * k + a] = prior[a];
+    for (int i = n - 2; i >= 0; i--) {
+        const int p = parent[i], s = sibling[i];
+        const double *ps = pms + (size_t)i * k * k, *ss = pms + (size_t)s * k * k;
+        const double *bp = beta + (size_t)p * k;
+        const double *xas = s < n_leaves ? leafvec + (size_t)s * k : alpha + (size_t)(s - n_leaves) * k;
+        for (int a = 0; a < k; a++) inter[a] = bp[a] * ddot(k, ss + (size_t)a * k, xas);
+        for (int b = 0; b < k; b++) {
+            double r = 0.;
+            for (int a = 0; a < k; a++) r += inter[a] * ps[(size_t)a * k + b]; /* ddot inter ps_colb */
+            beta[(size_t)i * k + b] = r;
+        }
+    }
+    free(parent);
+    free(sibling);
+}
+
+/*
+ * PhyloLik.node_posterior for every node and PhyloLik.branch_posteriors for every branch of one column.
+ *   node_post: (2*n_leaves-1) x k (may be NULL). z = 0 => zeros (PhyloLik.ml:131-132); leaf => its leaf vector (:133-134).
+ *   ecounts:   (2*n_leaves-2) x k x k, ACCUMULATED with `weight` (add_branch_posteriors, :140-174; may be NULL):
+ *              ecounts[br][a][b] += weight * beta_p[a] * ddot(P_sib[a,:], alpha_sib) * P_br[a][b] * alpha_br[b] / z,
+ *              only for z > 0 and beta_p[a] > 0.
+ * Returns z.
+ */
+double oracle_posteriors(int n_leaves, const int32_t *children, const double *pms, const double *prior, int k,
+                         const uint8_t *codes, double weight, double *node_post, double *ecounts) {
+    const int n = 2 * n_leaves - 1;
+    double *alpha = (double *)malloc(sizeof(double) * (size_t)(n_leaves - 1) * k);
+    double *leafvec = (double *)malloc(sizeof(double) * (size_t)n_leaves * k);
+    double *beta = (double *)malloc(sizeof(double) * (size_t)n * k);
+    double *inter = (double *)malloc(sizeof(double) * k);
+    const double z = ensure_alpha(n_leaves, children, pms, prior, k, codes, alpha, leafvec);
+    ensure_beta(n_leaves, children, pms, prior, k, alpha, leafvec, beta, inter);
+    if (node_post) {
+        for (int i = 0; i < n; i++) {
+            const double *ai = i < n_leaves ? leafvec + (size_t)i * k : alpha + (size_t)(i - n_leaves) * k;
+            for (int x = 0; x < k; x++) {
+                double v;
+                if (z == 0.) v = 0.;
+                else if (i < n_leaves) v = ai[x];
+                else v = ai[x] * beta[(size_t)i * k + x] / z;
+                node_post[(size_t)i * k + x] = v;
+            }
+        }
+    }
+    if (ecounts && z > 0.) {
+        int *parent = (int *)malloc(sizeof(int) * n);
+        int *sibling = (int *)malloc(sizeof(int) * n);
+        for (int i = n_leaves; i < n; i++) {
+            const int lc = children[2 * (i - n_leaves)], rc = children[2 * (i - n_leaves) + 1];
+            parent[lc] = parent[rc] = i;
+            sibling[lc] = rc;
+            sibling[rc] = lc;
+        }
+        for (int br = 0; br < n - 1; br++) {
+            const int p = parent[br], sib = sibling[br];
+            const double *sm = pms + (size_t)br * k * k, *sms = pms + (size_t)sib * k * k;
+            const double *bp = beta + (size_t)p * k;
+            const double *ab = br < n_leaves ? leafvec + (size_t)br * k : alpha + (size_t)(br - n_leaves) * k;
+            const double *xas = sib < n_leaves ? leafvec + (size_t)sib * k : alpha + (size_t)(sib - n_leaves) * k;
+            for (int a = 0; a < k; a++) {
+                const double bpa = bp[a];
+                if (bpa > 0.) {
+                    const double bpa_sibtot = bpa * ddot(k, sms + (size_t)a * k, xas);
+                    double *ea = ecounts + ((size_t)br * k + a) * k;
+                    for (int b = 0; b < k; b++) {
+                        const double pr = bpa_sibtot * sm[(size_t)a * k + b] * ab[b] / z;
+                        ea[b] += weight * pr;
+                    }
+                }
+            }
+        }
+        free(parent);
+        free(sibling);
+    }
+    free(alpha);
+    free(leafvec);
+    free(beta);
+    free(inter);
+    return z;
+}

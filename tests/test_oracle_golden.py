@@ -40,6 +40,26 @@ def test_two_state_pruning(lvs):
     post_root = alpha[1] * prior / z_o  # PhyloLik.ml:137-138 at the root
     np.testing.assert_allclose(post_root, prior * a4 / z, atol=1e-3)
     np.testing.assert_allclose(alpha[0], a3, atol=1e-15)
+    # outside pass: posterior(root) and posterior(internal) exactly as the reference's test writes them (test.ml:35-43)
+    b4 = prior
+    b3 = np.array([(b4[0] * sm0[0, 0] * a[0][0] + b4[0] * sm0[0, 1] * a[0][1]) * sm1[0, 0] + (b4[1] * sm0[1, 0] * a[0][0] + b4[1] * sm0[1, 1] * a[0][1]) * sm1[1, 0],
+                   (b4[0] * sm0[0, 0] * a[0][0] + b4[0] * sm0[0, 1] * a[0][1]) * sm1[0, 1] + (b4[1] * sm0[1, 0] * a[0][0] + b4[1] * sm0[1, 1] * a[0][1]) * sm1[1, 1]])
+    ec = np.zeros((4, 2, 2))
+    z2, post = o.posteriors_column(3, t.children_array(), M.pms, prior, list(lvs), 1.0, ec)
+    assert z2 == z_o
+    np.testing.assert_allclose(post[4], b4 * a4 / z, atol=1e-3)
+    np.testing.assert_allclose(post[3], b3 * a3 / z, atol=1e-3)
+    np.testing.assert_allclose(post[4], b4 * a4 / z, atol=1e-15)
+    np.testing.assert_allclose(post[3], b3 * a3 / z, atol=1e-15)
+    for i in range(3):
+        np.testing.assert_array_equal(post[i], a[i])  # a leaf's posterior is its leaf vector (PhyloLik.ml:133-134)
+    # branch posteriors (PhyloLik.ml:140-180): a joint distribution over (parent state, child state) of every branch
+    # whose marginals are the node posteriors of its two ends
+    for br in range(4):
+        par = 3 if br in (1, 2) else 4
+        assert abs(ec[br].sum() - 1.0) < 1e-12
+        np.testing.assert_allclose(ec[br].sum(axis=1), post[par], atol=1e-12)
+        np.testing.assert_allclose(ec[br].sum(axis=0), post[br], atol=1e-12)
 
 
 # ---------------------------------------------------------------- lib/CamlPaml/test.ml:56-99
