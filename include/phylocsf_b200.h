@@ -213,6 +213,24 @@ int pcsf_lpr_pairs(pcsf_ctx *ctx, int64_t n_evals, const int64_t *eval_pair, con
 int pcsf_column_terms(pcsf_ctx *ctx, int m, double *col_logz, double *col_anc);
 
 /*
+ * K6. Outside algorithm over the staged batch under the P set (model_id, scale_idx): PhyloLik.ensure_beta,
+ * node_posterior and add_branch_posteriors (lib/CamlPaml/PhyloLik.ml:96-180) - the E step of PhyloEM-style training;
+ * the command line's scoring strategies do not need it.
+ *   nodes[n_nodes]: nodes (T numbering: leaves first, root = 2 n_leaves - 2) whose posterior is wanted;
+ *   out_node_post[(q * total_cols + col) * 64 + x] = P(node nodes[q] in state x | column col): alpha_x beta_x / z for an
+ *     internal node, the leaf vector itself for a leaf (one-hot, or all ones when marginalised), all zeros when z = 0
+ *     (PhyloLik.ml:131-138). May be NULL when n_nodes = 0. Mind the size: 512 bytes per (node, column).
+ *   out_ecounts[(br * 64 + a) * 64 + b] (optional) = sum over all columns with z > 0 of
+ *     beta_parent[a] (P_sib alpha_sib)[a] P_br[a][b] alpha_br[b] / z, br = 0 .. 2 n_leaves - 3: branch_posteriors summed over
+ *     the batch with weight 1 (PhyloLik.ml:140-180) - the expected number of a -> b substitutions on branch br.
+ *   out_z[col] (optional) = likelihood of every column (PhyloLik.likelihood).
+ * Sums over columns are formed per CTA and then over CTAs in a fixed order (deterministic); they differ from the
+ * reference's column-by-column accumulation by rounding only.
+ */
+int pcsf_posteriors(pcsf_ctx *ctx, int model_id, int scale_idx, int n_nodes, const int32_t *nodes, double *out_node_post,
+                    double *out_ecounts, double *out_z);
+
+/*
  * Batched PhyloCSFModel.maximize_lpr (src/PhyloCSFModel.ml:84-99): for every region of the batch,
  * Fit.find_init (lib/CamlPaml/Fit.ml:27-48) then GSL Brent on -lpr(rho) until (ub-lb)/x <= accuracy,
  * then the final re-evaluation f(x). Each round builds P(t) for all live candidates (K1) and scores

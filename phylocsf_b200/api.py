@@ -181,6 +181,18 @@ class Context:
         self._check(self._L.pcsf_lpr_pairs(self._h, n, N.ptr(ep), N.ptr(er), N.ptr(lpr), N.ptr(elpr), N.ptr(st)))
         return lpr, elpr, st
 
+    def posteriors(self, model_id, scale_idx=0, nodes=(), ecounts=True, z=True):
+        """Outside algorithm over the staged batch (pcsf_posteriors): -> (node_post [len(nodes), ncols, 64],
+        ecounts [n_branches, 64, 64] or None, z [ncols] or None)."""
+        nd = np.ascontiguousarray(list(nodes), dtype=np.int32)
+        nc, nbr = self.ncols, 2 * self.n_leaves - 2
+        post = np.zeros((nd.size, nc, 64))
+        ec = np.zeros((nbr, 64, 64)) if ecounts else None
+        zz = np.zeros(nc) if z else None
+        self._check(self._L.pcsf_posteriors(self._h, model_id, scale_idx, nd.size, N.ptr(nd) if nd.size else None,
+                                            N.ptr(post) if nd.size else None, N.ptr(ec), N.ptr(zz)))
+        return post, ec, zz
+
     def column_terms(self, m):
         n = self.ncols
         a, b = np.empty(n), np.empty(n)

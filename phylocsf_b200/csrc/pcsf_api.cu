@@ -66,6 +66,7 @@ struct pcsf_ctx {
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
     DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs, d_gexp, d_pair_cherry;
+    DevBuf d_out_tree, d_out_scratch, d_out_gacc, d_out_post, d_out_ecounts, d_out_z, d_out_nodes;  // K6 (pcsf_posteriors)
     // pcsf_score_alignments: double-buffered chunk staging on a second stream
     DevBuf pipe_nt[2], pipe_aln_off[2], pipe_aln_len[2], pipe_codes[2], pipe_roff[2];
     cudaStream_t copy_stream = nullptr;
@@ -554,7 +555,8 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->d_region_off, &ctx->d_codes, &ctx->d_nt, &ctx->d_aln_off, &ctx->d_aln_len, &ctx->d_spans,
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
                       &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
-                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp, &ctx->d_pair_cherry, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
+                      &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp, &ctx->d_pair_cherry, &ctx->d_out_tree, &ctx->d_out_scratch, &ctx->d_out_gacc,
+                      &ctx->d_out_post, &ctx->d_out_ecounts, &ctx->d_out_z, &ctx->d_out_nodes, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
                       &ctx->pipe_aln_off[1], &ctx->pipe_aln_len[0], &ctx->pipe_aln_len[1], &ctx->pipe_codes[0], &ctx->pipe_codes[1],
                       &ctx->pipe_roff[0], &ctx->pipe_roff[1]};
     for (auto* b : bufs) fr(*b);
@@ -1341,6 +1343,86 @@ int pcsf_lpr_pairs(pcsf_ctx* ctx, int64_t n_evals, const int64_t* eval_pair, con
     if (out_status)
         for (int64_t e = 0; e < n_evals; e++)
             out_status[e] = ctx->pair_status[eval_pair[e]] | (std::isfinite(out_lpr[e]) ? 0 : PCSF_ST_NOT_FINITE);
+    return PCSF_OK;
+}
+
+// K6. Outside algorithm over the staged batch (PhyloLik.ml:96-180); see outside_kernel.
+int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, const int32_t* nodes, double* out_node_post,
+                    double* out_ecounts, double* out_z) {
+    TRY(check_ready(ctx, true));
+    TRY(check_model(ctx, model_id, scale_idx));
+    const int nl = ctx->n_leaves, n = 2 * nl - 1, ni = nl - 1, nbr = n - 1;
+    if (n_nodes < 0 || (n_nodes > 0 && (!nodes || !out_node_post))) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_posteriors: bad node list");
+    for (int q = 0; q < n_nodes; q++)
+        if (nodes[q] < 0 || nodes[q] >= n) return fail(ctx, PCSF_ERR_INVALID_ARG, "CamlPaml.PhyloLik.node_posterior: node index out of range");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t total = ctx->total_cols;
+    const Model& m = ctx->models[model_id];
+    if (m.status[scale_idx] != 0) return fail(ctx, PCSF_ERR_NUMERIC, "pcsf_posteriors: the P set failed its checks (see pcsf_pt_build)");
+    std::vector<int32_t> tree(2 * (nl - 1) + 2 * n, -1);  // children | parent | sibling
+    int32_t* par = tree.data() + 2 * (nl - 1);
+    int32_t* sib = par + n;
+    for (int i = nl; i < n; i++) {
+        const int l = ctx->children[2 * (i - nl)], r = ctx->children[2 * (i - nl) + 1];
+        tree[2 * (i - nl)] = l;
+        tree[2 * (i - nl) + 1] = r;
+        par[l] = par[r] = i;
+        sib[l] = r;
+        sib[r] = l;
+    }
+    const int64_t n_tiles = (total + OUT_TC - 1) / OUT_TC;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, ctx->num_sms));
+    TRY(reserve(ctx, ctx->d_out_tree, tree.size() * sizeof(int32_t)));
+    TRY(reserve(ctx, ctx->d_out_scratch, sizeof(double) * (size_t)grid * 3 * ni * OUT_TC * 64));
+    if (out_ecounts) {
+        TRY(reserve(ctx, ctx->d_out_gacc, sizeof(double) * (size_t)grid * nbr * 4096));
+        TRY(reserve(ctx, ctx->d_out_ecounts, sizeof(double) * (size_t)nbr * 4096));
+    }
+    if (n_nodes > 0) {
+        TRY(reserve(ctx, ctx->d_out_post, sizeof(double) * (size_t)n_nodes * std::max<int64_t>(total, 1) * 64));
+        TRY(reserve(ctx, ctx->d_out_nodes, sizeof(int32_t) * n_nodes));
+        CU(cudaMemcpyAsync(ctx->d_out_nodes.p, nodes, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (out_z) TRY(reserve(ctx, ctx->d_out_z, sizeof(double) * std::max<int64_t>(total, 1)));
+    CU(cudaMemcpyAsync(ctx->d_out_tree.p, tree.data(), tree.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    OutsideParams p;
+    memset(&p, 0, sizeof(p));
+    p.tables = (const double*)m.tables.p + (size_t)scale_idx * ctx->n_branches * PT_SLOT;
+    p.prior = m.prior();
+    p.codes = (const uint8_t*)ctx->d_codes.p;
+    p.total_cols = total;
+    p.n_leaves = nl;
+    p.children = (const int32_t*)ctx->d_out_tree.p;
+    p.parent = p.children + 2 * (nl - 1);
+    p.sibling = p.parent + n;
+    p.scratch = (double*)ctx->d_out_scratch.p;
+    p.gacc = out_ecounts ? (double*)ctx->d_out_gacc.p : nullptr;
+    p.n_post = n_nodes;
+    p.post_nodes = (const int32_t*)ctx->d_out_nodes.p;
+    p.post_out = (double*)ctx->d_out_post.p;
+    p.z_out = out_z ? (double*)ctx->d_out_z.p : nullptr;
+    const int smem = (4096 + 2 * OUT_TC * OUT_XS + OUT_TC) * (int)sizeof(double) + r16(OUT_TC * nl);
+    if (smem > ctx->prune_smem_optin) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_posteriors: tree too large for the kernel's shared memory");
+    CU(cudaFuncSetAttribute(outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    outside_kernel<<<grid, OUT_THREADS, smem, ctx->stream>>>(p);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    if (out_ecounts) {
+        outside_reduce_kernel<<<(unsigned)(((size_t)nbr * 4096 + 255) / 256), 256, 0, ctx->stream>>>(
+            (const double*)ctx->d_out_gacc.p, grid, nbr, nl, p.tables, (double*)ctx->d_out_ecounts.p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (out_ecounts) CU(cudaMemcpyAsync(out_ecounts, ctx->d_out_ecounts.p, sizeof(double) * (size_t)nbr * 4096, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_nodes > 0 && total > 0)
+        CU(cudaMemcpyAsync(out_node_post, ctx->d_out_post.p, sizeof(double) * (size_t)n_nodes * total * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_z && total > 0) CU(cudaMemcpyAsync(out_z, ctx->d_out_z.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+    ctx->ms[0] = t;
     return PCSF_OK;
 }
 

@@ -1322,6 +1322,222 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
 }
 
 // =================================================================================================
+// K6: outside algorithm, node posteriors and expected substitution counts
+//     (lib/CamlPaml/PhyloLik.ml:96-180: ensure_beta, node_posterior, add_branch_posteriors)
+// =================================================================================================
+// Not on the scoring path of the command line: this is the E step PhyloEM-style ECM training needs.
+// One CTA walks tiles of 32 codon columns. Per tile, with msg_i = P_i x alpha_i the message of node i to its parent
+// (a leaf's message is a row of its P^T table, as in the pruning kernels):
+//   inside   (i ascending, internal nodes): alpha_i = msg_lc * msg_rc; msg_i kept for the way down
+//   root:    z = alpha_root . prior; beta_root = prior
+//   outside  (i descending, internal nodes below the root): inter = beta_p * msg_sib; beta_i[b] = sum_a inter[a] P_i[a][b]
+//   branch br: G_br[a][b] += sum over the tile's columns with z > 0 of (beta_p[a] msg_sib[a] / z) alpha_br[b];
+//              the expected counts are P_br[a][b] * G_br[a][b] (the P factor does not depend on the column)
+// alpha, msg and beta of the tile live in a per-CTA global scratch block (L2), G_br in a per-CTA accumulator block that
+// outside_reduce_kernel sums over the CTAs in a fixed order: results do not depend on scheduling.
+// Every 64 x 64 product runs on the plain FP64 pipe as Y[c][o] = sum_k X[c][k] L[k][o] with L staged in shared memory in
+// the orientation the product needs (B200's plain-FP64 peak equals its DMMA peak, and this kernel is bound by the L2
+// traffic of its scratch blocks, not by arithmetic).
+constexpr int OUT_TC = 32;          // columns per tile
+constexpr int OUT_THREADS = 256;
+constexpr int OUT_XS = 65;          // padded row stride of the column-major operand tiles
+struct OutsideParams {
+    const double* tables;    // P set: [n_branches][PT_SLOT]
+    const double* prior;
+    const uint8_t* codes;    // [total_cols][n_leaves]
+    int64_t total_cols;
+    int n_leaves;
+    const int32_t* children; // [2 * (n_leaves - 1)]
+    const int32_t* parent;   // [2 n_leaves - 1]
+    const int32_t* sibling;  // [2 n_leaves - 1]
+    double* scratch;         // [grid][3 * n_internal][OUT_TC][64]: alpha | msg | beta of internal nodes
+    double* gacc;            // [grid][n_branches][64][64] or null (no expected counts wanted)
+    int n_post;              // node posteriors wanted for these nodes
+    const int32_t* post_nodes;
+    double* post_out;        // [n_post][total_cols][64]
+    double* z_out;           // [total_cols] or null
+};
+
+__device__ __forceinline__ double out_p_entry(const double* slot, bool leaf, int a, int b) {
+    return leaf ? slot[b * 64 + a] : slot[frag_index(a, b)];  // leaf slots hold P^T, internal ones the fragment-ordered image
+}
+
+// Y[c][o] = sum_k X[c][k] * L[k][o] for the tile's 32 columns; thread -> column tid / 8, outputs 8 (tid % 8) .. + 7
+__device__ __forceinline__ void out_product(const double* __restrict__ X, const double* __restrict__ L, double (&y)[8], int tid) {
+    const int c = tid >> 3, o0 = (tid & 7) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) y[j] = 0.0;
+    const double* x = X + c * OUT_XS;
+#pragma unroll 8
+    for (int k = 0; k < 64; k++) {
+        const double xv = x[k];
+        const double2* l = reinterpret_cast<const double2*>(L + k * 64 + o0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double2 v = l[j];
+            y[2 * j] = fma(xv, v.x, y[2 * j]);
+            y[2 * j + 1] = fma(xv, v.y, y[2 * j + 1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParams p) {
+    extern __shared__ __align__(16) double osm[];
+    double* L = osm;                      // 64 x 64 operand matrix
+    double* X = L + 4096;                 // OUT_TC x OUT_XS
+    double* U = X + OUT_TC * OUT_XS;      // OUT_TC x OUT_XS
+    double* zs = U + OUT_TC * OUT_XS;     // OUT_TC
+    uint8_t* codes_s = reinterpret_cast<uint8_t*>(zs + OUT_TC);  // OUT_TC x n_leaves
+    const int tid = threadIdx.x, nl = p.n_leaves, n = 2 * nl - 1, ni = nl - 1;
+    const int c = tid >> 3, o0 = (tid & 7) * 8;
+    double* sc = p.scratch + (size_t)blockIdx.x * 3 * ni * OUT_TC * 64;
+    auto alpha_at = [&](int node) { return sc + ((size_t)(node - nl) * OUT_TC) * 64; };
+    auto msg_at = [&](int node) { return sc + ((size_t)(ni + node - nl) * OUT_TC) * 64; };
+    auto beta_at = [&](int node) { return sc + ((size_t)(2 * ni + node - nl) * OUT_TC) * 64; };
+    double* gacc = p.gacc ? p.gacc + (size_t)blockIdx.x * (n - 1) * 4096 : nullptr;
+    if (gacc)
+        for (size_t i = tid; i < (size_t)(n - 1) * 4096; i += OUT_THREADS) gacc[i] = 0.0;
+    // message of node `node` for this thread's (column, 8 states): a leaf gathers its P^T row, an internal node reads msg
+    auto load_msg = [&](int node, double (&m)[8]) {
+        if (node < nl) {
+            int code = codes_s[c * nl + node];
+            code = code > 64 ? 64 : code;
+            const double* row = p.tables + (size_t)node * PT_SLOT + code * 64 + o0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) m[j] = row[j];
+        } else {
+            const double* row = msg_at(node) + c * 64 + o0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) m[j] = row[j];
+        }
+    };
+    auto stage_L = [&](int node, bool transposed) {  // L[k][o] = P[o][k] (inside) or P[k][o] (outside)
+        const double* slot = p.tables + (size_t)node * PT_SLOT;
+        const bool leaf = node < nl;
+        for (int i = tid; i < 4096; i += OUT_THREADS) {
+            const int k = i >> 6, o = i & 63;
+            L[i] = transposed ? out_p_entry(slot, leaf, o, k) : out_p_entry(slot, leaf, k, o);
+        }
+    };
+    const int64_t n_tiles = (p.total_cols + OUT_TC - 1) / OUT_TC;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t col0 = tile * OUT_TC;
+        const int ncols = (int)min((int64_t)OUT_TC, p.total_cols - col0);
+        __syncthreads();
+        for (int i = tid; i < OUT_TC * nl; i += OUT_THREADS) codes_s[i] = i < ncols * nl ? p.codes[(size_t)col0 * nl + i] : (uint8_t)64;
+        __syncthreads();
+        // ---------------- inside ----------------
+        for (int i = nl; i < n; i++) {
+            double ml[8], mr[8], a[8];
+            load_msg(p.children[2 * (i - nl)], ml);
+            load_msg(p.children[2 * (i - nl) + 1], mr);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                a[j] = ml[j] * mr[j];
+                alpha_at(i)[c * 64 + o0 + j] = a[j];
+                X[c * OUT_XS + o0 + j] = a[j];
+            }
+            if (i == n - 1) break;
+            stage_L(i, true);
+            __syncthreads();
+            double y[8];
+            out_product(X, L, y, tid);
+#pragma unroll
+            for (int j = 0; j < 8; j++) msg_at(i)[c * 64 + o0 + j] = y[j];
+            __syncthreads();  // msg_i visible to the CTA (global, same-CTA readers), L and X free again
+        }
+        // ---------------- root ----------------
+        __syncthreads();
+        if (tid < OUT_TC) {
+            double z = 0.0;
+            for (int a = 0; a < 64; a++) z += X[tid * OUT_XS + a] * p.prior[a];
+            zs[tid] = z;
+            if (p.z_out && tid < ncols) p.z_out[col0 + tid] = z;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) beta_at(n - 1)[c * 64 + o0 + j] = p.prior[o0 + j];
+        __syncthreads();
+        // ---------------- outside + expected counts, node by node from the top ----------------
+        for (int i = n - 2; i >= 0; i--) {
+            const int par = p.parent[i], sib = p.sibling[i];
+            double ms[8], inter[8];
+            load_msg(sib, ms);
+            const double* bp = beta_at(par) + c * 64 + o0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) inter[j] = bp[j] * ms[j];
+            if (i >= nl) {  // beta_i[b] = sum_a inter[a] P_i[a][b]
+#pragma unroll
+                for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = inter[j];
+                stage_L(i, false);
+                __syncthreads();
+                double y[8];
+                out_product(X, L, y, tid);
+#pragma unroll
+                for (int j = 0; j < 8; j++) beta_at(i)[c * 64 + o0 + j] = y[j];
+                __syncthreads();
+            }
+            if (gacc) {  // G_i[a][b] += sum_c u[c][a] v[c][b], u = inter / z (columns with z > 0), v = alpha_i
+                const double z = zs[c];
+                const bool live = c < ncols && z > 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) U[c * OUT_XS + o0 + j] = live ? inter[j] / z : 0.0;
+                if (i < nl) {
+                    const int code = codes_s[c * nl + i];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = (code >= 64 || code == o0 + j) ? 1.0 : 0.0;
+                } else {
+                    const double* ai = alpha_at(i) + c * 64 + o0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = ai[j];
+                }
+                __syncthreads();
+                const int a = tid >> 2, b0 = (tid & 3) * 16;
+                double g[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) g[j] = 0.0;
+                for (int cc = 0; cc < OUT_TC; cc++) {
+                    const double u = U[cc * OUT_XS + a];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) g[j] = fma(u, X[cc * OUT_XS + b0 + j], g[j]);
+                }
+                double* G = gacc + (size_t)i * 4096 + a * 64 + b0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) G[j] += g[j];
+                __syncthreads();
+            }
+        }
+        // ---------------- node posteriors (PhyloLik.ml:127-138) ----------------
+        for (int q = 0; q < p.n_post; q++) {
+            const int node = p.post_nodes[q];
+            if (c >= ncols) continue;
+            double* out = p.post_out + ((size_t)q * p.total_cols + col0 + c) * 64 + o0;
+            const double z = zs[c];
+            if (node < nl) {
+                const int code = codes_s[c * nl + node];
+#pragma unroll
+                for (int j = 0; j < 8; j++) out[j] = z == 0.0 ? 0.0 : ((code >= 64 || code == o0 + j) ? 1.0 : 0.0);
+            } else {
+                const double* ai = alpha_at(node) + c * 64 + o0;
+                const double* bi = beta_at(node) + c * 64 + o0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) out[j] = z == 0.0 ? 0.0 : ai[j] * bi[j] / z;
+            }
+        }
+    }
+}
+
+// ecounts[br][a][b] = P_br[a][b] * sum over CTAs (ascending) of G[cta][br][a][b]
+__global__ void outside_reduce_kernel(const double* __restrict__ gacc, int n_cta, int n_branches, int n_leaves,
+                                      const double* __restrict__ tables, double* __restrict__ ecounts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_branches * 4096) return;
+    const int br = (int)(i >> 12), a = (int)((i >> 6) & 63), b = (int)(i & 63);
+    double s = 0.0;
+    for (int k = 0; k < n_cta; k++) s += gacc[((size_t)k * n_branches + br) * 4096 + a * 64 + b];
+    ecounts[i] = out_p_entry(tables + (size_t)br * PT_SLOT, br < n_leaves, a, b) * s;
+}
+
+// =================================================================================================
 // K0: pleaves on the device. One thread per (region column, leaf).
 // =================================================================================================
 __device__ __forceinline__ int nt_index(uint8_t c) {
