@@ -192,7 +192,37 @@ def lookup_edges(ps, level):
     return (len(cherries) if level >= 2 else 0) + (len(triples) if level >= 3 else 0) + (len(quads) if level >= 4 else 0)
 
 
-def simulate_nt(ctx, ps, n_align, n_codons, seed, dev, scales=(1.0,)):
+def perturb_nt(nt_dev, gen):
+    """--data realistic: make the simulated block look like real alignments, on the device: 10 % of all nucleotides replaced
+    by random ones (code tuples far from the conserved diagonal), every sixth (alignment, species) row missing, a gap run of
+    3-60 nt in every fourth remaining row."""
+    import torch
+
+    A, n, L = nt_dev.shape
+    dev = nt_dev.device
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    pos = torch.arange(L, device=dev)[None, None, :]
+    for a0 in range(0, A, 8192):  # in slices: the random tensors are several times the size of the block itself
+        blk = nt_dev[a0:a0 + 8192]
+        m = blk.shape[0]
+        sub = torch.rand((m, n, L), device=dev, generator=gen) < 0.10
+        rnd = torch.randint(0, 4, (m, n, L), device=dev, generator=gen, dtype=torch.uint8)
+        blk[sub] = acgt[rnd[sub].long()]
+        del sub, rnd
+        missing = torch.rand((m, n), device=dev, generator=gen) < (1.0 / 6.0)
+        missing[:, 0] = False  # the reference species is always there
+        blk[missing] = ord("-")
+        start = torch.randint(0, L, (m, n), device=dev, generator=gen)
+        length = torch.randint(3, 61, (m, n), device=dev, generator=gen)
+        has = torch.rand((m, n), device=dev, generator=gen) < 0.25
+        has[:, 0] = False
+        gap = has[:, :, None] & (pos >= start[:, :, None]) & (pos < (start + length)[:, :, None])
+        blk[gap] = ord("-")
+        del gap
+    return nt_dev
+
+
+def simulate_nt(ctx, ps, n_align, n_codons, seed, dev, scales=(1.0,), realistic=False):
     """Synthetic alignments simulated under the context's two ECMs at the given tree scales (equal shares, coding
     first): uint8 [n_align, n_leaves, 3 * n_codons] on the HOST (pinned)."""
     import torch
@@ -216,6 +246,8 @@ def simulate_nt(ctx, ps, n_align, n_codons, seed, dev, scales=(1.0,)):
     codes0 = torch.cat(parts, dim=0)
     nt_dev = simulate.codes_to_nt(codes0, n_align, n_codons)
     del codes0, parts
+    if realistic:
+        nt_dev = perturb_nt(nt_dev, gen)
     nt_host = torch.empty(nt_dev.shape, dtype=torch.uint8, pin_memory=True)
     nt_host.copy_(nt_dev)
     del nt_dev
@@ -239,7 +271,7 @@ def run_headline(args, env):
     ps.install(ctx)
     ctx.stream_set(torch.cuda.current_stream().cuda_stream)
     A = args.alignments
-    nt_host = simulate_nt(ctx, ps, A, N_CODONS, 42 + rank, dev)
+    nt_host = simulate_nt(ctx, ps, A, N_CODONS, 42 + rank, dev, realistic=args.data == "realistic")
     ctx.pt_build(0, [1.0])
     ctx.pt_build(1, [1.0])
     Lnt = 3 * N_CODONS
@@ -308,7 +340,7 @@ def run_headline(args, env):
 
     # sanity: the scores are finite and the two halves separate (coding half scores higher)
     score = (10.0 / np.log(10.0)) * (outs[0][0] - outs[0][1])
-    if not os.environ.get("PCSF_BENCH_NO_SANITY"):  # unset except for timing-only kernel ablations (tools/ab.sh)
+    if not os.environ.get("PCSF_BENCH_NO_SANITY") and args.data == "simulated":  # unset except for timing-only kernel ablations (tools/ab.sh)
         assert np.isfinite(score).all()
         f0 = score[0::FRAMES]
         assert f0[: A // 2].mean() > f0[A // 2:].mean()
@@ -345,7 +377,8 @@ def run_headline(args, env):
         line = {
             "metric": "codon_columns_per_sec", "value": value, "unit": "codon-columns/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulated under the shipped 58mammals tree and ECMs, seed 42+rank)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulated under the shipped 58mammals tree and ECMs, seed 42+rank)" +
+                                         (" + 10 % random substitutions, 1/6 of the species rows missing, gap runs (--data realistic)" if args.data == "realistic" else ""),
             "config": config,
             "e2e": {"value": e2e_value, "unit": "codon-columns/s", "h2d_bytes_per_step": int(nt_np.nbytes + aln_off.nbytes + aln_len.nbytes),
                     "d2h_bytes_per_step": int(outs[0].nbytes + outs[1].nbytes), "ms_per_step": ms_e2e / args.steps,
@@ -570,6 +603,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline only")
+    ap.add_argument("--data", default="simulated", choices=["simulated", "realistic"],
+                    help="realistic: the simulated alignments with 10 %% random substitutions, missing species and gap runs (headline only)")
     ap.add_argument("--only", default="", choices=["", "headline", "cfg5", "mle", "omega"], help="run one part only (prints that part's JSON)")
     ap.add_argument("--cfg5-alignments", type=int, default=1000, help="alignments of 5,001 nt in the strong-scaling job (1000 = 10 M codon columns)")
     ap.add_argument("--mle-alignments", type=int, default=10000)
