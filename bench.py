@@ -512,14 +512,15 @@ def run_mle(args, env):
     best = None
     for it in range(2):  # first pass warms up (allocations); second is reported
         ctx.total_ms(reset=True)
+        ctx.counters(reset=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx.batch_upload_alignments(aln_off, aln_len, nt, 1)  # host rows -> device pleaves (frames = 1)
         rho, lpr, elpr, st, ne = ctx.maximize_lpr_multi([0, 1])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        best = (dt, ctx.total_ms(), int(ne.sum()), st, rho, lpr)
-    dt, ms, evals, st, rho, lpr = best
+        best = (dt, ctx.total_ms(), int(ne.sum()), st, rho, lpr, ctx.counters())
+    dt, ms, evals, st, rho, lpr, cnt = best
     peak, _ = dmma_peak_tflops()
     n = ps.n_leaves
     res = {"workload": "120mammals mle (both ECMs maximised in the same rounds), %d alignments x %d codons, frames=1" % (N, NCOD),
@@ -529,9 +530,17 @@ def run_mle(args, env):
            "failed_regions": int(((st[0] | st[1]) & ~64).astype(bool).sum()),
            "median_rho_coding": float(np.median(rho[0])),
            "pruning_algorithmic_tflops": evals * NCOD * (n - 2) * 8192 / (ms["prune"] * 1e-3) / 1e12 if ms["prune"] > 0 else None,
+           "counters": cnt,
+           "pt_build_tflops": cnt["pt_slots"] * 524288.0 / (ms["pt_build"] * 1e-3) / 1e12 if ms["pt_build"] > 0 else None,
+           "dmma_total_tflops": (cnt["pt_slots"] * 524288.0 + evals * NCOD * (n - 2) * 8192.0) / ((ms["pt_build"] + ms["prune"]) * 1e-3) / 1e12,
            "dmma_peak_tflops": peak,
            "path": "pcsf_batch_upload_alignments (host rows) + pcsf_maximize_lpr_multi, wall clock"}
     res["pruning_algorithmic_frac"] = res["pruning_algorithmic_tflops"] / peak if res["pruning_algorithmic_tflops"] else None
+    res["pt_build_frac"] = res["pt_build_tflops"] / peak if res["pt_build_tflops"] else None
+    res["dmma_total_frac"] = res["dmma_total_tflops"] / peak
+    res["note"] = ("K1 (P(t) build) and pruning both run on the DMMA pipe: dmma_total = (524,288 flop x P(t) slots built + 8,192 flop x (n-2) internal edges x "
+                   "codon-column evaluations) / (K1 + pruning device time); pruning_algorithmic counts every evaluation although the rounds whose candidates all "
+                   "regions share use cherry tables")
     ctx.close()
     return res
 
@@ -575,6 +584,7 @@ def run_omega(args, env):
     w = min(len(regs), 90)
     host.omega_score(ctx, off[: w + 1], codes[: off[w]])
     ctx.total_ms(reset=True)
+    ctx.counters(reset=True)
     l0 = ctx.launch_count
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -582,11 +592,19 @@ def run_omega(args, env):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ms = ctx.total_ms()
+    cnt = ctx.counters()
+    peak, _ = dmma_peak_tflops()
+    n = ps.n_leaves
     res = {"workload": "100vertebrates omega, --allScores --frames=3: %d exon-length alignments (median %d nt) = %d regions, %d codon columns"
                        % (N, int(np.median(lens) * 3), len(regs), int(off[-1])),
            "alignments_per_s": N / dt, "regions_per_s": len(regs) / dt, "seconds": dt, "device_ms": ms,
            "device_share_of_wall": (ms["prune"] + ms["reduce"] + ms["pt_build"] + ms["omega_eig"]) / (dt * 1e3),
-           "gpu_launches": ctx.launch_count - l0, "failed_regions": int((st != 0).sum()),
+           "gpu_launches": ctx.launch_count - l0, "failed_regions": int((st != 0).sum()), "counters": cnt,
+           "evaluations_per_region": cnt["column_evaluations"] / max(1, int(off[-1])),
+           "jacobi_sweeps_per_matrix": cnt["eig_sweeps"] / max(1, cnt["eig_matrices"]),
+           "pt_build_tflops": cnt["pt_slots"] * 524288.0 / (ms["pt_build"] * 1e-3) / 1e12 if ms["pt_build"] > 0 else None,
+           "pruning_tflops": cnt["column_evaluations"] * (n - 2) * 8192.0 / (ms["prune"] * 1e-3) / 1e12 if ms["prune"] > 0 else None,
+           "dmma_peak_tflops": peak,
            "median_score_db": float(np.median(score)), "median_rho_H0": float(np.median(diag[:, 1])), "median_kappa_H0": float(np.median(diag[:, 2])),
            "path": "pcsf_omega_score (stages the regions, then kr_map for H0 and H1 in batched Brent rounds: K5 + K1 + K2..K4 per round), wall clock"}
     ctx.close()

@@ -201,6 +201,18 @@ int pcsf_models_set(pcsf_ctx *ctx, int first_id, int n, const double *S, const d
  * status bits: 128 = Q scale non-positive (PhyloModel.ml:99-100), 256 = no zero eigenvalue (Q.ml:168-169).
  */
 int pcsf_omega_models_set(pcsf_ctx *ctx, int first_id, int n, const double *q_settings, int32_t *status);
+/*
+ * The same with warm starts for the diagonalisation. A search over kappa (src/OmegaModel.ml:177-188) diagonalises a
+ * sequence of nearby rate matrices per region; cache_slot[i] >= 0 names a per-region slot (0 .. n_slots-1 of the last
+ * pcsf_omega_cache_reset) that holds the eigenvectors of the region's previous candidate: the Jacobi sweeps then start
+ * from them (2-4 sweeps instead of ~9) and leave the new eigenvectors in the slot. cache_slot[i] < 0, a NULL cache_slot
+ * or an empty slot = cold start. Slots within one call must be distinct. The eigensystem is that of the same matrix to
+ * the same stopping threshold; against a cold start it differs by rounding only.
+ * pcsf_omega_cache_reset empties all slots (call it when a new search begins: bounds the accumulation of rotations).
+ */
+int pcsf_omega_cache_reset(pcsf_ctx *ctx, int64_t n_slots);
+int pcsf_omega_models_set_cached(pcsf_ctx *ctx, int first_id, int n, const double *q_settings, const int64_t *cache_slot,
+                                 int32_t *status);
 /* Read a model slot back (S, Sinv 64x64; lambda, prior 64); any output may be NULL. For tests. */
 int pcsf_model_get(pcsf_ctx *ctx, int model_id, double *S, double *Sinv, double *lambda, double *prior);
 int pcsf_pt_build_pairs(pcsf_ctx *ctx, int64_t npairs, const int32_t *pair_model, const double *pair_scale,
@@ -257,6 +269,10 @@ double pcsf_last_ms(const pcsf_ctx *ctx, int which);
  * which = 0 pruning (K2+K3), 1 region reduction (K4), 2 P(t) build (K1), 5 subtree tables, 6 omega Q assembly +
  * diagonalisation (K5). Lets a caller split a whole strategy run (mle, omega: hundreds of launch sequences) by kernel. */
 double pcsf_total_ms(pcsf_ctx *ctx, int which);
+/* Work counters since creation or last reset (which < 0 resets): 0 = P(t) slots built by K1 (branch x candidate),
+ * 1 = codon-column evaluations pruned (columns x P sets), 2 = matrices diagonalised by K5, 3 = Jacobi sweeps they took,
+ * 4 = pruning tiles. With pcsf_total_ms they give a strategy run's achieved FLOP/s per kernel. */
+int64_t pcsf_counter(pcsf_ctx *ctx, int which);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t pcsf_launch_count(const pcsf_ctx *ctx);
 

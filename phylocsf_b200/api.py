@@ -161,6 +161,24 @@ class Context:
         self._check(self._L.pcsf_omega_models_set(self._h, first_id, qs.shape[0], N.ptr(qs), N.ptr(st)), ok_numeric=not check)
         return st
 
+    def omega_cache_reset(self, n_slots):
+        self._check(self._L.pcsf_omega_cache_reset(self._h, int(n_slots)))
+
+    def omega_models_set_cached(self, first_id, q_settings, cache_slot, check=True):
+        qs = _f64(q_settings).reshape(-1, 12)
+        sl = np.ascontiguousarray(cache_slot, dtype=np.int64)
+        assert sl.size == qs.shape[0]
+        st = np.zeros(qs.shape[0], dtype=np.int32)
+        self._check(self._L.pcsf_omega_models_set_cached(self._h, first_id, qs.shape[0], N.ptr(qs), N.ptr(sl), N.ptr(st)), ok_numeric=not check)
+        return st
+
+    def counters(self, reset=False):
+        names = {0: "pt_slots", 1: "column_evaluations", 2: "eig_matrices", 3: "eig_sweeps", 4: "tiles"}
+        out = {v: int(self._L.pcsf_counter(self._h, k)) for k, v in names.items()}
+        if reset:
+            self._L.pcsf_counter(self._h, -1)
+        return out
+
     def model_get(self, model_id):
         S, Sinv, lam, prior = np.empty((64, 64)), np.empty((64, 64)), np.empty(64), np.empty(64)
         self._check(self._L.pcsf_model_get(self._h, model_id, N.ptr(S), N.ptr(Sinv), N.ptr(lam), N.ptr(prior)))

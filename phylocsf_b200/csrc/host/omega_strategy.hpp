@@ -9,6 +9,7 @@
 // Used by the command line (driver.hpp: DeviceScorer::score_omega) and by pcsf_omega_score (phylocsf_host.h).
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -36,6 +37,7 @@ struct OmegaStrategy {
     pcsf_ctx* ctx;
     int n_leaves;
     int64_t evaluations = 0;  // likelihood evaluations (region x candidate) issued
+    bool use_cache = std::getenv("PCSF_OMEGA_COLD") == nullptr;  // PCSF_OMEGA_COLD=1: every diagonalisation from the identity (A/B runs)
     OmegaStrategy(pcsf_ctx* c, int nl) : ctx(c), n_leaves(nl) {}
 
     void check(int rc) {
@@ -62,12 +64,13 @@ struct OmegaStrategy {
     }
 
     // Assemble and diagonalise Q(qs) for every listed region on the device (K5) as models slot = index.
-    void omega_install_models(const std::vector<OmegaInst>& inst, const std::vector<int64_t>& which, std::vector<std::string>& exn) {
+    // `warm`: region r's slot of the eigenvector cache starts (and keeps) its diagonalisation (kappa searches)
+    void omega_install_models(const std::vector<OmegaInst>& inst, const std::vector<int64_t>& which, std::vector<std::string>& exn, bool warm = false) {
         const size_t n = which.size();
         std::vector<double> qs(n * 12);
         for (size_t i = 0; i < n; i++) std::memcpy(&qs[i * 12], inst[which[i]].qs, 12 * sizeof(double));
         std::vector<int32_t> st(n, 0);
-        check(pcsf_omega_models_set(ctx, 0, (int)n, qs.data(), st.data()));
+        check(pcsf_omega_models_set_cached(ctx, 0, (int)n, qs.data(), warm && use_cache ? which.data() : nullptr, st.data()));
         for (size_t i = 0; i < n; i++) {
             if (st[i] & 128) exn[which[i]] = "Failure(\"CamlPaml.P14n.instantiate_q: Q scale evaluated to a non-positive value\")";
             else if (st[i]) exn[which[i]] = "Failure(\"CamlPaml.Q.equilibrium: smallest-magnitude eigenvalue is unacceptably large; check rate matrix validity or increase tol\")";
@@ -85,6 +88,7 @@ struct OmegaStrategy {
         std::vector<int64_t> all(R);
         for (int64_t r = 0; r < R; r++) all[r] = r;
         if (!kappa_phase) omega_install_models(inst, all, exn);  // slot r = region r
+        else if (use_cache) check(pcsf_omega_cache_reset(ctx, R));  // every kappa search starts cold: bounds the accumulated rotations
         std::vector<int64_t> live, eval_pair;
         std::vector<int32_t> pair_model, pstat, estat;
         std::vector<double> pair_scale, lpr, xs;
@@ -101,7 +105,7 @@ struct OmegaStrategy {
             if (kappa_phase) {
                 std::vector<OmegaInst> cand(inst);
                 for (int64_t i = 0; i < n; i++) cand[live[i]].qs[0] = xs[i];
-                omega_install_models(cand, live, exn);  // slot i = i-th live region
+                omega_install_models(cand, live, exn, true);  // slot i = i-th live region
                 for (int64_t i = 0; i < n; i++) { pair_model[i] = (int32_t)i; pair_scale[i] = inst[live[i]].rho; }
             } else {
                 for (int64_t i = 0; i < n; i++) { pair_model[i] = (int32_t)live[i]; pair_scale[i] = xs[i]; }

@@ -66,6 +66,9 @@ struct pcsf_ctx {
     // work + outputs
     DevBuf d_spans, d_psets, d_out_logz, d_out_anc, d_seg_begin, d_seg_end, d_lpr, d_elpr, d_gstack;
     DevBuf d_jobs, d_batch_params, d_pair_tables, d_pair_status, d_qs, d_gexp, d_pair_cherry;
+    DevBuf d_eig_cache, d_eig_valid, d_eig_slots, d_eig_sweeps;  // K5 warm starts (pcsf_omega_models_set_cached)
+    int64_t eig_slots = 0;
+    int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // pcsf_counter: 0 K1 slots built, 1 codon-column evaluations pruned, 2 K5 matrices, 3 K5 sweeps, 4 tiles
     DevBuf d_out_tree, d_out_scratch, d_out_gacc, d_out_post, d_out_ecounts, d_out_z, d_out_nodes;  // K6 (pcsf_posteriors)
     // pcsf_score_alignments: double-buffered chunk staging on a second stream
     DevBuf pipe_nt[2], pipe_aln_off[2], pipe_aln_len[2], pipe_codes[2], pipe_roff[2];
@@ -286,6 +289,8 @@ int run_prune(pcsf_ctx* ctx, const std::vector<Span>& spans_in, const std::vecto
         ctx->last_level = (int)level;
         ctx->last_grid = grid;
         ctx->last_tiles = tiles;
+        ctx->counters[4] += tiles;
+        for (const Span& sp : spans) ctx->counters[1] += sp.ncols;
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     return PCSF_OK;
@@ -445,6 +450,7 @@ int pt_build_jobs(pcsf_ctx* ctx, const std::vector<PtJob>& jobs, DevBuf& tables,
                                                        ctx->n_leaves, (double*)tables.p, (int32_t*)d_status.p, 1e-6);
         CU(cudaGetLastError());
         ctx->launches++;
+        ctx->counters[0] += n_items;
     }
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     status.assign(n, 0);
@@ -556,7 +562,8 @@ void pcsf_destroy(pcsf_ctx* ctx) {
                       &ctx->d_psets, &ctx->d_out_logz, &ctx->d_out_anc, &ctx->d_seg_begin, &ctx->d_seg_end,
                       &ctx->d_lpr, &ctx->d_elpr, &ctx->d_gstack, &ctx->d_jobs, &ctx->d_batch_params, &ctx->d_pair_tables,
                       &ctx->d_pair_status, &ctx->d_qs, &ctx->d_gexp, &ctx->d_pair_cherry, &ctx->d_out_tree, &ctx->d_out_scratch, &ctx->d_out_gacc,
-                      &ctx->d_out_post, &ctx->d_out_ecounts, &ctx->d_out_z, &ctx->d_out_nodes, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
+                      &ctx->d_out_post, &ctx->d_out_ecounts, &ctx->d_out_z, &ctx->d_out_nodes, &ctx->d_eig_cache, &ctx->d_eig_valid, &ctx->d_eig_slots,
+                      &ctx->d_eig_sweeps, &ctx->pipe_nt[0], &ctx->pipe_nt[1], &ctx->pipe_aln_off[0],
                       &ctx->pipe_aln_off[1], &ctx->pipe_aln_len[0], &ctx->pipe_aln_len[1], &ctx->pipe_codes[0], &ctx->pipe_codes[1],
                       &ctx->pipe_roff[0], &ctx->pipe_roff[1]};
     for (auto* b : bufs) fr(*b);
@@ -1194,8 +1201,25 @@ int pcsf_models_set(pcsf_ctx* ctx, int first_id, int n, const double* S, const d
     return PCSF_OK;
 }
 
+int pcsf_omega_cache_reset(pcsf_ctx* ctx, int64_t n_slots) {
+    if (!ctx || n_slots < 0) return PCSF_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    TRY(reserve(ctx, ctx->d_eig_cache, sizeof(double) * 4096 * (size_t)std::max<int64_t>(n_slots, 1)));
+    TRY(reserve(ctx, ctx->d_eig_valid, sizeof(int32_t) * (size_t)std::max<int64_t>(n_slots, 1)));
+    CU(cudaMemsetAsync(ctx->d_eig_valid.p, 0, sizeof(int32_t) * (size_t)std::max<int64_t>(n_slots, 1), ctx->stream));
+    ctx->eig_slots = n_slots;
+    return PCSF_OK;
+}
+
 int pcsf_omega_models_set(pcsf_ctx* ctx, int first_id, int n, const double* q_settings, int32_t* status) {
+    return pcsf_omega_models_set_cached(ctx, first_id, n, q_settings, nullptr, status);
+}
+
+int pcsf_omega_models_set_cached(pcsf_ctx* ctx, int first_id, int n, const double* q_settings, const int64_t* cache_slot, int32_t* status) {
     if (!ctx) return PCSF_ERR_INVALID_ARG;
+    if (cache_slot)
+        for (int i = 0; i < n; i++)
+            if (cache_slot[i] >= ctx->eig_slots) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_omega_models_set_cached: cache slot out of range (pcsf_omega_cache_reset)");
     if (first_id < 0 || n < 1 || first_id + n > (1 << 22) || !q_settings)
         return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_omega_models_set: bad argument");
     for (int i = 0; i < n * 12; i++)
@@ -1213,18 +1237,29 @@ int pcsf_omega_models_set(pcsf_ctx* ctx, int first_id, int n, const double* q_se
     const int smem = (2 * 64 * 65 + 64 + 64 + 32 + 32) * 8;
     CU(cudaFuncSetAttribute(omega_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    const int64_t* d_slots = nullptr;
+    if (cache_slot) {
+        TRY(reserve(ctx, ctx->d_eig_slots, sizeof(int64_t) * (size_t)n));
+        CU(cudaMemcpyAsync(ctx->d_eig_slots.p, cache_slot, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        d_slots = (const int64_t*)ctx->d_eig_slots.p;
+    }
+    TRY(reserve(ctx, ctx->d_eig_sweeps, sizeof(int32_t) * (size_t)n));
     omega_eig_kernel<<<n, EIG_THREADS, smem, ctx->stream>>>((const double*)ctx->d_qs.p, (double*)ctx->d_batch_params.p,
-                                                            (int32_t*)ctx->d_pair_status.p);
+                                                            (int32_t*)ctx->d_pair_status.p, d_slots, (double*)ctx->d_eig_cache.p,
+                                                            (int32_t*)ctx->d_eig_valid.p, (int32_t*)ctx->d_eig_sweeps.p);
     CU(cudaGetLastError());
     ctx->launches++;
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-    std::vector<int32_t> st(n);
+    std::vector<int32_t> st(n), sw(n);
     CU(cudaMemcpyAsync(st.data(), ctx->d_pair_status.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(sw.data(), ctx->d_eig_sweeps.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
     ctx->ms[2] = t;
     ctx->ms_total[6] += t;
+    for (int i = 0; i < n; i++) ctx->counters[3] += sw[i];
+    ctx->counters[2] += n;
     if ((int)ctx->models.size() < first_id + n) ctx->models.resize(first_id + n);
     bool bad = false;
     for (int i = 0; i < n; i++) {
@@ -1568,6 +1603,15 @@ int64_t pcsf_last_launch_info(const pcsf_ctx* ctx, int which) {
 double pcsf_last_ms(const pcsf_ctx* ctx, int which) {
     if (!ctx || which < 0 || which > 5) return -1.0;
     return ctx->ms[which];
+}
+
+int64_t pcsf_counter(pcsf_ctx* ctx, int which) {
+    if (!ctx) return -1;
+    if (which < 0) {
+        for (int64_t& v : ctx->counters) v = 0;
+        return 0;
+    }
+    return which < 8 ? ctx->counters[which] : -1;
 }
 
 double pcsf_total_ms(pcsf_ctx* ctx, int which) {

@@ -1150,8 +1150,15 @@ __device__ __forceinline__ bool omega_is_stop(int c) { return c == 48 || c == 50
 __constant__ char kOmegaAA[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
 
 constexpr int EIG_THREADS = 256;
+// Warm start (cache_slot[i] >= 0 and the slot holds eigenvectors of an earlier solve): the kappa search of a region
+// visits a sequence of nearby rate matrices, so the previous candidate's eigenvectors V0 nearly diagonalise the new
+// matrix; the sweeps then run on V0^T A V0 with the rotations accumulated onto V0 and converge in 2-4 sweeps instead
+// of ~9. The result is an eigensystem of the same matrix to the same stopping threshold (it differs from a cold
+// solve by rounding, like any two eigensolvers do); it depends only on the region's own sequence of candidates.
 __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __restrict__ qs_all, double* __restrict__ params_all,
-                                                               int32_t* __restrict__ status) {
+                                                                  int32_t* __restrict__ status, const int64_t* __restrict__ cache_slot,
+                                                                  double* __restrict__ cache, int32_t* __restrict__ cache_valid,
+                                                                  int32_t* __restrict__ sweeps_out) {
     extern __shared__ double esm[];
     double* A = esm;              // 64 x 65 (padded)
     double* V = esm + 64 * 65;    // 64 x 65
@@ -1160,7 +1167,7 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
     double* rc = sw + 64;         // 32 cosines
     double* rs = rc + 32;         // 32 sines
     __shared__ int pp[32], pq[32];
-    __shared__ double red[EIG_THREADS / 32];
+    __shared__ double red[EIG_THREADS / 32], red2[EIG_THREADS / 32];
     __shared__ double s_factor, s_off, s_diag;
     const int tid = threadIdx.x;
     const double* v = qs_all + (size_t)blockIdx.x * 12;
@@ -1229,9 +1236,46 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
         A[i * 65 + j] = (i == j) ? V[i * 65 + i] : 0.5 * (V[i * 65 + j] + V[j * 65 + i]);
     }
     __syncthreads();
-    for (int idx = tid; idx < 4096; idx += EIG_THREADS) V[(idx >> 6) * 65 + (idx & 63)] = ((idx >> 6) == (idx & 63)) ? 1.0 : 0.0;
-    __syncthreads();
+    const int64_t slot = cache_slot ? cache_slot[blockIdx.x] : -1;
+    const bool warm = slot >= 0 && cache_valid[slot] != 0;  // uniform across the CTA
+    if (!warm) {
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) V[(idx >> 6) * 65 + (idx & 63)] = ((idx >> 6) == (idx & 63)) ? 1.0 : 0.0;
+        __syncthreads();
+    } else {
+        // A <- V0^T A V0, V <- V0. The intermediate A V0 goes through this model's own output block (global, L2;
+        // overwritten with S at the end), so the kernel keeps its two shared-memory matrices and three CTAs per SM.
+        const double* V0 = cache + (size_t)slot * 4096;
+        double* Tg = out;
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) V[(idx >> 6) * 65 + (idx & 63)] = V0[idx];
+        __syncthreads();
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+            const int i = idx >> 6, j = idx & 63;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < 64; k++) acc += A[i * 65 + k] * V[k * 65 + j];
+            Tg[idx] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
+            const int i = idx >> 6, j = idx & 63;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < 64; k++) acc += V[k * 65 + i] * Tg[k * 64 + j];
+            A[i * 65 + j] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) {  // exactly symmetric again
+            const int i = idx >> 6, j = idx & 63;
+            if (i < j) {
+                const double m = 0.5 * (A[i * 65 + j] + A[j * 65 + i]);
+                A[i * 65 + j] = m;
+                A[j * 65 + i] = m;
+            }
+        }
+        __syncthreads();
+    }
     // ---- parallel cyclic Jacobi ----
+    int sweeps = 0;
     for (int sweep = 0; sweep < 40; sweep++) {
         double o2 = 0.0, d2 = 0.0;
         for (int idx = tid; idx < 4096; idx += EIG_THREADS) {
@@ -1241,15 +1285,17 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
         }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) { o2 += __shfl_xor_sync(0xffffffffu, o2, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
-        if ((tid & 31) == 0) red[tid >> 5] = o2;
+        if ((tid & 31) == 0) { red[tid >> 5] = o2; red2[tid >> 5] = d2; }
         __syncthreads();
-        if (tid == 0) { double t = 0; for (int k = 0; k < EIG_THREADS / 32; k++) t += red[k]; s_off = t; }
-        __syncthreads();
-        if ((tid & 31) == 0) red[tid >> 5] = d2;
-        __syncthreads();
-        if (tid == 0) { double t = 0; for (int k = 0; k < EIG_THREADS / 32; k++) t += red[k]; s_diag = t; }
+        if (tid == 0) {
+            double t = 0, u = 0;
+            for (int k = 0; k < EIG_THREADS / 32; k++) { t += red[k]; u += red2[k]; }
+            s_off = t;
+            s_diag = u;
+        }
         __syncthreads();
         if (s_off <= 1e-34 * s_diag || s_off == 0.0) break;
+        sweeps++;
         for (int r = 0; r < 63; r++) {
             if (tid < 32) {  // pairing of round r and its rotations
                 int a = tid == 0 ? 63 : (r + tid) % 63, b = tid == 0 ? r : (r - tid + 63) % 63;
@@ -1258,7 +1304,8 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
                 pq[tid] = q_;
                 const double apq = A[p_ * 65 + q_], app = A[p_ * 65 + p_], aqq = A[q_ * 65 + q_];
                 double c = 1.0, s = 0.0;
-                if (apq != 0.0 && !(sweep > 4 && fabs(apq) <= 1e-20 * fabs(app) && fabs(apq) <= 1e-20 * fabs(aqq))) {
+                // the second test: after a warm start most pairs are already negligible in the first sweeps
+                if (apq != 0.0 && !((sweep > 4 || warm) && fabs(apq) <= 1e-20 * fabs(app) && fabs(apq) <= 1e-20 * fabs(aqq))) {
                     const double theta = (aqq - app) / (2.0 * apq);
                     const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                     c = 1.0 / sqrt(t * t + 1.0);
@@ -1268,33 +1315,45 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
                 rs[tid] = s;
             }
             __syncthreads();
-            // columns: A <- A J, V <- V J   (pair k touches columns p,q of every row)
+            // A <- J^T A J in one pass: the 2 x 2 block (rows of pair ki, columns of pair kj) only needs the two pairs'
+            // rotations and belongs to one thread; columns first, then rows, as two separate passes would do it
+#pragma unroll 2
+            for (int b = tid; b < 1024; b += EIG_THREADS) {
+                const int ki = b >> 5, kj = b & 31;
+                const int pi_ = pp[ki], qi_ = pq[ki], pj_ = pp[kj], qj_ = pq[kj];
+                const double ci = rc[ki], si = rs[ki], cj = rc[kj], sj = rs[kj];
+                const double a_pp = A[pi_ * 65 + pj_], a_pq = A[pi_ * 65 + qj_], a_qp = A[qi_ * 65 + pj_], a_qq = A[qi_ * 65 + qj_];
+                const double t_pp = cj * a_pp - sj * a_pq, t_pq = sj * a_pp + cj * a_pq;
+                const double t_qp = cj * a_qp - sj * a_qq, t_qq = sj * a_qp + cj * a_qq;
+                double n_pp = ci * t_pp - si * t_qp, n_qp = si * t_pp + ci * t_qp;
+                double n_pq = ci * t_pq - si * t_qq, n_qq = si * t_pq + ci * t_qq;
+                // the rotated pair itself ends up exactly zero (annihilated, or flushed when it no longer registers
+                // against the diagonal), as in the host's Jacobi: without this the off-diagonal norm stalls at
+                // rounding level above the stopping threshold and every matrix runs all 40 sweeps instead of ~9
+                if (ki == kj) { n_pq = 0.0; n_qp = 0.0; }
+                A[pi_ * 65 + pj_] = n_pp;
+                A[pi_ * 65 + qj_] = n_pq;
+                A[qi_ * 65 + pj_] = n_qp;
+                A[qi_ * 65 + qj_] = n_qq;
+            }
+            // V <- V J (pair k touches columns p, q of every row)
+#pragma unroll 4
             for (int idx = tid; idx < 2048; idx += EIG_THREADS) {
                 const int k = idx & 31, row = idx >> 5;
                 const int p_ = pp[k], q_ = pq[k];
                 const double c = rc[k], s = rs[k];
-                const double akp = A[row * 65 + p_], akq = A[row * 65 + q_];
-                A[row * 65 + p_] = c * akp - s * akq;
-                A[row * 65 + q_] = s * akp + c * akq;
                 const double vkp = V[row * 65 + p_], vkq = V[row * 65 + q_];
                 V[row * 65 + p_] = c * vkp - s * vkq;
                 V[row * 65 + q_] = s * vkp + c * vkq;
             }
             __syncthreads();
-            // rows: A <- J^T A
-            for (int idx = tid; idx < 2048; idx += EIG_THREADS) {
-                const int col = idx & 63, k = idx >> 6;
-                const int p_ = pp[k], q_ = pq[k];
-                const double c = rc[k], s = rs[k];
-                const double apk = A[p_ * 65 + col], aqk = A[q_ * 65 + col];
-                // the rotated pair itself ends up exactly zero (annihilated, or flushed when it no longer registers
-                // against the diagonal), as in the host's Jacobi: without this the off-diagonal norm stalls at
-                // rounding level above the stopping threshold and every matrix runs all 40 sweeps instead of ~9
-                A[p_ * 65 + col] = col == q_ ? 0.0 : c * apk - s * aqk;
-                A[q_ * 65 + col] = col == p_ ? 0.0 : s * apk + c * aqk;
-            }
-            __syncthreads();
         }
+    }
+    if (sweeps_out && tid == 0) sweeps_out[blockIdx.x] = sweeps;
+    if (slot >= 0) {  // this solve's eigenvectors start the region's next one
+        double* V0 = cache + (size_t)slot * 4096;
+        for (int idx = tid; idx < 4096; idx += EIG_THREADS) V0[idx] = V[(idx >> 6) * 65 + (idx & 63)];
+        if (tid == 0) cache_valid[slot] = 1;
     }
     // ---- outputs: S = W^-1/2 U, S^-1 = U^T W^1/2, lambda, equilibrium (Q.ml:153-177) ----
     for (int idx = tid; idx < 4096; idx += EIG_THREADS) {

@@ -21,7 +21,7 @@ def _check(ps, regs, rho=1.0, models=(0, 1)):
         ctx.pt_build(m, [0.7, rho])
         post, ec, z = ctx.posteriors(m, 1, nodes=nodes)
         zo, po, eo = o.posteriors_columns(inst.model(rho), codes)
-        np.testing.assert_allclose(z, zo, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(z, zo, rtol=1e-10, atol=0)
         np.testing.assert_allclose(post, po.transpose(1, 0, 2), rtol=0, atol=2e-12)
         np.testing.assert_allclose(ec, eo, rtol=0, atol=1e-11 * max(1, codes.shape[0]))
         live = int((zo > 0).sum())

@@ -163,11 +163,36 @@ def test_headline_config_level4_against_oracle_540_regions(params_base):
                             [rng.integers(0, A * F, size=240)])
     regs = [_frame_codes(nt[int(r) // F], int(r) % F) for r in sample]
     assert sum((c == 64).any() for c in regs) > 150  # the sample does contain gapped / missing-species regions
+    # kinds 2, 3, 4 of _perturb put codons into the columns that are unrelated to their neighbours' (random substitutions)
+    unrelated = np.array([any(lo <= int(r) // F < hi and (int(r) // F - lo) % 5 in (2, 3, 4) for lo, hi in pert) for r in sample])
+    assert 100 < unrelated.sum() < 300
     ops = H.oracle_paramset(params_base, "58mammals")
+    # (1) pruning alone, on all 540 regions: the oracle walks the tree with the very P(t) tables the device holds
+    t = ops.tree
+    off_s, codes_s = H.regions_to_batch(regs)
+    for m in (0, 1):
+        pms = np.ascontiguousarray(np.stack([ctx.pt_get(m, 0, br) for br in range(nbr)]))
+        prior = np.ascontiguousarray(ps.qdiag(m)["prior"])
+        a, b = np.empty(len(regs)), np.empty(len(regs))
+        o.lib().oracle_lpr_batch(t.n_leaves, t.children_array().ctypes.data, o._dp(pms), None, o._dp(prior), 64, len(regs),
+                                 off_s.ctypes.data, codes_s.ctypes.data, o._dp(a), o._dp(b), H.host_cores())
+        d1 = np.abs(H.DB * (lpr[m, sample] - a)).max()
+        d2 = np.abs(H.DB * (elpr[m, sample] - b)).max()
+        assert d1 < 1e-7 and d2 < 1e-7, ("pruning parity", m, d1, d2)
+    # (2) end to end: the oracle with its own P(t) (LAPACK eigensystem, dgemm order) against the product's (Jacobi
+    # eigensystem, DMMA order). Regions made of columns the model could have drawn - gaps, missing species and N included -
+    # agree to the 1e-6 dB bar. Regions with unrelated substitutions do not and cannot: their likelihood runs through
+    # entries of P(t) of 1e-9 and below, which S exp(L t) S^-1 delivers with an ABSOLUTE error of 1e-14, so even the CPU
+    # oracle moves by up to 1e-4 dB when only its eigensolver is swapped (conditioning). For those the
+    # bar is relative: 2e-9 of |lpr|.
     lo_, eo_ = H.oracle_fixed_batch(ops, regs)
-    d1 = np.abs(H.DB * (lpr[:, sample] - lo_)).max()
-    d2 = np.abs(H.DB * (elpr[:, sample] - eo_)).max()
-    assert d1 < 1e-6 and d2 < 1e-6, (d1, d2)
+    d = np.abs(H.DB * (lpr[:, sample] - lo_))
+    da = np.abs(H.DB * (elpr[:, sample] - eo_))
+    assert d[:, ~unrelated].max() < 1e-6 and da[:, ~unrelated].max() < 1e-6, (d[:, ~unrelated].max(), da[:, ~unrelated].max())
+    rel = d[:, unrelated] / np.abs(H.DB * lo_[:, unrelated])
+    assert rel.max() < 2e-9, rel.max()
+    print("headline sample: model-like max |d lpr| %.2e dB; unrelated-substitution regions max %.2e dB (relative %.2e)"
+          % (d[:, ~unrelated].max(), d[:, unrelated].max(), rel.max()))
     ctx.close()
 
 
@@ -200,14 +225,26 @@ def test_mle_120mammals_56_full_regions_vs_oracle(params_base):
             assert (st[m, r] & ~64) == 0
             # rho is a Brent iterate: parabolic steps amplify the 1e-13 relative differences between the two likelihood
             # evaluations (measured: up to 3e-7 relative over these regions); the same path is taken (equal evaluation
-            # counts) and the stop rule only asks for 1 % anyway. The bar that matters is the score, below.
+            # counts) and the stop rule only asks for 1 % anyway.
             assert abs(rho[m, r] - ox) < 1e-5 * max(1.0, ox), (r, m, rho[m, r], ox)
             assert ne[m, r] == 3 + otries + 3 + 1 + oit + 1, (r, m)
             worst = max(worst, abs(H.DB * (lpr[m, r] - olp)), abs(H.DB * (elpr[m, r] - oel)))
-    assert worst < 1e-6, worst
+    # The returned lpr is the likelihood AT the final iterate, which sits up to 1 % away from the optimum, where the slope is
+    # a few nats per unit of rho: a 3e-7 shift of the iterate moves it by ~2e-6 dB (measured worst over these 112 searches:
+    # 1.9e-6). That is the conditioning of the reference's own procedure, not evaluation error - shown by (2) below.
+    assert worst < 1e-5, worst
     score = H.DB * (lpr[0] - lpr[1])
     want = np.array([H.DB * (ora[r][0][1] - ora[r][1][1]) for r in range(len(regs))])
-    assert np.abs(score - want).max() < 1e-6
+    assert np.abs(score - want).max() < 1e-5
+    # (2) the same likelihoods evaluated at the ORACLE's final rho: no search in between, the 1e-6 dB bar holds
+    R = len(regs)
+    ctx.pt_build_pairs(np.repeat([0, 1], R), np.array([ora[r][m][0] for m in (0, 1) for r in range(R)]))
+    l2, e2, s2 = ctx.lpr_pairs(np.arange(2 * R), np.tile(np.arange(R), 2))
+    olp = np.array([ora[r][m][1] for m in (0, 1) for r in range(R)])
+    oel = np.array([ora[r][m][2] for m in (0, 1) for r in range(R)])
+    d_at = max(np.abs(H.DB * (l2 - olp)).max(), np.abs(H.DB * (e2 - oel)).max())
+    assert (s2 == 0).all() and d_at < 1e-6, d_at
+    print("120mammals mle: worst |d lpr| at the device's own iterate %.2e dB, at the oracle's rho %.2e dB" % (worst, d_at))
     ctx.close()
 
 
@@ -273,4 +310,50 @@ def test_omega_full_100vertebrates_tree_abi_vs_oracle(params_base):
         for got, exp in ((diag[r, 1], w[2]), (diag[r, 2], w[3]), (diag[r, 6], w[5]), (diag[r, 7], w[6])):
             assert abs(got - exp) < 1e-4 * max(1.0, abs(exp)), (r, got, exp)
         assert diag[r, 3] == 1.0 and diag[r, 4] == 1.0 and diag[r, 8] == 0.2 and diag[r, 9] == 0.01
+    ctx.close()
+
+
+def test_omega_eigen_warm_start_matches_cold(params_base):
+    """K5 with warm starts (pcsf_omega_models_set_cached: the previous candidate's eigenvectors start the next
+    diagonalisation of the same region) against cold starts: the same eigensystem of the same matrix - S diag(lambda) S^-1
+    reproduces the oracle's Q, S S^-1 = I, the equilibrium prior and the likelihood agree to rounding - in fewer sweeps."""
+    ps = H.oracle_paramset(params_base, "12flies")
+    ctx = H.make_context(ps)
+    regs, _ = H.example_codes(ps, "tal-AA.fa")
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    rng = np.random.default_rng(8)
+    base = np.array([[2.5, 1.0, 1.0] + [1.0] * 9, [1.7, 0.2, 0.01, 1.3, 0.8, 1.1, 0.9, 1.2, 0.7, 1.05, 0.95, 1.4],
+                     [4.0, 0.5, 0.3] + list(rng.uniform(0.3, 3.0, 9))])
+    kappas = [2.5, 1.0, 10.0, 4.4377, 3.9, 4.02, 4.011, 4.0101]  # a search closing in, as Brent's does
+    ctx.omega_cache_reset(3)
+    ctx.counters(reset=True)
+    warm_sweeps = []
+    for kappa in kappas:
+        qs = base.copy()
+        qs[:, 0] = kappa
+        st = ctx.omega_models_set_cached(3, qs, [0, 1, 2])
+        assert (st == 0).all()
+        warm = [ctx.model_get(3 + i) for i in range(3)]
+        ctx.pt_build_pairs([3, 4, 5], [1.0, 0.6, 1.7])
+        lw = ctx.lpr_pairs([0, 1, 2], [0, 0, 0])[0]
+        warm_sweeps.append(ctx.counters(reset=True)["eig_sweeps"])
+        st = ctx.omega_models_set(3, qs)  # cold
+        cold = [ctx.model_get(3 + i) for i in range(3)]
+        ctx.pt_build_pairs([3, 4, 5], [1.0, 0.6, 1.7])
+        lc = ctx.lpr_pairs([0, 1, 2], [0, 0, 0])[0]
+        cold_sweeps = ctx.counters(reset=True)["eig_sweeps"]
+        for i in range(3):
+            Qo = o.omega_q(list(qs[i]))
+            d = warm[i]
+            np.testing.assert_allclose(d["S"] @ np.diag(d["lam"]) @ d["Sinv"], Qo, atol=5e-13)
+            np.testing.assert_allclose(d["S"] @ d["Sinv"], np.eye(64), atol=1e-12)
+            np.testing.assert_allclose(np.sort(d["lam"]), np.sort(cold[i]["lam"]), atol=1e-12)
+            np.testing.assert_allclose(d["prior"], cold[i]["prior"], atol=1e-14)
+        assert np.abs(H.DB * (lw - lc)).max() < 1e-8, (kappa, lw, lc)
+    assert warm_sweeps[0] == cold_sweeps or warm_sweeps[0] >= 3 * 7   # the first solve of a slot is a cold one
+    assert warm_sweeps[-1] < 0.6 * cold_sweeps, (warm_sweeps, cold_sweeps)  # nearby candidates converge in a few sweeps
+    print("K5 sweeps per 3 matrices: warm", warm_sweeps, "cold", cold_sweeps)
+    with pytest.raises(Exception):
+        ctx.omega_models_set_cached(3, base, [0, 1, 7])  # slot out of range
     ctx.close()
