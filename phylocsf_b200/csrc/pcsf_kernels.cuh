@@ -147,11 +147,24 @@ struct PtJob {               // one P set to build: a diagonalised model at one 
     const double* params;   // S | Sinv | lambda | prior | logprior (pcsf_api.cu: Model)
     double scale;
 };
+#ifndef PCSF_K1_ROWSUM_DMMA
+#define PCSF_K1_ROWSUM_DMMA 1
+#endif
+// Plain FP64 instructions of one warp do not get between the DMMAs of the other warps of a sub-partition (DESIGN
+// section 3), so every DADD of the fix-ups costs far more than its two pipe cycles: the first version of this kernel
+// (16 + 16 adds and 16 FP64 compares per thread and slot) ran at 66 % of the DMMA peak (round-2 measurement:
+// 24.4 TFLOP/s over 33.4 M slots; profiles/r02_pt_build_ncu_summary.json). Now
+//   - the pre-clamp row sum comes out of the tensor pipe: a ninth n-tile whose B operand carries the row sums of
+//     S^-1 in its first column gives sum_j P[i][j] = sum_k (S e)[i][k] rowsum(S^-1)[k] as one more accumulator
+//     (PCSF_K1_ROWSUM_DMMA=0 keeps the 16 adds instead),
+//   - the sign test reads the high word on the integer pipe, and
+//   - the off-diagonal sum is (row sum - P[i][i]) unless the warp holds a negative entry; only then the explicit
+//     clamped sums of the reference run (negative entries do not occur for the shipped models at any scale tried).
 __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restrict__ jobs, long long n_items,
                                                           const double* __restrict__ branch_len, int n_branches,
                                                           int n_leaves, double* __restrict__ tables,
                                                           int32_t* __restrict__ status, double tol) {
-    __shared__ double Sinv_s[4096];  // fragment-ordered: [(j*16+s)*32 + lane] = Sinv[4s+t][8j+g]
+    __shared__ double Sinv_s[4096 + 512];  // fragment-ordered: [(j*16+s)*32 + lane] = Sinv[4s+t][8j+g]; n-tile 8: row sums of Sinv in column 0
     __shared__ double e_s[2][64];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -173,6 +186,17 @@ __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restric
                 const int l = idx & 31, s = (idx >> 5) & 15, j = idx >> 9;
                 Sinv_s[idx] = Sinv[(4 * s + (l & 3)) * 64 + 8 * j + (l >> 2)];
             }
+#if PCSF_K1_ROWSUM_DMMA
+            for (int idx = tid; idx < 512; idx += 256) {
+                const int l = idx & 31, s = idx >> 5;
+                double r = 0.0;
+                if ((l >> 2) == 0) {
+                    const double* row = Sinv + (4 * s + (l & 3)) * 64;
+                    for (int j = 0; j < 64; j++) r += row[j];
+                }
+                Sinv_s[4096 + idx] = r;
+            }
+#endif
 #pragma unroll
             for (int s = 0; s < 16; s++) afrag[s] = job.params[(8 * w + g) * 64 + 4 * s + t];
             cur_params = job.params;
@@ -181,33 +205,62 @@ __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restric
         double acc[8][2];
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
+#if PCSF_K1_ROWSUM_DMMA
+        double rs0 = 0.0, rs1 = 0.0;
+#endif
 #pragma unroll
         for (int s = 0; s < 16; s++) {
             const double a = afrag[s] * e_s[buf][4 * s + t];
 #pragma unroll
             for (int j = 0; j < 8; j++) dmma(acc[j][0], acc[j][1], a, Sinv_s[(j * 16 + s) * 32 + lane]);
+#if PCSF_K1_ROWSUM_DMMA
+            dmma(rs0, rs1, a, Sinv_s[4096 + s * 32 + lane]);
+#endif
         }
-        // ---- fix-ups on row i = 8w+g, whose 64 entries sit in the quad's accumulators ----
+        // ---- fix-ups on row i = 8w+g, whose 64 entries sit in the quad's accumulators (Q.ml:226-247) ----
         const int i = 8 * w + g;
         int st = (tt < 0.0) ? 1 : 0;
-        double tot = 0.0, off = 0.0;
+        bool neg = false;
 #pragma unroll
-        for (int j = 0; j < 8; j++)
+        for (int j = 0; j < 8; j++) neg |= (__double2hiint(acc[j][0]) < 0) | (__double2hiint(acc[j][1]) < 0);
+        double tot, off;
+#if PCSF_K1_ROWSUM_DMMA
+        tot = __shfl_sync(0xffffffffu, rs0, lane & ~3);  // D[g][0] of the ninth n-tile sits in lane t = 0 of the quad
+#else
+        tot = 0.0;
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                double v = acc[j][e];
-                tot += v;
-                if (v < 0.0) {
-                    if (fabs(v) > tol) st |= 2;
-                    v = 0.0;
-                    acc[j][e] = 0.0;
-                }
-                if (8 * j + 2 * t + e != i) off += v;
-            }
+        for (int j = 0; j < 8; j++) tot += acc[j][0] + acc[j][1];
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
         tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-        off += __shfl_xor_sync(0xffffffffu, off, 1);
-        off += __shfl_xor_sync(0xffffffffu, off, 2);
+#endif
+        if (__any_sync(0xffffffffu, neg)) {  // rare: the reference's explicit pre-clamp / post-clamp sums
+            tot = 0.0;
+            off = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    double v = acc[j][e];
+                    tot += v;
+                    if (v < 0.0) {
+                        if (fabs(v) > tol) st |= 2;
+                        v = 0.0;
+                        acc[j][e] = 0.0;
+                    }
+                    if (8 * j + 2 * t + e != i) off += v;
+                }
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            off += __shfl_xor_sync(0xffffffffu, off, 1);
+            off += __shfl_xor_sync(0xffffffffu, off, 2);
+        } else {  // P[i][i] is entry (n-tile w, slot g & 1) of lane t = g >> 1
+            double pii = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j == w) pii = (g & 1) ? acc[j][1] : acc[j][0];
+            pii = __shfl_sync(0xffffffffu, pii, (lane & ~3) | (g >> 1));
+            off = tot - pii;
+        }
         const double smii = 1.0 - off;
         if (fabs(tot - 1.0) > tol) st |= 4;
         if (!(smii <= 1.0 && smii > 0.0)) st |= 8;
