@@ -148,37 +148,42 @@ struct PtJob {               // one P set to build: a diagonalised model at one 
     double scale;
 };
 #ifndef PCSF_K1_ROWSUM_DMMA
-#define PCSF_K1_ROWSUM_DMMA 1
+#define PCSF_K1_ROWSUM_DMMA 0
 #endif
-// Plain FP64 instructions of one warp do not get between the DMMAs of the other warps of a sub-partition (DESIGN
-// section 3), so every DADD of the fix-ups costs far more than its two pipe cycles: the first version of this kernel
-// (16 + 16 adds and 16 FP64 compares per thread and slot) ran at 66 % of the DMMA peak (round-2 measurement:
-// 24.4 TFLOP/s over 33.4 M slots; profiles/r02_pt_build_ncu_summary.json). Now
-//   - the pre-clamp row sum comes out of the tensor pipe: a ninth n-tile whose B operand carries the row sums of
-//     S^-1 in its first column gives sum_j P[i][j] = sum_k (S e)[i][k] rowsum(S^-1)[k] as one more accumulator
-//     (PCSF_K1_ROWSUM_DMMA=0 keeps the 16 adds instead),
-//   - the sign test reads the high word on the integer pipe, and
-//   - the off-diagonal sum is (row sum - P[i][i]) unless the warp holds a negative entry; only then the explicit
-//     clamped sums of the reference run (negative entries do not occur for the shipped models at any scale tried).
+// Round-2 measurements on this kernel (33.4 M slots of the 120mammals mle benchmark; tools/bench_k1.py; the round-1
+// figure of 98 % of the DMMA peak divided by a slot count that was 1.5 x too high - it was 66 %):
+//   as in round 1 (64 exp by two warps right before the barrier, 16 + 16 adds and 16 FP64 compares per thread)   24.4 TFLOP/s
+//   + sign test on the integer pipe, off-diagonal sum = row sum - P[i][i] unless the warp holds a negative entry,
+//     exponentials one item ahead, eight per warp (no global load between barrier and contraction)               26.5 TFLOP/s = 71 %
+//   row sum as a ninth n-tile on the tensor pipe instead of 16 adds (PCSF_K1_ROWSUM_DMMA=1)                        25.0 (12.5 % more DMMAs)
+//   timing-only ablations: no stores 29.9; no stores, no exp, no S diag(e) products 30.0 (81 %) - what is left is one
+//     LDS.64 per DMMA (LSU data pipe 54 % busy) and the barrier per slot; stores cost 11 %, the plain FP64 work nothing.
+//   a phased form (one CTA of 16 warps per SM, exponentials from a pre-pass kernel, two barriers per pair of slots so that
+//     the pipe sees either plain FP64 instructions or DMMAs) ran at 21.7: the idle pipe at the phase changes costs more
+//     than the contention it removes. Not kept.
 __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restrict__ jobs, long long n_items,
                                                           const double* __restrict__ branch_len, int n_branches,
                                                           int n_leaves, double* __restrict__ tables,
                                                           int32_t* __restrict__ status, double tol) {
     __shared__ double Sinv_s[4096 + 512];  // fragment-ordered: [(j*16+s)*32 + lane] = Sinv[4s+t][8j+g]; n-tile 8: row sums of Sinv in column 0
     __shared__ double e_s[2][64];
+    __shared__ double lam_s[64];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const long long per = (n_items + gridDim.x - 1) / gridDim.x;
     const long long lo = per * blockIdx.x, hi = min(n_items, lo + per);
+    if (lo >= hi) return;
     const double* cur_params = nullptr;
     double afrag[16];  // S[8w+g][4s+t]
     int buf = 0;
+    long long job_i = lo / n_branches;
+    int br = (int)(lo - job_i * n_branches);
+    PtJob job = jobs[job_i];
+    // The exponentials of an item are computed one item ahead, eight per warp (lanes 0-7), so that neither their
+    // global loads nor their ~40 dependent FP64 instructions sit between the barrier and the contraction.
+    if (lane < 8) e_s[0][8 * w + lane] = exp(job.scale * branch_len[br] * job.params[8192 + 8 * w + lane]);  // Q.ml:216-217
     for (long long item = lo; item < hi; item++, buf ^= 1) {
-        const long long job_i = item / n_branches;
-        const int br = (int)(item - job_i * n_branches);
-        const PtJob job = jobs[job_i];
         const double tt = job.scale * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
-        if (tid < 64) e_s[buf][tid] = exp(tt * job.params[8192 + tid]);  // Q.ml:216-217
         if (job.params != cur_params) {  // uniform across the CTA
             __syncthreads();             // everybody is done reading the previous model's image
             const double* Sinv = job.params + 4096;
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restric
                 const int l = idx & 31, s = (idx >> 5) & 15, j = idx >> 9;
                 Sinv_s[idx] = Sinv[(4 * s + (l & 3)) * 64 + 8 * j + (l >> 2)];
             }
+            if (tid < 64) lam_s[tid] = job.params[8192 + tid];
 #if PCSF_K1_ROWSUM_DMMA
             for (int idx = tid; idx < 512; idx += 256) {
                 const int l = idx & 31, s = idx >> 5;
@@ -202,19 +208,36 @@ __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restric
             cur_params = job.params;
         }
         __syncthreads();  // e_s[buf] (and the image) visible; e_s[buf^1] is free for the next item
+        // the next item (same job's next branch, or the next job's first): its exponentials go into e_s[buf^1]
+        PtJob njob = job;
+        long long njob_i = job_i;
+        int nbr = br + 1;
+        if (nbr == n_branches) {
+            nbr = 0;
+            njob_i = job_i + 1;
+            if (item + 1 < hi) njob = jobs[njob_i];
+        }
+        if (item + 1 < hi && lane < 8) {
+            const double lam = njob.params == cur_params ? lam_s[8 * w + lane] : njob.params[8192 + 8 * w + lane];
+            e_s[buf ^ 1][8 * w + lane] = exp(njob.scale * branch_len[nbr] * lam);
+        }
         double acc[8][2];
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
 #if PCSF_K1_ROWSUM_DMMA
         double rs0 = 0.0, rs1 = 0.0;
 #endif
+        double a[16];  // S diag(e) (ptxas weaves these products into the DMMA stream, one per k-step, whatever the source order)
 #pragma unroll
         for (int s = 0; s < 16; s++) {
-            const double a = afrag[s] * e_s[buf][4 * s + t];
+            a[s] = afrag[s] * e_s[buf][4 * s + t];
+        }
 #pragma unroll
-            for (int j = 0; j < 8; j++) dmma(acc[j][0], acc[j][1], a, Sinv_s[(j * 16 + s) * 32 + lane]);
+        for (int s = 0; s < 16; s++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) dmma(acc[j][0], acc[j][1], a[s], Sinv_s[(j * 16 + s) * 32 + lane]);
 #if PCSF_K1_ROWSUM_DMMA
-            dmma(rs0, rs1, a, Sinv_s[4096 + s * 32 + lane]);
+            dmma(rs0, rs1, a[s], Sinv_s[4096 + s * 32 + lane]);
 #endif
         }
         // ---- fix-ups on row i = 8w+g, whose 64 entries sit in the quad's accumulators (Q.ml:226-247) ----
@@ -283,6 +306,9 @@ __global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restric
 #pragma unroll
                 for (int e = 0; e < 2; e++) out[((w * 16 + 2 * j + e) * 32) + lane] = acc[j][e];
         }
+        job = njob;
+        job_i = njob_i;
+        br = nbr;
     }
 }
 
