@@ -1695,9 +1695,17 @@ __device__ __forceinline__ uint8_t nt_comp(uint8_t c) {  // Code.ml:39-51 (valid
     }
 }
 // region r = alignment a, frame f: columns at lo = f%3, strand = f/3 (src/PhyloCSF.ml:198-205,219-246)
-__global__ void frame_codes_kernel(const uint8_t* __restrict__ nt, const int64_t* __restrict__ aln_off,
-                                   const int32_t* __restrict__ aln_len, const int64_t* __restrict__ region_off,
-                                   int64_t nregions, int frames, int n_leaves, uint8_t* __restrict__ codes) {
+// One CTA per region, tiles of 32 codon columns: the nucleotides are read along the rows (a warp reads 96 consecutive
+// bytes of one species), the codes are written along the columns (consecutive leaves of one column), and a shared-memory
+// tile turns one order into the other - both sides of the kernel move whole sectors. (The first version read three
+// bytes per thread with a stride of one row between neighbouring threads: 410 GB/s, 5 % of the HBM peak; ncu,
+// profiles/r02_frame_codes_ncu_summary.json.)
+constexpr int K0_COLS = 32;
+constexpr int K0_THREADS = 256;
+__global__ void __launch_bounds__(K0_THREADS) frame_codes_kernel(const uint8_t* __restrict__ nt, const int64_t* __restrict__ aln_off,
+                                                                 const int32_t* __restrict__ aln_len, const int64_t* __restrict__ region_off,
+                                                                 int64_t nregions, int frames, int n_leaves, uint8_t* __restrict__ codes) {
+    extern __shared__ uint8_t k0_tile[];  // [n_leaves][K0_COLS + 1]
     const int64_t r = blockIdx.x;
     if (r >= nregions) return;
     const int64_t a = r / frames;
@@ -1708,18 +1716,29 @@ __global__ void frame_codes_kernel(const uint8_t* __restrict__ nt, const int64_t
     const uint8_t* base = nt + aln_off[a];
     const int64_t c0 = region_off[r];
     const int ncols = (int)(region_off[r + 1] - c0);
-    for (int idx = threadIdx.x; idx < ncols * n_leaves; idx += blockDim.x) {
-        const int c = idx / n_leaves, l = idx - c * n_leaves;
-        const int pos = ofs + 3 * c;
-        const uint8_t* row = base + (size_t)l * len;
-        uint8_t n1, n2, n3;
-        if (!rc) {
-            n1 = row[pos]; n2 = row[pos + 1]; n3 = row[pos + 2];
-        } else {
-            n1 = nt_comp(row[len - 1 - pos]); n2 = nt_comp(row[len - 2 - pos]); n3 = nt_comp(row[len - 3 - pos]);
+    for (int t0 = 0; t0 < ncols; t0 += K0_COLS) {
+        const int tc = min(K0_COLS, ncols - t0);
+        for (int idx = threadIdx.x; idx < n_leaves * K0_COLS; idx += K0_THREADS) {
+            const int l = idx / K0_COLS, c = idx - l * K0_COLS;
+            if (c >= tc) continue;
+            const int pos = ofs + 3 * (t0 + c);
+            const uint8_t* row = base + (size_t)l * len;
+            uint8_t n1, n2, n3;
+            if (!rc) {
+                n1 = row[pos]; n2 = row[pos + 1]; n3 = row[pos + 2];
+            } else {
+                n1 = nt_comp(row[len - 1 - pos]); n2 = nt_comp(row[len - 2 - pos]); n3 = nt_comp(row[len - 3 - pos]);
+            }
+            const int i1 = nt_index(n1), i2 = nt_index(n2), i3 = nt_index(n3);
+            k0_tile[l * (K0_COLS + 1) + c] = (i1 < 0 || i2 < 0 || i3 < 0) ? (uint8_t)64 : (uint8_t)(16 * i1 + 4 * i2 + i3);
         }
-        const int i1 = nt_index(n1), i2 = nt_index(n2), i3 = nt_index(n3);
-        codes[(size_t)(c0 + c) * n_leaves + l] = (i1 < 0 || i2 < 0 || i3 < 0) ? (uint8_t)64 : (uint8_t)(16 * i1 + 4 * i2 + i3);
+        __syncthreads();
+        uint8_t* out = codes + (size_t)(c0 + t0) * n_leaves;
+        for (int idx = threadIdx.x; idx < tc * n_leaves; idx += K0_THREADS) {
+            const int c = idx / n_leaves, l = idx - c * n_leaves;
+            out[idx] = k0_tile[l * (K0_COLS + 1) + c];
+        }
+        __syncthreads();
     }
 }
 
