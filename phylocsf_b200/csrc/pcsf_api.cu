@@ -934,7 +934,7 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     CU(cudaMemcpyAsync(ctx->d_region_off.p, roff.data(), sizeof(int64_t) * (nregions + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev[7], ctx->stream));
     if (nregions > 0) {
-        frame_codes_kernel<<<(unsigned)nregions, K0_THREADS, (size_t)ctx->n_leaves * (K0_COLS + 1), ctx->stream>>>(
+        frame_codes_kernel<<<(unsigned)nregions, 128, 0, ctx->stream>>>(
             (const uint8_t*)ctx->d_nt.p, (const int64_t*)ctx->d_aln_off.p, (const int32_t*)ctx->d_aln_len.p,
             (const int64_t*)ctx->d_region_off.p, nregions, frames, ctx->n_leaves, (uint8_t*)ctx->d_codes.p);
         CU(cudaGetLastError());
@@ -1080,7 +1080,7 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
         CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
         // ---- compute stream: pleaves, pruning, reduction, results back ----
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-        frame_codes_kernel<<<(unsigned)nreg, K0_THREADS, (size_t)ctx->n_leaves * (K0_COLS + 1), ctx->stream>>>(
+        frame_codes_kernel<<<(unsigned)nreg, 128, 0, ctx->stream>>>(
             (const uint8_t*)ctx->pipe_nt[b].p, (const int64_t*)ctx->pipe_aln_off[b].p, (const int32_t*)ctx->pipe_aln_len[b].p,
             (const int64_t*)ctx->pipe_roff[b].p, nreg, frames, ctx->n_leaves, (uint8_t*)ctx->pipe_codes[b].p);
         CU(cudaGetLastError());

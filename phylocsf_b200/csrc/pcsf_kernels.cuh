@@ -1615,6 +1615,7 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
                 __syncthreads();
             }
             if (gacc) {  // G_i[a][b] += sum_c u[c][a] v[c][b], u = inter / z (columns with z > 0), v = alpha_i
+                const int i0 = i;
                 const double z = zs[c];
                 const bool live = c < ncols && z > 0.0;
 #pragma unroll
@@ -1629,18 +1630,32 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
                     for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = ai[j];
                 }
                 __syncthreads();
-                const int a = tid >> 2, b0 = (tid & 3) * 16;
-                double g[16];
+                // 4 x 4 register tile per thread: four u and four v loads feed sixteen FMAs (a 1 x 16 tile needed
+                // seventeen loads for the same work and sat on the shared-memory pipe: 67 % short-scoreboard stalls)
+                const int a0 = (tid >> 4) * 4, b0 = (tid & 15) * 4;
+                double g[4][4];
 #pragma unroll
-                for (int j = 0; j < 16; j++) g[j] = 0.0;
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) g[i][j] = 0.0;
+#pragma unroll 4
                 for (int cc = 0; cc < OUT_TC; cc++) {
-                    const double u = U[cc * OUT_XS + a];
+                    double u[4], v[4];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) g[j] = fma(u, X[cc * OUT_XS + b0 + j], g[j]);
+                    for (int i = 0; i < 4; i++) u[i] = U[cc * OUT_XS + a0 + i];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = X[cc * OUT_XS + b0 + j];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) g[i][j] = fma(u[i], v[j], g[i][j]);
                 }
-                double* G = gacc + (size_t)i * 4096 + a * 64 + b0;
 #pragma unroll
-                for (int j = 0; j < 16; j++) G[j] += g[j];
+                for (int i = 0; i < 4; i++) {
+                    double* G = gacc + (size_t)i0 * 4096 + (a0 + i) * 64 + b0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) G[j] += g[i][j];
+                }
                 __syncthreads();
             }
         }
@@ -1695,17 +1710,14 @@ __device__ __forceinline__ uint8_t nt_comp(uint8_t c) {  // Code.ml:39-51 (valid
     }
 }
 // region r = alignment a, frame f: columns at lo = f%3, strand = f/3 (src/PhyloCSF.ml:198-205,219-246)
-// One CTA per region, tiles of 32 codon columns: the nucleotides are read along the rows (a warp reads 96 consecutive
-// bytes of one species), the codes are written along the columns (consecutive leaves of one column), and a shared-memory
-// tile turns one order into the other - both sides of the kernel move whole sectors. (The first version read three
-// bytes per thread with a stride of one row between neighbouring threads: 410 GB/s, 5 % of the HBM peak; ncu,
-// profiles/r02_frame_codes_ncu_summary.json.)
-constexpr int K0_COLS = 32;
-constexpr int K0_THREADS = 256;
-__global__ void __launch_bounds__(K0_THREADS) frame_codes_kernel(const uint8_t* __restrict__ nt, const int64_t* __restrict__ aln_off,
-                                                                 const int32_t* __restrict__ aln_len, const int64_t* __restrict__ region_off,
-                                                                 int64_t nregions, int frames, int n_leaves, uint8_t* __restrict__ codes) {
-    extern __shared__ uint8_t k0_tile[];  // [n_leaves][K0_COLS + 1]
+// One CTA per region, one thread per (column, leaf). ncu (profiles/r02_frame_codes_ncu_summary.json): 482 us for 40,000
+// alignments x 3 frames, 117 MB read + 80 MB written = 410 GB/s, 6 % of the HBM peak - the kernel is bound by its
+// byte-granular load instructions (three LDG.U8 per code), not by sectors: a version that read along the rows and
+// transposed 32-column tiles through shared memory moved the same bytes in 613 us (two barriers per tile, the same byte
+// loads). K0 is 0.3 % of a fixed-strategy step; a faster one would decode 16-byte row chunks per thread.
+__global__ void frame_codes_kernel(const uint8_t* __restrict__ nt, const int64_t* __restrict__ aln_off,
+                                   const int32_t* __restrict__ aln_len, const int64_t* __restrict__ region_off,
+                                   int64_t nregions, int frames, int n_leaves, uint8_t* __restrict__ codes) {
     const int64_t r = blockIdx.x;
     if (r >= nregions) return;
     const int64_t a = r / frames;
@@ -1716,29 +1728,18 @@ __global__ void __launch_bounds__(K0_THREADS) frame_codes_kernel(const uint8_t* 
     const uint8_t* base = nt + aln_off[a];
     const int64_t c0 = region_off[r];
     const int ncols = (int)(region_off[r + 1] - c0);
-    for (int t0 = 0; t0 < ncols; t0 += K0_COLS) {
-        const int tc = min(K0_COLS, ncols - t0);
-        for (int idx = threadIdx.x; idx < n_leaves * K0_COLS; idx += K0_THREADS) {
-            const int l = idx / K0_COLS, c = idx - l * K0_COLS;
-            if (c >= tc) continue;
-            const int pos = ofs + 3 * (t0 + c);
-            const uint8_t* row = base + (size_t)l * len;
-            uint8_t n1, n2, n3;
-            if (!rc) {
-                n1 = row[pos]; n2 = row[pos + 1]; n3 = row[pos + 2];
-            } else {
-                n1 = nt_comp(row[len - 1 - pos]); n2 = nt_comp(row[len - 2 - pos]); n3 = nt_comp(row[len - 3 - pos]);
-            }
-            const int i1 = nt_index(n1), i2 = nt_index(n2), i3 = nt_index(n3);
-            k0_tile[l * (K0_COLS + 1) + c] = (i1 < 0 || i2 < 0 || i3 < 0) ? (uint8_t)64 : (uint8_t)(16 * i1 + 4 * i2 + i3);
+    for (int idx = threadIdx.x; idx < ncols * n_leaves; idx += blockDim.x) {
+        const int c = idx / n_leaves, l = idx - c * n_leaves;
+        const int pos = ofs + 3 * c;
+        const uint8_t* row = base + (size_t)l * len;
+        uint8_t n1, n2, n3;
+        if (!rc) {
+            n1 = row[pos]; n2 = row[pos + 1]; n3 = row[pos + 2];
+        } else {
+            n1 = nt_comp(row[len - 1 - pos]); n2 = nt_comp(row[len - 2 - pos]); n3 = nt_comp(row[len - 3 - pos]);
         }
-        __syncthreads();
-        uint8_t* out = codes + (size_t)(c0 + t0) * n_leaves;
-        for (int idx = threadIdx.x; idx < tc * n_leaves; idx += K0_THREADS) {
-            const int c = idx / n_leaves, l = idx - c * n_leaves;
-            out[idx] = k0_tile[l * (K0_COLS + 1) + c];
-        }
-        __syncthreads();
+        const int i1 = nt_index(n1), i2 = nt_index(n2), i3 = nt_index(n3);
+        codes[(size_t)(c0 + c) * n_leaves + l] = (i1 < 0 || i2 < 0 || i3 < 0) ? (uint8_t)64 : (uint8_t)(16 * i1 + 4 * i2 + i3);
     }
 }
 
