@@ -56,7 +56,11 @@ N *= REPEAT
 env = dict(os.environ, PHYLOCSF_BASE=base)
 t0 = time.perf_counter()
 wrap = os.environ.get("PCSF_NCU_WRAP", "").split()  # e.g. an ncu command line, for per-kernel time splits
-r = subprocess.run(wrap + [os.path.join(ROOT, "phylocsf_b200", "bin", "PhyloCSF"), pset, lst, "--files"] + flags, env=env, capture_output=True, text=True)
+if os.environ.get("PCSF_MULTI"):  # one process per GPU over the same list (tools/phylocsf_multi.py)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "phylocsf_multi.py"), "--gpus", os.environ["PCSF_MULTI"], pset, lst] + flags
+else:
+    cmd = wrap + [os.path.join(ROOT, "phylocsf_b200", "bin", "PhyloCSF"), pset, lst, "--files"] + flags
+r = subprocess.run(cmd, env=env, capture_output=True, text=True)
 dt = time.perf_counter() - t0
 lines = r.stdout.splitlines()
 print(json.dumps({"paramset": pset, "alignments": N, "codons": ncod, "flags": flags, "rc": r.returncode, "seconds": dt,

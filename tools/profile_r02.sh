@@ -9,7 +9,7 @@ parts=${@:-launches prune_sim prune_real k1 k5 k0 tables outside}
 for part in $parts; do
   case $part in
     launches)   # headline workload at full size: which kernels make up a step (cold-cache, serialised times: shares only)
-      ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/r02_launches.csv \
+      ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:prune|frame_codes|region_reduce|make_segments|pt_build|subtree_table' -c 200 --csv --log-file gpurun_out/r02_launches.csv \
         python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/r02_launches_bench.log 2>&1 ;;
     prune_sim)  # the headline kernel at the headline size (100,000 alignments, level-4 table program)
       $NCU_FULL -k regex:prune_wide -s 3 -c 1 -f -o gpurun_out/r02_prune_wide_tabled_100k \

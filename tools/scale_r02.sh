@@ -18,3 +18,9 @@ export PCSF_DEVICES=all PCSF_HOST_PROFILE=1
 python tools/bench_cli.py 58mammals 10000 100 100 -- --strategy=fixed --frames=3 > gpurun_out/r02_scale_cli_n$N.json 2> gpurun_out/r02_scale_cli_n$N.err
 python tools/bench_cli.py 58mammals 250 1667 4 -- --strategy=fixed --frames=6 > gpurun_out/r02_scale_cli_cfg5_n$N.json 2> gpurun_out/r02_scale_cli_cfg5_n$N.err
 cut -c1-700 gpurun_out/r02_scale_cli_n$N.json gpurun_out/r02_scale_cli_cfg5_n$N.json
+# 3. one process per GPU over the same list (tools/phylocsf_multi.py): the multi-GPU form of the command line that scales
+if [ "$N" -gt 1 ]; then
+  unset PCSF_DEVICES
+  PCSF_MULTI=$N python tools/bench_cli.py 58mammals 10000 100 100 -- --strategy=fixed --frames=3 > gpurun_out/r02_scale_cli_multi_n$N.json 2> gpurun_out/r02_scale_cli_multi_n$N.err
+  cut -c1-400 gpurun_out/r02_scale_cli_multi_n$N.json
+fi
