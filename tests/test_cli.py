@@ -378,3 +378,20 @@ def test_fast_reader_equals_general_reader_on_random_alignments(params_base, tmp
             assert (a.returncode, a.stdout) == (b.returncode, b.stdout), (f, flags, a.stdout, b.stdout)
             took_fast += "fast reader took 1 alignments" in a.stderr
     assert took_fast > 100  # the fast reader did take most of the well-formed ones
+
+
+def test_one_process_per_gpu_launcher_keeps_order(params_base, tmp_path):
+    """tools/phylocsf_multi.py (the list cut into contiguous shards, one command-line process per GPU, outputs
+    concatenated in input order) prints exactly what one process prints - checked without a GPU under --strategy=nop."""
+    import sys
+
+    files = [ex(params_base, "ALDH2.exon5.fa"), ex(params_base, "Aldh2.mRNA.fa")] * 5 + [ex(params_base, "ALDH2.exon5.fa")]
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(files) + "\n")
+    flags = ["--strategy=nop", "--frames=3", "--removeRefGaps", "--bls"]
+    one = run_cli(params_base, "29mammals", [str(lst)], "--files", *flags)
+    env = dict(os.environ, PHYLOCSF_BASE=params_base)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "phylocsf_multi.py"), "--gpus", "3", "29mammals", str(lst)] + flags,
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines() == one and len(one) == len(files)
