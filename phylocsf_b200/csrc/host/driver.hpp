@@ -69,6 +69,7 @@ struct ScoreRecord {
     enum DiagKind : uint8_t { D_NONE, D_FIXED, D_MLE, D_OMEGA } dk = D_NONE;
     double dv[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     std::string exn;  // non-empty: this region raised (Printexc text)
+    bool random_init = false;  // Fit.find_init took its random branch (PCSF_ST_RANDOM_INIT): the restated OCaml Random stream decided the start
 
     std::vector<std::pair<std::string, std::string>> diag() const {
         static const char* const kFixed[] = {"rho", "L(C)", "L(NC)"};
@@ -318,6 +319,7 @@ class DeviceScorer {
             rec[r].score = db(lpr[0][r] - lpr[1][r]);
             rec[r].anc_comp = db(elpr[0][r] - elpr[1][r]);
             rec[r].set_diag(ScoreRecord::D_MLE, {1.0, rho[0][r], rho[1][r], db(lpr[0][r]), db(lpr[1][r])});
+            rec[r].random_init = ((st[0][r] | st[1][r]) & PCSF_ST_RANDOM_INIT) != 0;
         }
     }
 
@@ -390,6 +392,9 @@ class DeviceScorer {
             if (opt.debug) {
                 out << "\t#";
                 for (auto& kv : s.diag()) out << " " << kv.first << "=" << kv.second;
+                // not part of the reference's report (stdout stays a drop-in): regions whose search started from
+                // Fit.find_init's random branch depend on the restated OCaml Random stream, which no reference test pins
+                if (s.random_init) std::cerr << j.name << "\t" << rg.lo << "\t" << rg.hi << "\tnote: find_init took its random branch (PCSF_ST_RANDOM_INIT)\n";
             }
             out << "\n";
         };
