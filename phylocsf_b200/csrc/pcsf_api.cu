@@ -445,9 +445,10 @@ int pt_build_jobs(pcsf_ctx* ctx, const std::vector<PtJob>& jobs, DevBuf& tables,
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     {
         const long long n_items = (long long)n * ctx->n_branches;
-        const int grid = (int)std::min<long long>(n_items, 2LL * ctx->num_sms);
-        pt_build_kernel<<<grid, 256, 0, ctx->stream>>>((const PtJob*)ctx->d_jobs.p, n_items, ctx->d_branch_len, ctx->n_branches,
-                                                       ctx->n_leaves, (double*)tables.p, (int32_t*)d_status.p, 1e-6);
+        const int grid = (int)std::min<long long>((n_items + 1) / 2, 2LL * ctx->num_sms);
+        CU(cudaFuncSetAttribute(pt_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
+        pt_build_kernel<<<grid, K1_THREADS, K1_SMEM, ctx->stream>>>((const PtJob*)ctx->d_jobs.p, n_items, ctx->d_branch_len, ctx->n_branches,
+                                                                   ctx->n_leaves, (double*)tables.p, (int32_t*)d_status.p, 1e-6);
         CU(cudaGetLastError());
         ctx->launches++;
         ctx->counters[0] += n_items;

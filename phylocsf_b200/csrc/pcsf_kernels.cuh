@@ -147,168 +147,145 @@ struct PtJob {               // one P set to build: a diagonalised model at one 
     const double* params;   // S | Sinv | lambda | prior | logprior (pcsf_api.cu: Model)
     double scale;
 };
-#ifndef PCSF_K1_ROWSUM_DMMA
-#define PCSF_K1_ROWSUM_DMMA 0
-#endif
-// Round-2 measurements on this kernel (33.4 M slots of the 120mammals mle benchmark; tools/bench_k1.py; the round-1
-// figure of 98 % of the DMMA peak divided by a slot count that was 1.5 x too high - it was 66 %):
-//   as in round 1 (64 exp by two warps right before the barrier, 16 + 16 adds and 16 FP64 compares per thread)   24.4 TFLOP/s
+// Round-2 measurements on this kernel (tools/bench_k1.py: 4.76 M slots = 20,000 candidate scales x 238 branches;
+// profiles/r02_k1_ablation.json; the round-1 figure of 98 % of the DMMA peak divided by a slot count that was 1.5 x too
+// high - it was 66 %):
+//   round 1: eight warps per slot, each 8 rows; 64 exp by two warps right before a per-slot barrier; 16 + 16 adds and
+//     16 FP64 compares per thread for the fix-ups                                                         24.4 TFLOP/s
 //   + sign test on the integer pipe, off-diagonal sum = row sum - P[i][i] unless the warp holds a negative entry,
-//     exponentials one item ahead, eight per warp (no global load between barrier and contraction)               26.5 TFLOP/s = 71 %
-//   row sum as a ninth n-tile on the tensor pipe instead of 16 adds (PCSF_K1_ROWSUM_DMMA=1)                        25.0 (12.5 % more DMMAs)
-//   timing-only ablations: no stores 29.9; no stores, no exp, no S diag(e) products 30.0 (81 %) - what is left is one
-//     LDS.64 per DMMA (LSU data pipe 54 % busy) and the barrier per slot; stores cost 11 %, the plain FP64 work nothing.
-//   a phased form (one CTA of 16 warps per SM, exponentials from a pre-pass kernel, two barriers per pair of slots so that
-//     the pipe sees either plain FP64 instructions or DMMAs) ran at 21.7: the idle pipe at the phase changes costs more
-//     than the contention it removes. Not kept.
-__global__ void __launch_bounds__(256, 2) pt_build_kernel(const PtJob* __restrict__ jobs, long long n_items,
-                                                          const double* __restrict__ branch_len, int n_branches,
-                                                          int n_leaves, double* __restrict__ tables,
-                                                          int32_t* __restrict__ status, double tol) {
-    __shared__ double Sinv_s[4096 + 512];  // fragment-ordered: [(j*16+s)*32 + lane] = Sinv[4s+t][8j+g]; n-tile 8: row sums of Sinv in column 0
-    __shared__ double e_s[2][64];
-    __shared__ double lam_s[64];
+//     exponentials one slot ahead, eight per warp                                                         26.5 = 71 %
+//   row sum as a ninth n-tile on the tensor pipe instead of 16 adds                                       25.0
+//   timing-only ablations of that form: no stores 29.9; no stores, no exp, no S diag(e) products 30.0 (81 %): what was
+//     left was one LDS.64 of S^-1 per DMMA (LSU data pipe 54 % busy) and the barrier per slot
+//   a phased form (one CTA of 16 warps per SM, exponentials from a pre-pass kernel, two barriers per pair of slots so
+//     that the pipe sees either plain FP64 instructions or DMMAs): 21.7 - the idle pipe at the phase changes costs more
+//     than the contention it removes
+//   this form: a warp owns 16 rows of a slot (four warps per slot, two slots per CTA step), so every S^-1 fragment it
+//     loads feeds two DMMAs; each warp computes the slot's 64 exponentials itself (two per lane) and keeps them in its
+//     own scratch line, so there is no barrier per slot at all - warps only meet when the model changes.
+constexpr int K1_THREADS = 256;
+constexpr int K1_SMEM = (4096 + 4096 + 64 + 8 * 64) * 8;  // S^-1 image, S image, lambda, per-warp exponentials
+__global__ void __launch_bounds__(K1_THREADS, 2) pt_build_kernel(const PtJob* __restrict__ jobs, long long n_items,
+                                                                 const double* __restrict__ branch_len, int n_branches,
+                                                                 int n_leaves, double* __restrict__ tables,
+                                                                 int32_t* __restrict__ status, double tol) {
+    extern __shared__ __align__(16) double k1sm[];
+    double* Sinv_s = k1sm;          // B fragments: [(j*16+s)*32 + lane] = Sinv[4s+t][8j+g]
+    double* S_s = k1sm + 4096;      // A fragments: [(m*16+s)*32 + lane] = S[8m+g][4s+t], m = block of 8 rows
+    double* lam_s = S_s + 4096;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const long long per = (n_items + gridDim.x - 1) / gridDim.x;
+    double* ew = lam_s + 64 + w * 64;  // this warp's exponentials
+    const int sub = w >> 2, rb = w & 3;  // which slot of the pair, which block of 16 rows
+    // contiguous runs of an even number of items: a pair of items never straddles two jobs (n_branches = 2n-2 is even)
+    long long per = (n_items + gridDim.x - 1) / gridDim.x;
+    per += per & 1;
     const long long lo = per * blockIdx.x, hi = min(n_items, lo + per);
-    if (lo >= hi) return;
     const double* cur_params = nullptr;
-    double afrag[16];  // S[8w+g][4s+t]
-    int buf = 0;
-    long long job_i = lo / n_branches;
-    int br = (int)(lo - job_i * n_branches);
-    PtJob job = jobs[job_i];
-    // The exponentials of an item are computed one item ahead, eight per warp (lanes 0-7), so that neither their
-    // global loads nor their ~40 dependent FP64 instructions sit between the barrier and the contraction.
-    if (lane < 8) e_s[0][8 * w + lane] = exp(job.scale * branch_len[br] * job.params[8192 + 8 * w + lane]);  // Q.ml:216-217
-    for (long long item = lo; item < hi; item++, buf ^= 1) {
-        const double tt = job.scale * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
+    for (long long pair = lo; pair < hi; pair += 2) {
+        const long long job_i = pair / n_branches;
+        const PtJob job = jobs[job_i];
         if (job.params != cur_params) {  // uniform across the CTA
-            __syncthreads();             // everybody is done reading the previous model's image
+            __syncthreads();             // everybody is done with the previous model's images
+            const double* S = job.params;
             const double* Sinv = job.params + 4096;
-            for (int idx = tid; idx < 4096; idx += 256) {
+            for (int idx = tid; idx < 4096; idx += K1_THREADS) {
                 const int l = idx & 31, s = (idx >> 5) & 15, j = idx >> 9;
                 Sinv_s[idx] = Sinv[(4 * s + (l & 3)) * 64 + 8 * j + (l >> 2)];
+                S_s[idx] = S[(8 * j + (l >> 2)) * 64 + 4 * s + (l & 3)];
             }
             if (tid < 64) lam_s[tid] = job.params[8192 + tid];
-#if PCSF_K1_ROWSUM_DMMA
-            for (int idx = tid; idx < 512; idx += 256) {
-                const int l = idx & 31, s = idx >> 5;
-                double r = 0.0;
-                if ((l >> 2) == 0) {
-                    const double* row = Sinv + (4 * s + (l & 3)) * 64;
-                    for (int j = 0; j < 64; j++) r += row[j];
-                }
-                Sinv_s[4096 + idx] = r;
-            }
-#endif
-#pragma unroll
-            for (int s = 0; s < 16; s++) afrag[s] = job.params[(8 * w + g) * 64 + 4 * s + t];
             cur_params = job.params;
+            __syncthreads();
         }
-        __syncthreads();  // e_s[buf] (and the image) visible; e_s[buf^1] is free for the next item
-        // the next item (same job's next branch, or the next job's first): its exponentials go into e_s[buf^1]
-        PtJob njob = job;
-        long long njob_i = job_i;
-        int nbr = br + 1;
-        if (nbr == n_branches) {
-            nbr = 0;
-            njob_i = job_i + 1;
-            if (item + 1 < hi) njob = jobs[njob_i];
-        }
-        if (item + 1 < hi && lane < 8) {
-            const double lam = njob.params == cur_params ? lam_s[8 * w + lane] : njob.params[8192 + 8 * w + lane];
-            e_s[buf ^ 1][8 * w + lane] = exp(njob.scale * branch_len[nbr] * lam);
-        }
-        double acc[8][2];
+        const long long item = pair + sub;
+        if (item >= hi) continue;
+        const int br = (int)(item - job_i * n_branches);
+        const double tt = job.scale * branch_len[br];  // Mul (Var 0, Val b), src/PhyloCSFModel.ml:33
+        __syncwarp();                                  // the previous slot's reads of ew are over
+        ew[lane] = exp(tt * lam_s[lane]);              // Q.ml:216-217
+        ew[lane + 32] = exp(tt * lam_s[lane + 32]);
+        __syncwarp();
+        double acc[2][8][2];
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j][0] = acc[j][1] = 0.0;
-#if PCSF_K1_ROWSUM_DMMA
-        double rs0 = 0.0, rs1 = 0.0;
-#endif
-        double a[16];  // S diag(e) (ptxas weaves these products into the DMMA stream, one per k-step, whatever the source order)
+        for (int m = 0; m < 2; m++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
 #pragma unroll
         for (int s = 0; s < 16; s++) {
-            a[s] = afrag[s] * e_s[buf][4 * s + t];
-        }
+            const double e = ew[4 * s + t];
+            const double a0 = S_s[((2 * rb) * 16 + s) * 32 + lane] * e, a1 = S_s[((2 * rb + 1) * 16 + s) * 32 + lane] * e;
 #pragma unroll
-        for (int s = 0; s < 16; s++) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) dmma(acc[j][0], acc[j][1], a[s], Sinv_s[(j * 16 + s) * 32 + lane]);
-#if PCSF_K1_ROWSUM_DMMA
-            dmma(rs0, rs1, a[s], Sinv_s[4096 + s * 32 + lane]);
-#endif
+            for (int j = 0; j < 8; j++) {
+                const double bf = Sinv_s[(j * 16 + s) * 32 + lane];
+                dmma(acc[0][j][0], acc[0][j][1], a0, bf);
+                dmma(acc[1][j][0], acc[1][j][1], a1, bf);
+            }
         }
-        // ---- fix-ups on row i = 8w+g, whose 64 entries sit in the quad's accumulators (Q.ml:226-247) ----
-        const int i = 8 * w + g;
+        // ---- fix-ups (Q.ml:226-247) on rows i = 16 rb + 8 m + g, whose 64 entries sit in the quad's accumulators ----
         int st = (tt < 0.0) ? 1 : 0;
-        bool neg = false;
+        double* out = tables + (size_t)item * PT_SLOT;
 #pragma unroll
-        for (int j = 0; j < 8; j++) neg |= (__double2hiint(acc[j][0]) < 0) | (__double2hiint(acc[j][1]) < 0);
-        double tot, off;
-#if PCSF_K1_ROWSUM_DMMA
-        tot = __shfl_sync(0xffffffffu, rs0, lane & ~3);  // D[g][0] of the ninth n-tile sits in lane t = 0 of the quad
-#else
-        tot = 0.0;
+        for (int m = 0; m < 2; m++) {
+            const int mt = 2 * rb + m, i = 8 * mt + g;
+            bool neg = false;
 #pragma unroll
-        for (int j = 0; j < 8; j++) tot += acc[j][0] + acc[j][1];
-        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-#endif
-        if (__any_sync(0xffffffffu, neg)) {  // rare: the reference's explicit pre-clamp / post-clamp sums
-            tot = 0.0;
-            off = 0.0;
+            for (int j = 0; j < 8; j++) neg |= (__double2hiint(acc[m][j][0]) < 0) | (__double2hiint(acc[m][j][1]) < 0);
+            double tot = 0.0, off;
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    double v = acc[j][e];
-                    tot += v;
-                    if (v < 0.0) {
-                        if (fabs(v) > tol) st |= 2;
-                        v = 0.0;
-                        acc[j][e] = 0.0;
-                    }
-                    if (8 * j + 2 * t + e != i) off += v;
-                }
+            for (int j = 0; j < 8; j++) tot += acc[m][j][0] + acc[m][j][1];
             tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-            off += __shfl_xor_sync(0xffffffffu, off, 1);
-            off += __shfl_xor_sync(0xffffffffu, off, 2);
-        } else {  // P[i][i] is entry (n-tile w, slot g & 1) of lane t = g >> 1
-            double pii = 0.0;
+            if (__any_sync(0xffffffffu, neg)) {  // rare: the reference's explicit pre-clamp / post-clamp sums
+                tot = 0.0;
+                off = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        double v = acc[m][j][e];
+                        tot += v;
+                        if (v < 0.0) {
+                            if (fabs(v) > tol) st |= 2;
+                            v = 0.0;
+                            acc[m][j][e] = 0.0;
+                        }
+                        if (8 * j + 2 * t + e != i) off += v;
+                    }
+                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                off += __shfl_xor_sync(0xffffffffu, off, 1);
+                off += __shfl_xor_sync(0xffffffffu, off, 2);
+            } else {  // P[i][i] is entry (n-tile mt, slot g & 1) of lane t = g >> 1
+                double pii = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (j == mt) pii = (g & 1) ? acc[m][j][1] : acc[m][j][0];
+                pii = __shfl_sync(0xffffffffu, pii, (lane & ~3) | (g >> 1));
+                off = tot - pii;
+            }
+            const double smii = 1.0 - off;
+            if (fabs(tot - 1.0) > tol) st |= 4;
+            if (!(smii <= 1.0 && smii > 0.0)) st |= 8;
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if (j == w) pii = (g & 1) ? acc[j][1] : acc[j][0];
-            pii = __shfl_sync(0xffffffffu, pii, (lane & ~3) | (g >> 1));
-            off = tot - pii;
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (8 * j + 2 * t + e == i) acc[m][j][e] = smii;
+            if (br < n_leaves) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) out[(8 * j + 2 * t + e) * 64 + i] = acc[m][j][e];
+                if (t == 0) out[4096 + i] = off + smii;  // ddot(row, ones): the `Marginalize leaf message
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) out[((mt * 16 + 2 * j + e) * 32) + lane] = acc[m][j][e];
+            }
         }
-        const double smii = 1.0 - off;
-        if (fabs(tot - 1.0) > tol) st |= 4;
-        if (!(smii <= 1.0 && smii > 0.0)) st |= 8;
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-#pragma unroll
-            for (int e = 0; e < 2; e++)
-                if (8 * j + 2 * t + e == i) acc[j][e] = smii;
         if (st) atomicOr(&status[job_i], st);
-        double* out = tables + (size_t)item * PT_SLOT;
-        if (br < n_leaves) {
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-#pragma unroll
-                for (int e = 0; e < 2; e++) out[(8 * j + 2 * t + e) * 64 + i] = acc[j][e];
-            if (t == 0) out[4096 + i] = off + smii;  // ddot(row, ones): the `Marginalize leaf message
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-#pragma unroll
-                for (int e = 0; e < 2; e++) out[((w * 16 + 2 * j + e) * 32) + lane] = acc[j][e];
-        }
-        job = njob;
-        job_i = njob_i;
-        br = nbr;
     }
 }
 

@@ -110,3 +110,19 @@ def test_bad_inputs_raise(tmp_path, params_base):
         open(str(tmp_path / ("x" + suf)), "w").write(txt)
     with pytest.raises(host.HostError, match="codon order"):
         host.ParamSet(str(tmp_path / "x"))
+
+
+def test_reemitted_parameter_files_hold_the_reference_tokens(params_base):
+    """tools/golden_params.py re-emits the packed parameter sets in the reference's formats with normalised blanks. Where
+    the reference tree is present (the build container), every token - each number as its original text, each Newick
+    string - must equal the shipped file's; elsewhere (GPU box) the test has nothing to compare with and is skipped."""
+    ref = "/root/reference/PhyloCSF_Parameters"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    mine = os.path.join(params_base, "PhyloCSF_Parameters")
+    names = sorted(f for f in os.listdir(ref) if f.endswith((".nh", ".ECM")))
+    assert len(names) == 42 and sorted(os.listdir(mine)) == names
+    for f in names:
+        a = open(os.path.join(ref, f)).read().split()
+        b = open(os.path.join(mine, f)).read().split()
+        assert a == b, f

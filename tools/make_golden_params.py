@@ -8,7 +8,10 @@ Run in the build container only:  python tools/make_golden_params.py [/root/refe
 What it writes (data only, no reference source code):
   tests/golden/phylocsf_parameters.json  - all 14 PhyloCSF_Parameters sets; ECMs de-duplicated
                                            by content hash; numbers kept as their original text
-                                           tokens so a byte-faithful .ECM/.nh can be re-emitted
+                                           tokens, so the re-emitted .ECM / .nh hold exactly the
+                                           reference's tokens (blanks are normalised: 33 of the 42
+                                           files differ from the originals in whitespace only;
+                                           tests/test_host_model.py pins the token identity)
   tests/golden/examples.json             - the three PhyloCSF_Examples/*.fa alignments
                                            (raw header text + sequence per row)
 Formats: SURVEY.md Appendix B (src/ECM.ml:18-72, lib/CamlPaml/NewickLexer.mll:5-14).
