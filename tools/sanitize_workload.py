@@ -4,7 +4,8 @@
 29mammals, regions of 200/130/17/0/64 columns: pcsf_lpr_all in the narrow and the wide form (two scales,
 both models), PCSF_OPT_RESCALE in both forms, pcsf_maximize_lpr_multi, the omega entry points
 (pcsf_omega_models_set + pcsf_pt_build_pairs + pcsf_lpr_pairs), pcsf_score_alignments and
-pcsf_batch_upload_alignments_parts (6 frames). Results are checked against the oracle where it is cheap."""
+pcsf_batch_upload_alignments_parts (6 frames); round 2: pcsf_omega_models_set_cached (warm starts), pcsf_posteriors (K6),
+pcsf_omega_score. Results are checked against the oracle where it is cheap."""
 import os
 import sys
 import tempfile
@@ -57,5 +58,19 @@ a = ctx.score_alignments(aoff, [L, L], flat, 6, [0, 1])
 ctx.batch_upload_alignments_parts(aoff, [L, L], [flat[: n * L], flat[n * L:]], 6)
 b = ctx.lpr_all([0, 1])
 assert np.array_equal(a[0], b[0], equal_nan=True)
+# round 2: K5 with warm starts (one-pass rotations), K6 (outside algorithm + expected counts), the omega strategy in one call
+ctx.omega_cache_reset(3)
+for kappa in (2.5, 2.7, 2.71):
+    q2 = qs.copy()
+    q2[:, 0] = kappa
+    ctx.omega_models_set_cached(4, q2, [0, 1, 2])
+ctx.batch_upload(off, codes)
+ctx.pt_build(0, [1.0])
+post, ec, z = ctx.posteriors(0, 0, nodes=[2 * n - 2, n, 0])
+zo, po, eo2 = o.posteriors_columns(mc, codes[:40])
+assert np.allclose(z[:40], zo, rtol=1e-10) and np.allclose(post[0][:40], po[:, 2 * n - 2], atol=1e-11)
+from phylocsf_b200 import host  # noqa: E402
+sc, dg, st = host.omega_score(ctx, off[:3], codes[: off[2]])
+assert (st == 0).all() and np.isfinite(sc).all()
 ctx.close()
 print("sanitize workload ok")
