@@ -31,33 +31,36 @@ ctx.pt_build(1, [1.0, 0.5])
 off, codes = H.regions_to_batch(regs)
 ctx.batch_upload(off, codes)
 lo, eo = H.oracle_fixed(ps, regs)
-res = {}
-for form in (1, 2):
-    ctx.option_set(2, form)
-    for rescale in (0, 1):
-        ctx.option_set(1, rescale)
-        lpr, elpr, st = ctx.lpr_all([0, 1])
-        assert np.abs(H.DB * (lpr - lo)).max() < 1e-7
-        res[(form, rescale)] = lpr
-        ctx.lpr_all([0, 1], scale_idx=[1, 1])
-assert (res[(1, 0)] == res[(2, 0)]).all()
-ctx.option_set(1, 0)
-ctx.option_set(2, 0)
-ctx.maximize_lpr_multi([0, 1])
+ONLY_NEW = os.environ.get("PCSF_SAN_ONLY") == "round2"  # racecheck: K1 / K5 / K6 only (the pruning kernels take hours under it)
 qs = np.tile(np.array([2.5, 1.0, 1.0] + [1.0] * 9), (3, 1))
-ctx.omega_models_set(4, qs)
-ctx.pt_build_pairs([4, 5, 6], [1.0, 0.7, 1.3])
-ctx.lpr_pairs([0, 1, 2], [0, 1, 2])
-L = 93
-nt = np.frombuffer(b"ACGTacgtN-", dtype=np.uint8)[rng.integers(0, 10, size=(2, n, L))]
-flat = nt.reshape(-1)
-aoff = np.array([0, n * L], dtype=np.int64)
-ctx.pt_build(0, [1.0])
-ctx.pt_build(1, [1.0])
-a = ctx.score_alignments(aoff, [L, L], flat, 6, [0, 1])
-ctx.batch_upload_alignments_parts(aoff, [L, L], [flat[: n * L], flat[n * L:]], 6)
-b = ctx.lpr_all([0, 1])
-assert np.array_equal(a[0], b[0], equal_nan=True)
+if not ONLY_NEW:
+    res = {}
+    for form in (1, 2):
+        ctx.option_set(2, form)
+        for rescale in (0, 1):
+            ctx.option_set(1, rescale)
+            lpr, elpr, st = ctx.lpr_all([0, 1])
+            assert np.abs(H.DB * (lpr - lo)).max() < 1e-7
+            res[(form, rescale)] = lpr
+            ctx.lpr_all([0, 1], scale_idx=[1, 1])
+    assert (res[(1, 0)] == res[(2, 0)]).all()
+    ctx.option_set(1, 0)
+    ctx.option_set(2, 0)
+    ctx.maximize_lpr_multi([0, 1])
+    qs = np.tile(np.array([2.5, 1.0, 1.0] + [1.0] * 9), (3, 1))
+    ctx.omega_models_set(4, qs)
+    ctx.pt_build_pairs([4, 5, 6], [1.0, 0.7, 1.3])
+    ctx.lpr_pairs([0, 1, 2], [0, 1, 2])
+    L = 93
+    nt = np.frombuffer(b"ACGTacgtN-", dtype=np.uint8)[rng.integers(0, 10, size=(2, n, L))]
+    flat = nt.reshape(-1)
+    aoff = np.array([0, n * L], dtype=np.int64)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    a = ctx.score_alignments(aoff, [L, L], flat, 6, [0, 1])
+    ctx.batch_upload_alignments_parts(aoff, [L, L], [flat[: n * L], flat[n * L:]], 6)
+    b = ctx.lpr_all([0, 1])
+    assert np.array_equal(a[0], b[0], equal_nan=True)
 # round 2: K5 with warm starts (one-pass rotations), K6 (outside algorithm + expected counts), the omega strategy in one call
 ctx.omega_cache_reset(3)
 for kappa in (2.5, 2.7, 2.71):
@@ -70,7 +73,8 @@ post, ec, z = ctx.posteriors(0, 0, nodes=[2 * n - 2, n, 0])
 zo, po, eo2 = o.posteriors_columns(mc, codes[:40])
 assert np.allclose(z[:40], zo, rtol=1e-10) and np.allclose(post[0][:40], po[:, 2 * n - 2], atol=1e-11)
 from phylocsf_b200 import host  # noqa: E402
-sc, dg, st = host.omega_score(ctx, off[:3], codes[: off[2]])
-assert (st == 0).all() and np.isfinite(sc).all()
+if not ONLY_NEW:
+    sc, dg, st = host.omega_score(ctx, off[:3], codes[: off[2]])
+    assert (st == 0).all() and np.isfinite(sc).all()
 ctx.close()
 print("sanitize workload ok")
