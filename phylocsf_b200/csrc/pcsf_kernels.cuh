@@ -162,7 +162,10 @@ struct PtJob {               // one P set to build: a diagonalised model at one 
 //     than the contention it removes
 //   this form: a warp owns 16 rows of a slot (four warps per slot, two slots per CTA step), so every S^-1 fragment it
 //     loads feeds two DMMAs; each warp computes the slot's 64 exponentials itself (two per lane) and keeps them in its
-//     own scratch line, so there is no barrier per slot at all - warps only meet when the model changes.
+//     own scratch line, so there is no barrier per slot at all - warps only meet when the model changes.       30.5 = 82 %
+//   the same with the rows leaving through a per-warp staging line and cp.async.bulk shared -> global (one 8 KB copy
+//     per warp for an internal slot, 64 copies of 128 B for a leaf slot; one CTA of 16 warps per SM): 29.6 - the
+//     stores are not what limits this form. Not kept.
 constexpr int K1_THREADS = 256;
 constexpr int K1_SMEM = (4096 + 4096 + 64 + 8 * 64) * 8;  // S^-1 image, S image, lambda, per-warp exponentials
 __global__ void __launch_bounds__(K1_THREADS, 2) pt_build_kernel(const PtJob* __restrict__ jobs, long long n_items,
