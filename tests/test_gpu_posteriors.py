@@ -31,7 +31,7 @@ def _check(ps, regs, rho=1.0, models=(0, 1)):
         par = np.zeros(t.size, dtype=int)
         for i in range(t.n_leaves, t.size):
             par[t.children[i][0]] = par[t.children[i][1]] = i
-        for br in (0, t.n_leaves, t.size - 2):
+        for br in sorted({0, min(t.n_leaves, t.size - 2), t.size - 2}):
             np.testing.assert_allclose(ec[br].sum(axis=1), post[par[br]].sum(axis=0), atol=1e-9)
             if br >= t.n_leaves:  # (a marginalised leaf's node_posterior is its all-ones leaf vector, not a distribution)
                 np.testing.assert_allclose(ec[br].sum(axis=0), post[br].sum(axis=0), atol=1e-9)
@@ -79,4 +79,25 @@ def test_posteriors_impossible_columns_are_zero(params_base):
     np.testing.assert_allclose(ec, eo, atol=1e-10)
     with pytest.raises(Exception):
         ctx.posteriors(0, 0, nodes=[239])
+    ctx.close()
+
+
+@pytest.mark.parametrize("species", [["dmel", "dvir"], ["dmel", "dana", "dvir"], ["dmel", "dsim", "dsec", "dyak", "dere"]])
+def test_posteriors_tiny_trees_and_ragged_tiles(params_base, species):
+    """Two-, three- and five-leaf trees (a root cherry has no internal non-root node; three leaves have one) and column
+    counts around the kernel's 32-column tiles (1, 31, 32, 33, 0 columns)."""
+    ps = H.oracle_paramset(params_base, "12flies", species=species)
+    rng = np.random.default_rng(4)
+    n = len(species)
+    regs = [rng.integers(0, 65, size=(c, n)).astype(np.uint8) for c in (1, 31, 0, 32, 33)]
+    _check(ps, regs, rho=0.8, models=(0,))
+
+
+def test_posteriors_empty_batch(params_base):
+    ps = H.oracle_paramset(params_base, "12flies")
+    ctx = H.make_context(ps)
+    ctx.batch_upload(np.array([0, 0], dtype=np.int64), np.zeros((0, 12), dtype=np.uint8))
+    ctx.pt_build(0, [1.0])
+    post, ec, z = ctx.posteriors(0, 0, nodes=[22, 3])
+    assert post.shape == (2, 0, 64) and z.size == 0 and (ec == 0).all()
     ctx.close()
