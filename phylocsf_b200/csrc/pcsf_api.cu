@@ -1407,9 +1407,9 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
         sib[r] = l;
     }
     const int64_t n_tiles = (total + OUT_TC - 1) / OUT_TC;
-    // three CTAs per SM (70 KB of shared memory each): the walk is a chain of short products separated by barriers, so
+    // two CTAs per SM (~105 KB of shared memory each): the walk is a chain of short products separated by barriers, so
     // co-resident CTAs are what hides its latencies
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 3LL * ctx->num_sms));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 2LL * ctx->num_sms));
     TRY(reserve(ctx, ctx->d_out_tree, tree.size() * sizeof(int32_t)));
     TRY(reserve(ctx, ctx->d_out_scratch, sizeof(double) * (size_t)grid * 3 * ni * OUT_TC * 64));
     if (out_ecounts) {

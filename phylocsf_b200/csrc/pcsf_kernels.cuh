@@ -1448,7 +1448,7 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
 //     (lib/CamlPaml/PhyloLik.ml:96-180: ensure_beta, node_posterior, add_branch_posteriors)
 // =================================================================================================
 // Not on the scoring path of the command line: this is the E step PhyloEM-style ECM training needs.
-// One CTA walks tiles of 32 codon columns. Per tile, with msg_i = P_i x alpha_i the message of node i to its parent
+// CTAs walk tiles of 64 codon columns. Per tile, with msg_i = P_i x alpha_i the message of node i to its parent
 // (a leaf's message is a row of its P^T table, as in the pruning kernels):
 //   inside   (i ascending, internal nodes): alpha_i = msg_lc * msg_rc; msg_i kept for the way down
 //   root:    z = alpha_root . prior; beta_root = prior
@@ -1460,7 +1460,7 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
 // Every 64 x 64 product runs on the plain FP64 pipe as Y[c][o] = sum_k X[c][k] L[k][o] with L staged in shared memory in
 // the orientation the product needs (B200's plain-FP64 peak equals its DMMA peak, and this kernel is bound by the L2
 // traffic of its scratch blocks, not by arithmetic).
-constexpr int OUT_TC = 32;          // columns per tile
+constexpr int OUT_TC = 64;          // columns per tile
 constexpr int OUT_THREADS = 256;
 constexpr int OUT_XS = 65;          // padded row stride of the column-major operand tiles
 struct OutsideParams {
@@ -1484,26 +1484,32 @@ __device__ __forceinline__ double out_p_entry(const double* slot, bool leaf, int
     return leaf ? slot[b * 64 + a] : slot[frag_index(a, b)];  // leaf slots hold P^T, internal ones the fragment-ordered image
 }
 
-// Y[c][o] = sum_k X[c][k] * L[k][o] for the tile's 32 columns; thread -> column tid / 8, outputs 8 (tid % 8) .. + 7
-__device__ __forceinline__ void out_product(const double* __restrict__ X, const double* __restrict__ L, double (&y)[8], int tid) {
-    const int c = tid >> 3, o0 = (tid & 7) * 8;
+// Y[c][o] = sum_k X[c][k] * L[k][o] for the tile's 64 columns; thread -> columns 2 (tid / 8), + 1 and outputs
+// 8 (tid % 8) .. + 7: two X loads and four 16-byte loads of L feed sixteen FMAs
+__device__ __forceinline__ void out_product(const double* __restrict__ X, const double* __restrict__ L, double (&y)[2][8], int tid) {
+    const int c0 = (tid >> 3) * 2, o0 = (tid & 7) * 8;
 #pragma unroll
-    for (int j = 0; j < 8; j++) y[j] = 0.0;
-    const double* x = X + c * OUT_XS;
-#pragma unroll 8
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) y[i][j] = 0.0;
+    const double* x0 = X + c0 * OUT_XS;
+    const double* x1 = x0 + OUT_XS;
+#pragma unroll 4
     for (int k = 0; k < 64; k++) {
-        const double xv = x[k];
+        const double xa = x0[k], xb = x1[k];
         const double2* l = reinterpret_cast<const double2*>(L + k * 64 + o0);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const double2 v = l[j];
-            y[2 * j] = fma(xv, v.x, y[2 * j]);
-            y[2 * j + 1] = fma(xv, v.y, y[2 * j + 1]);
+            y[0][2 * j] = fma(xa, v.x, y[0][2 * j]);
+            y[0][2 * j + 1] = fma(xa, v.y, y[0][2 * j + 1]);
+            y[1][2 * j] = fma(xb, v.x, y[1][2 * j]);
+            y[1][2 * j + 1] = fma(xb, v.y, y[1][2 * j + 1]);
         }
     }
 }
 
-__global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParams p) {
+__global__ void __launch_bounds__(OUT_THREADS, 2) outside_kernel(const OutsideParams p) {
     extern __shared__ __align__(16) double osm[];
     double* L = osm;                      // 64 x 64 operand matrix
     double* X = L + 4096;                 // OUT_TC x OUT_XS
@@ -1511,7 +1517,7 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
     double* zs = U + OUT_TC * OUT_XS;     // OUT_TC
     uint8_t* codes_s = reinterpret_cast<uint8_t*>(zs + OUT_TC);  // OUT_TC x n_leaves
     const int tid = threadIdx.x, nl = p.n_leaves, n = 2 * nl - 1, ni = nl - 1;
-    const int c = tid >> 3, o0 = (tid & 7) * 8;
+    const int c0 = (tid >> 3) * 2, o0 = (tid & 7) * 8;  // this thread's two columns and eight states
     double* sc = p.scratch + (size_t)blockIdx.x * 3 * ni * OUT_TC * 64;
     auto alpha_at = [&](int node) { return sc + ((size_t)(node - nl) * OUT_TC) * 64; };
     auto msg_at = [&](int node) { return sc + ((size_t)(ni + node - nl) * OUT_TC) * 64; };
@@ -1519,26 +1525,37 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
     double* gacc = p.gacc ? p.gacc + (size_t)blockIdx.x * (n - 1) * 4096 : nullptr;
     if (gacc)
         for (size_t i = tid; i < (size_t)(n - 1) * 4096; i += OUT_THREADS) gacc[i] = 0.0;
-    // message of node `node` for this thread's (column, 8 states): a leaf gathers its P^T row, an internal node reads msg
-    auto load_msg = [&](int node, double (&m)[8]) {
-        if (node < nl) {
-            int code = codes_s[c * nl + node];
-            code = code > 64 ? 64 : code;
-            const double* row = p.tables + (size_t)node * PT_SLOT + code * 64 + o0;
+    // message of node `node` for this thread's (columns, 8 states): a leaf gathers its P^T row, an internal node reads msg
+    auto load_msg = [&](int node, double (&m)[2][8]) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) m[j] = row[j];
-        } else {
-            const double* row = msg_at(node) + c * 64 + o0;
+        for (int i = 0; i < 2; i++) {
+            const double* row;
+            if (node < nl) {
+                int code = codes_s[(c0 + i) * nl + node];
+                code = code > 64 ? 64 : code;
+                row = p.tables + (size_t)node * PT_SLOT + code * 64 + o0;
+            } else {
+                row = msg_at(node) + (c0 + i) * 64 + o0;
+            }
 #pragma unroll
-            for (int j = 0; j < 8; j++) m[j] = row[j];
+            for (int j = 0; j < 8; j++) m[i][j] = row[j];
         }
     };
-    auto stage_L = [&](int node, bool transposed) {  // L[k][o] = P[o][k] (inside) or P[k][o] (outside)
+    // L[k][o] = P[o][k] (inside pass) or P[k][o] (outside pass): the slot is read linearly (coalesced) and scattered
+    auto stage_L = [&](int node, bool transposed) {
         const double* slot = p.tables + (size_t)node * PT_SLOT;
         const bool leaf = node < nl;
-        for (int i = tid; i < 4096; i += OUT_THREADS) {
-            const int k = i >> 6, o = i & 63;
-            L[i] = transposed ? out_p_entry(slot, leaf, o, k) : out_p_entry(slot, leaf, k, o);
+        for (int idx = tid; idx < 4096; idx += OUT_THREADS) {
+            int a, b;
+            if (leaf) {
+                a = idx & 63;
+                b = idx >> 6;
+            } else {  // inverse of frag_index
+                const int j = idx >> 9, s = (idx >> 5) & 15, ln = idx & 31;
+                a = 8 * j + (ln >> 2);
+                b = 8 * (s >> 1) + 2 * (ln & 3) + (s & 1);
+            }
+            L[transposed ? b * 64 + a : a * 64 + b] = slot[idx];
         }
     };
     const int64_t n_tiles = (p.total_cols + OUT_TC - 1) / OUT_TC;
@@ -1550,23 +1567,27 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
         __syncthreads();
         // ---------------- inside ----------------
         for (int i = nl; i < n; i++) {
-            double ml[8], mr[8], a[8];
+            double ml[2][8], mr[2][8];
             load_msg(p.children[2 * (i - nl)], ml);
             load_msg(p.children[2 * (i - nl) + 1], mr);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                a[j] = ml[j] * mr[j];
-                alpha_at(i)[c * 64 + o0 + j] = a[j];
-                X[c * OUT_XS + o0 + j] = a[j];
-            }
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double a = ml[q][j] * mr[q][j];
+                    alpha_at(i)[(c0 + q) * 64 + o0 + j] = a;
+                    X[(c0 + q) * OUT_XS + o0 + j] = a;
+                }
             if (i == n - 1) break;
             stage_L(i, true);
             __syncthreads();
-            double y[8];
+            double y[2][8];
             out_product(X, L, y, tid);
 #pragma unroll
-            for (int j = 0; j < 8; j++) msg_at(i)[c * 64 + o0 + j] = y[j];
-            __syncthreads();  // msg_i visible to the CTA (global, same-CTA readers), L and X free again
+            for (int q = 0; q < 2; q++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) msg_at(i)[(c0 + q) * 64 + o0 + j] = y[q][j];
+            __syncthreads();  // L and X free again (msg_i is only ever read back by the thread that wrote it)
         }
         // ---------------- root ----------------
         __syncthreads();
@@ -1577,41 +1598,54 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
             if (p.z_out && tid < ncols) p.z_out[col0 + tid] = z;
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) beta_at(n - 1)[c * 64 + o0 + j] = p.prior[o0 + j];
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) beta_at(n - 1)[(c0 + q) * 64 + o0 + j] = p.prior[o0 + j];
         __syncthreads();
         // ---------------- outside + expected counts, node by node from the top ----------------
         for (int i = n - 2; i >= 0; i--) {
             const int par = p.parent[i], sib = p.sibling[i];
-            double ms[8], inter[8];
+            double ms[2][8], inter[2][8];
             load_msg(sib, ms);
-            const double* bp = beta_at(par) + c * 64 + o0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) inter[j] = bp[j] * ms[j];
+            for (int q = 0; q < 2; q++) {
+                const double* bp = beta_at(par) + (c0 + q) * 64 + o0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) inter[q][j] = bp[j] * ms[q][j];
+            }
             if (i >= nl) {  // beta_i[b] = sum_a inter[a] P_i[a][b]
 #pragma unroll
-                for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = inter[j];
+                for (int q = 0; q < 2; q++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) X[(c0 + q) * OUT_XS + o0 + j] = inter[q][j];
                 stage_L(i, false);
                 __syncthreads();
-                double y[8];
+                double y[2][8];
                 out_product(X, L, y, tid);
 #pragma unroll
-                for (int j = 0; j < 8; j++) beta_at(i)[c * 64 + o0 + j] = y[j];
+                for (int q = 0; q < 2; q++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) beta_at(i)[(c0 + q) * 64 + o0 + j] = y[q][j];
                 __syncthreads();
             }
             if (gacc) {  // G_i[a][b] += sum_c u[c][a] v[c][b], u = inter / z (columns with z > 0), v = alpha_i
                 const int i0 = i;
-                const double z = zs[c];
-                const bool live = c < ncols && z > 0.0;
 #pragma unroll
-                for (int j = 0; j < 8; j++) U[c * OUT_XS + o0 + j] = live ? inter[j] / z : 0.0;
-                if (i < nl) {
-                    const int code = codes_s[c * nl + i];
+                for (int q = 0; q < 2; q++) {
+                    const int c = c0 + q;
+                    const double z = zs[c];
+                    const bool live = c < ncols && z > 0.0;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = (code >= 64 || code == o0 + j) ? 1.0 : 0.0;
-                } else {
-                    const double* ai = alpha_at(i) + c * 64 + o0;
+                    for (int j = 0; j < 8; j++) U[c * OUT_XS + o0 + j] = live ? inter[q][j] / z : 0.0;
+                    if (i < nl) {
+                        const int code = codes_s[c * nl + i];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = ai[j];
+                        for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = (code >= 64 || code == o0 + j) ? 1.0 : 0.0;
+                    } else {
+                        const double* ai = alpha_at(i) + c * 64 + o0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) X[c * OUT_XS + o0 + j] = ai[j];
+                    }
                 }
                 __syncthreads();
                 // 4 x 4 register tile per thread: four u and four v loads feed sixteen FMAs (a 1 x 16 tile needed
@@ -1619,26 +1653,26 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
                 const int a0 = (tid >> 4) * 4, b0 = (tid & 15) * 4;
                 double g[4][4];
 #pragma unroll
-                for (int i = 0; i < 4; i++)
+                for (int ii = 0; ii < 4; ii++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) g[i][j] = 0.0;
+                    for (int j = 0; j < 4; j++) g[ii][j] = 0.0;
 #pragma unroll 4
                 for (int cc = 0; cc < OUT_TC; cc++) {
                     double u[4], v[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) u[i] = U[cc * OUT_XS + a0 + i];
+                    for (int ii = 0; ii < 4; ii++) u[ii] = U[cc * OUT_XS + a0 + ii];
 #pragma unroll
                     for (int j = 0; j < 4; j++) v[j] = X[cc * OUT_XS + b0 + j];
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                    for (int ii = 0; ii < 4; ii++)
 #pragma unroll
-                        for (int j = 0; j < 4; j++) g[i][j] = fma(u[i], v[j], g[i][j]);
+                        for (int j = 0; j < 4; j++) g[ii][j] = fma(u[ii], v[j], g[ii][j]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    double* G = gacc + (size_t)i0 * 4096 + (a0 + i) * 64 + b0;
+                for (int ii = 0; ii < 4; ii++) {
+                    double* G = gacc + (size_t)i0 * 4096 + (a0 + ii) * 64 + b0;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) G[j] += g[i][j];
+                    for (int j = 0; j < 4; j++) G[j] += g[ii][j];
                 }
                 __syncthreads();
             }
@@ -1646,18 +1680,22 @@ __global__ void __launch_bounds__(OUT_THREADS) outside_kernel(const OutsideParam
         // ---------------- node posteriors (PhyloLik.ml:127-138) ----------------
         for (int q = 0; q < p.n_post; q++) {
             const int node = p.post_nodes[q];
-            if (c >= ncols) continue;
-            double* out = p.post_out + ((size_t)q * p.total_cols + col0 + c) * 64 + o0;
-            const double z = zs[c];
-            if (node < nl) {
-                const int code = codes_s[c * nl + node];
 #pragma unroll
-                for (int j = 0; j < 8; j++) out[j] = z == 0.0 ? 0.0 : ((code >= 64 || code == o0 + j) ? 1.0 : 0.0);
-            } else {
-                const double* ai = alpha_at(node) + c * 64 + o0;
-                const double* bi = beta_at(node) + c * 64 + o0;
+            for (int r = 0; r < 2; r++) {
+                const int c = c0 + r;
+                if (c >= ncols) continue;
+                double* out = p.post_out + ((size_t)q * p.total_cols + col0 + c) * 64 + o0;
+                const double z = zs[c];
+                if (node < nl) {
+                    const int code = codes_s[c * nl + node];
 #pragma unroll
-                for (int j = 0; j < 8; j++) out[j] = z == 0.0 ? 0.0 : ai[j] * bi[j] / z;
+                    for (int j = 0; j < 8; j++) out[j] = z == 0.0 ? 0.0 : ((code >= 64 || code == o0 + j) ? 1.0 : 0.0);
+                } else {
+                    const double* ai = alpha_at(node) + c * 64 + o0;
+                    const double* bi = beta_at(node) + c * 64 + o0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) out[j] = z == 0.0 ? 0.0 : ai[j] * bi[j] / z;
+                }
             }
         }
     }
