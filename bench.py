@@ -580,34 +580,66 @@ def run_omega(args, env):
     off = np.zeros(len(regs) + 1, dtype=np.int64)
     off[1:] = np.cumsum([r.shape[0] for r in regs])
     codes = np.concatenate(regs, axis=0)
+    # --omega-contexts N > 1: N scoring contexts on the one GPU, each with a share of the regions and a host thread of its
+    # own (what the command line does with its batches). Measured slower than one context for this strategy, see --help.
+    import threading
+
+    ncx = max(1, args.omega_contexts)
+    ctxs = [ctx] + [pb.Context(env["local_rank"]) for _ in range(ncx - 1)]
+    for c in ctxs[1:]:
+        ps.install(c)
+    R = len(regs)
+    cuts = [R * k // ncx for k in range(ncx + 1)]
+    parts = []
+    for k in range(ncx):
+        o_k = off[cuts[k]:cuts[k + 1] + 1] - off[cuts[k]]
+        parts.append((np.ascontiguousarray(o_k), np.ascontiguousarray(codes[off[cuts[k]]:off[cuts[k + 1]]])))
     # warm-up on a slice, then the timed pass over everything
-    w = min(len(regs), 90)
-    host.omega_score(ctx, off[: w + 1], codes[: off[w]])
-    ctx.total_ms(reset=True)
-    ctx.counters(reset=True)
-    l0 = ctx.launch_count
+    w = min(R // ncx, 90)
+    for c, (o_k, c_k) in zip(ctxs, parts):
+        host.omega_score(c, o_k[: w + 1], c_k[: o_k[w]])
+    for c in ctxs:
+        c.total_ms(reset=True)
+        c.counters(reset=True)
+    l0 = sum(c.launch_count for c in ctxs)
+    out = [None] * ncx
+
+    def work(k):
+        out[k] = host.omega_score(ctxs[k], parts[k][0], parts[k][1])
+
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    score, diag, st = host.omega_score(ctx, off, codes)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(ncx)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    ms = ctx.total_ms()
-    cnt = ctx.counters()
+    score = np.concatenate([o_[0] for o_ in out])
+    diag = np.concatenate([o_[1] for o_ in out])
+    st = np.concatenate([o_[2] for o_ in out])
+    ms = {k: sum(c.total_ms()[k] for c in ctxs) for k in ctxs[0].total_ms()}
+    cnt = {k: sum(c.counters()[k] for c in ctxs) for k in ctxs[0].counters()}
+    launches = sum(c.launch_count for c in ctxs) - l0
     peak, _ = dmma_peak_tflops()
     n = ps.n_leaves
     res = {"workload": "100vertebrates omega, --allScores --frames=3: %d exon-length alignments (median %d nt) = %d regions, %d codon columns"
                        % (N, int(np.median(lens) * 3), len(regs), int(off[-1])),
            "alignments_per_s": N / dt, "regions_per_s": len(regs) / dt, "seconds": dt, "device_ms": ms,
            "device_share_of_wall": (ms["prune"] + ms["reduce"] + ms["pt_build"] + ms["omega_eig"]) / (dt * 1e3),
-           "gpu_launches": ctx.launch_count - l0, "failed_regions": int((st != 0).sum()), "counters": cnt,
+           "scoring_contexts": ncx, "gpu_launches": launches, "failed_regions": int((st != 0).sum()), "counters": cnt,
            "evaluations_per_region": cnt["column_evaluations"] / max(1, int(off[-1])),
            "jacobi_sweeps_per_matrix": cnt["eig_sweeps"] / max(1, cnt["eig_matrices"]),
            "pt_build_tflops": cnt["pt_slots"] * 524288.0 / (ms["pt_build"] * 1e-3) / 1e12 if ms["pt_build"] > 0 else None,
            "pruning_tflops": cnt["column_evaluations"] * (n - 2) * 8192.0 / (ms["prune"] * 1e-3) / 1e12 if ms["prune"] > 0 else None,
            "dmma_peak_tflops": peak,
            "median_score_db": float(np.median(score)), "median_rho_H0": float(np.median(diag[:, 1])), "median_kappa_H0": float(np.median(diag[:, 2])),
-           "path": "pcsf_omega_score (stages the regions, then kr_map for H0 and H1 in batched Brent rounds: K5 + K1 + K2..K4 per round), wall clock"}
-    ctx.close()
+           "path": "pcsf_omega_score (stages the regions, then kr_map for H0 and H1 in batched Brent rounds: K5 + K1 + K2..K4 per round) on "
+                   "%d scoring context(s) of the one GPU, each with a host thread and an equal share of the regions; wall clock; device_ms are "
+                   "summed over the contexts (kernels of different contexts overlap, so the share can exceed 1)" % ncx}
+    for c in ctxs:
+        c.close()
     return res
 
 
@@ -627,6 +659,9 @@ def main():
     ap.add_argument("--cfg5-alignments", type=int, default=1000, help="alignments of 5,001 nt in the strong-scaling job (1000 = 10 M codon columns)")
     ap.add_argument("--mle-alignments", type=int, default=10000)
     ap.add_argument("--omega-alignments", type=int, default=1000)
+    ap.add_argument("--omega-contexts", type=int, default=1,
+                    help="scoring contexts on the GPU for the omega leg, each with a host thread and a share of the regions (measured: 268 / 240 / 262 "
+                         "alignments/s with 1 / 2 / 3 - the persistent pruning kernels of two contexts cannot share the SMs, so there is nothing to overlap)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
