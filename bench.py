@@ -385,6 +385,8 @@ def run_headline(args, env):
                     "table_level": info_e2e["table_level"], "kernel_form": info_e2e["form"],
                     "path": "pcsf_score_alignments: pinned host nucleotide rows -> chunked H2D overlapped with on-device pleaves + pruning + reduction -> D2H"},
             "gpu_launches": int(launches),
+            "baseline_kind": "port: the CPU arm (cpu_baseline, --impl reference) is the oracle's C restatement of the reference's algorithm on all host "
+                             "cores; the OCaml + GSL reference itself cannot be built in this image",
             "setup": setup,
             "clocks": clocks,
             "roofline": {"kernel": kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -751,6 +753,7 @@ def run_reference(args, config):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulated under the shipped 58mammals tree and ECMs)",
             "config": config, "cores": cores,
+            "baseline_kind": "port: the oracle's C restatement of the reference's algorithm; the OCaml + GSL reference itself cannot be built in this image",
             "cpu_baseline": {"value": value, "unit": "codon-columns/s", "cores": cores, "kind": "port",
                              "sample": "per step: " + sample + " (a bounded sample of the 100,000-alignment workload, same alignment shape); "
                                        "OCaml+GSL reference not buildable here, CPU restatement (oracle port) timed instead"},
