@@ -368,3 +368,30 @@ def test_omega_eigen_warm_start_matches_cold(params_base):
     with pytest.raises(Exception):
         ctx.omega_models_set_cached(3, base, [0, 1, 7])  # slot out of range
     ctx.close()
+
+
+@pytest.mark.parametrize("kappa", [1.0, 2.7])
+def test_omega_pipeline_against_the_beagle_pinned_nucleotide_model(kappa):
+    """K5 (Q assembly + Jacobi) -> K1 -> pruning on the BEAGLE test's tree and sequences with omega = sigma = 1, uniform
+    F3x4, tree scale 3: the codon likelihood must equal the product of the three nucleotide columns' K80 / JC69 likelihoods
+    (oracle, 4 states - the configuration whose lnL the reference pins, lib/CamlPaml/test.ml:81). The one corner of the
+    omega pipeline that is tied to a reference-held vector rather than to the oracle's reading of OmegaModel.ml."""
+    import json
+
+    import phylocsf_b200 as pb
+    from test_oracle_golden import _k80, gapfree_codon_columns
+
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "beagle_tiny.json")))
+    t = o.Tree.of_newick(o.newick_parse(d["newick"]))
+    cod, nuc = gapfree_codon_columns([d["human"], d["chimp"], d["gorilla"]])
+    ll_nt = o.lpr_columns(o.PhyloModel(t, o.QDiag(_k80(kappa)), t.branches), nuc)[0]
+    ctx = pb.Context(0)
+    H.push_tree(ctx, t)
+    st = ctx.omega_models_set(0, [[kappa, 1.0, 1.0] + [1.0] * 9])
+    assert (st == 0).all()
+    np.testing.assert_allclose(ctx.model_get(0)["prior"], np.full(64, 1.0 / 64), atol=1e-14)
+    ctx.pt_build_pairs([0], [3.0])
+    ctx.batch_upload(np.array([0, cod.shape[0]], dtype=np.int64), cod)
+    lpr, _, st = ctx.lpr_pairs([0], [0])
+    assert st[0] == 0 and abs(lpr[0] - ll_nt) < 1e-9 * abs(ll_nt), (lpr[0], ll_nt)
+    ctx.close()

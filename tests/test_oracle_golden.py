@@ -177,3 +177,54 @@ def test_find_orfs_modes():
     assert o.find_orfs("CCCAAATAGGGGTTTCC", 0, "StopStop", 1) == [(0, 5), (9, 14)]
     assert o.find_orfs("CCCAAATAGGGGTTTCC", 0, "ToFirstStop", 1) == [(0, 5)]
     assert o.find_orfs("CCCAAATAGGGGTTTCC", 0, "FromLastStop", 1) == [(9, 14)]
+
+
+# ---------------------------------------------------------------- an analytic pin for the omega model
+def _k80(kappa):
+    """Unit-rate K80 (HKY85 with uniform frequencies): transitions A<->G, C<->T at kappa, transversions at 1."""
+    m = np.ones((4, 4))
+    for a, b in ((0, 2), (2, 0), (1, 3), (3, 1)):
+        m[a, b] = kappa
+    m /= 4.0
+    np.fill_diagonal(m, 0.0)
+    np.fill_diagonal(m, -m.sum(axis=1))
+    return m * 4.0 / (kappa + 2.0)
+
+
+def gapfree_codon_columns(seqs):
+    """(codon codes [ncols, n], nucleotide codes [3 ncols, n]) of the codon columns in which no sequence has a gap."""
+    idx = {"A": 0, "C": 1, "G": 2, "T": 3}
+    L = len(seqs[0]) // 3 * 3
+    cod, nuc = [], []
+    for p in range(0, L, 3):
+        trip = [[idx.get(s[p + k], -1) for k in range(3)] for s in seqs]
+        if all(min(t) >= 0 for t in trip):
+            cod.append([16 * t[0] + 4 * t[1] + t[2] for t in trip])
+            for k in range(3):
+                nuc.append([t[k] for t in trip])
+    return np.array(cod, dtype=np.uint8), np.array(nuc, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("kappa", [1.0, 2.7])
+def test_omega_model_at_omega_1_is_three_independent_nucleotide_processes(kappa):
+    """The reference holds no golden for the omega strategy, but one corner of it is pinned analytically: with omega =
+    sigma = 1 and uniform F3x4 the codon rate matrix (src/OmegaModel.ml:21-80, scaled to unit rate, PhyloModel.ml:94-106)
+    is the Kronecker sum of three K80 nucleotide processes at a third of the rate each, so a codon column's likelihood is
+    the product of its three nucleotide columns' likelihoods. On the BEAGLE test's tree and sequences (lib/CamlPaml/test.ml:
+    56-99) with kappa = 1 and the tree scaled by 3 the nucleotide side is exactly the configuration whose lnL the
+    reference pins (-1574.63623 over all columns)."""
+    qs = [kappa, 1.0, 1.0] + [1.0] * 9
+    Qc = o.omega_q(qs)
+    Qn = _k80(kappa)
+    I = np.eye(4)
+    ksum = np.kron(np.kron(Qn, I), I) + np.kron(np.kron(I, Qn), I) + np.kron(np.kron(I, I), Qn)
+    np.testing.assert_allclose(Qc, ksum / 3.0, atol=1e-15)
+    d = _beagle()
+    t = o.Tree.of_newick(o.newick_parse(d["newick"]))
+    cod, nuc = gapfree_codon_columns([d["human"], d["chimp"], d["gorilla"]])
+    assert cod.shape[0] > 200
+    inst = o.OmegaInstance(t, qs, 3.0)
+    ll_codon = o.omega_lpr_leaves(inst, cod)
+    mn = o.PhyloModel(t, o.QDiag(Qn), t.branches)
+    ll_nt = o.lpr_columns(mn, nuc)[0]
+    assert abs(ll_codon - ll_nt) < 1e-9 * abs(ll_nt), (ll_codon, ll_nt)
