@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,9 +37,60 @@ struct Model {
     DevBuf cherry;                  // [nscales][subtree tables of one P set], built on demand (fixed strategy)
     std::vector<char> cherry_built; // per scale: 0, or the level built (2 cherries, 3 cherries + cherry-and-leaf subtrees)
     int cherry_level = 0;           // level the buffer's per-scale stride was sized for
+    struct TabBlock* tab = nullptr; // one-scale models (fixed strategy): subtree tables shared by the process's contexts on this GPU
+    uint64_t params_hash = 0;       // of S | Sinv | lambda as given to pcsf_model_set (0: not shareable)
+    std::vector<double> scales;     // the tree scales of the P tables
     const double* prior() const { return d_params + 8192 + 64; }
     const double* logprior() const { return d_params + 8192 + 128; }
 };
+
+// Subtree tables of one P set, shared by every context of the process on the same GPU that has the same tree, the same
+// diagonalised model and the same scale (the command line runs two contexts per device; 58mammals level 4 is 47 GB per
+// model - two private copies do not fit in 180 GB). A block is immutable once built. A higher level is a NEW block that
+// becomes the key's current one; a context keeps the block it holds until its next call and a block is freed when the
+// last context lets go of it, so nobody's kernels ever run on freed memory.
+struct TabBlock {
+    int device = 0;
+    uint64_t key = 0;
+    int level = 0;
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t ready = nullptr;  // recorded after the building kernels: other contexts' streams wait for it
+    int refs = 0;
+    bool current = false;
+};
+struct TabKey {  // per (GPU, P set): how many columns have been scored under it by all contexts (cumulative level rule)
+    int device;
+    uint64_t key;
+    int64_t cols_seen;
+};
+std::mutex g_tab_mu;
+std::vector<TabBlock*> g_tab_blocks;
+std::vector<TabKey> g_tab_keys;
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* b = (const unsigned char*)data;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+void tab_release_locked(TabBlock* b) {  // g_tab_mu held
+    if (!b) return;
+    if (--b->refs > 0) return;
+    for (size_t i = 0; i < g_tab_blocks.size(); i++)
+        if (g_tab_blocks[i] == b) { g_tab_blocks.erase(g_tab_blocks.begin() + i); break; }
+    cudaSetDevice(b->device);
+    if (b->p) cudaFree(b->p);  // (synchronises the device: nothing in flight still reads the block)
+    if (b->ready) cudaEventDestroy(b->ready);
+    delete b;
+}
+
+void tab_release(Model& m) {
+    if (!m.tab) return;
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    tab_release_locked(m.tab);
+    m.tab = nullptr;
+}
 
 }  // namespace
 
@@ -95,6 +147,8 @@ struct pcsf_ctx {
     int cherry_mode = 0;  // PCSF_OPT_CHERRY_TABLES: 0 by the number of columns a P set scores, 1 never, 2 always levels 2-3, 3 always cherries only, 4 always levels 2-4
     int wide = -1;  // pruning kernel form: 0 narrow (128-column tiles), 1 wide (192), -1 chosen per launch (PCSF_WIDE overrides)
     int rescale = 0;  // PCSF_OPT_RESCALE
+    uint64_t tree_hash = 0;
+    int share_tables = 1;  // PCSF_SHARE_TABLES=0: every context builds its own subtree tables (as in round 1)
     int last_form = 0, last_level = 0, last_grid = 0;  // what the most recent pruning launch ran (pcsf_last_launch_info)
     int64_t last_tiles = 0;
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
@@ -353,7 +407,11 @@ PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
     ps.logprior = m.logprior();
     ps.cherry = nullptr;
     ps.tab_level = 0;
-    if (scale < (int)m.cherry_built.size() && m.cherry_built[scale]) {
+    if (m.tab && ctx->cherry_mode != 1) {  // shared block (one-scale models); a block of level L holds the tables of all levels <= L
+        const int cap = ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : 4;  // PCSF_OPT_CHERRY_TABLES: "always, up to ..."
+        ps.cherry = (const double*)m.tab->p;
+        ps.tab_level = std::min(m.tab->level, cap);
+    } else if (scale < (int)m.cherry_built.size() && m.cherry_built[scale]) {
         ps.cherry = (const double*)m.cherry.p + (size_t)scale * table_block_doubles(ctx, m.cherry_level);
         ps.tab_level = m.cherry_built[scale];
     }
@@ -363,14 +421,121 @@ PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
 // Which subtree tables a P set that scores `cols_per_pset` columns should carry: cherries (2.16 MB each, built in
 // well under a millisecond) pay from a few ten thousand columns; the 140.6 MB tables of cherry-and-leaf subtrees
 // from about a million, and only while they fit comfortably in device memory.
-int want_table_level(pcsf_ctx* ctx, int64_t cols_per_pset) {
+// `seen`: columns already scored under this P set (by all contexts that share its tables). A level pays for itself over
+// a run, not only over one call: level 4 costs 45 ms to build for both models and saves 2.2 ns per column against
+// level 3, i.e. breaks even at 20 M columns - a P set that has seen twice that gets it even if no single batch is big.
+int want_table_level(pcsf_ctx* ctx, int64_t cols_per_pset, int64_t seen = 0) {
     if (ctx->cherry_mode == 1 || ctx->wide == 0 || ctx->n_tab2 == 0) return 0;
     if (ctx->cherry_mode >= 2) return ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : 4;
-    return cols_per_pset >= 5000000 ? 4 : cols_per_pset >= 1000000 ? 3 : cols_per_pset >= 50000 ? 2 : 0;
+    const int64_t cum = cols_per_pset + seen;
+    return (cols_per_pset >= 5000000 || cum >= 40000000) ? 4 : (cols_per_pset >= 1000000 || cum >= 8000000) ? 3
+           : (cols_per_pset >= 50000 || cum >= 400000) ? 2 : 0;
 }
 
 // Build (once) the subtree tables of model `m` at scale index `scale` up to `level`. Only for models with a handful
 // of scales (the fixed strategy's): per-candidate P sets of mle / omega score too few columns to pay for them.
+int build_table_levels(pcsf_ctx* ctx, const double* tables, double* base, int from_level, int level) {
+    if (from_level < 2) {
+        const long long warps = (long long)ctx->n_tab2 * ((CHERRY_ROWS + 15) / 16);
+        subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, 0, ctx->n_tab2, CHERRY_ROWS, base);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (level >= 3 && from_level < 3 && ctx->n_tab3 > 0) {
+        const long long warps = (long long)ctx->n_tab3 * ((TRIPLE_ROWS + 15) / 16);
+        subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, ctx->n_tab2, ctx->n_tab3, TRIPLE_ROWS, base);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (level >= 4 && ctx->n_tab4 > 0) {
+        const long long warps = (long long)ctx->n_tab4 * ((QUAD_ROWS + 15) / 16);
+        subtree_table_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>(tables, ctx->d_subtabs, ctx->n_tab2 + ctx->n_tab3, ctx->n_tab4, QUAD_ROWS, base);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    return PCSF_OK;
+}
+
+// The shared path: one-scale models whose inputs are known by hash (pcsf_model_set). `est_cols` columns are about to be
+// scored under the P set.
+int ensure_tables_shared(pcsf_ctx* ctx, Model& m, int64_t est_cols) {
+    const double scale_v = m.scales[0];
+    uint64_t key = fnv1a(&ctx->tree_hash, sizeof(uint64_t), m.params_hash);
+    key = fnv1a(&scale_v, sizeof(double), key);
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    TabKey* ks = nullptr;
+    for (TabKey& k : g_tab_keys)
+        if (k.device == ctx->device && k.key == key) ks = &k;
+    if (!ks) {
+        g_tab_keys.push_back(TabKey{ctx->device, key, 0});
+        ks = &g_tab_keys.back();
+    }
+    int level = want_table_level(ctx, est_cols, ks->cols_seen);
+    ks->cols_seen += est_cols;
+    if (level == 4 && ctx->n_tab4 == 0) level = 3;
+    if (level == 3 && ctx->n_tab3 == 0) level = 2;
+    TabBlock* cur = nullptr;
+    for (TabBlock* b : g_tab_blocks)
+        if (b->device == ctx->device && b->key == key && b->current) cur = b;
+    auto attach = [&](TabBlock* b) {
+        if (m.tab != b) {
+            b->refs++;
+            tab_release_locked(m.tab);
+            m.tab = b;
+            if (b->ready) cudaStreamWaitEvent(ctx->stream, b->ready, 0);
+        }
+        if ((int)m.cherry_built.size() != m.nscales) m.cherry_built.assign(m.nscales, 0);
+        m.cherry_built[0] = (char)b->level;
+    };
+    const int have = cur ? cur->level : 0;
+    if (level <= have) {
+        if (cur) attach(cur);
+        return PCSF_OK;
+    }
+    // a new block at `level`: large levels only while they fit comfortably next to everything else on the device
+    void* p = nullptr;
+    size_t bytes = 0;
+    for (; level > have; level--) {
+        if (level == 3 && ctx->n_tab3 == 0) continue;
+        bytes = sizeof(double) * table_block_doubles(ctx, level);
+        if (level >= 3) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+            // level 4 (tens of GB): room for the other model's block too and 16 GB to spare; level 3: a few blocks' worth
+            if ((double)free_b < (level == 3 ? 6.0 : 2.0) * (double)bytes + (level == 4 ? 16e9 : 0.0)) continue;
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (cudaMalloc(&p, bytes) == cudaSuccess) break;
+        cudaGetLastError();
+        p = nullptr;
+    }
+    if (!p) {
+        if (cur) attach(cur);
+        return PCSF_OK;  // no (better) tables is fine too
+    }
+    TabBlock* nb = new TabBlock();
+    nb->device = ctx->device;
+    nb->key = key;
+    nb->level = level;
+    nb->p = p;
+    nb->bytes = bytes;
+    CU(cudaEventCreateWithFlags(&nb->ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev[10], ctx->stream));
+    TRY(build_table_levels(ctx, (const double*)m.tables.p, (double*)p, 0, level));
+    CU(cudaEventRecord(nb->ready, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[11], ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev[11]));
+    float t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[10], ctx->ev[11]));
+    ctx->ms[5] = t;
+    ctx->ms_total[5] += t;
+    if (cur) cur->current = false;
+    nb->current = true;
+    g_tab_blocks.push_back(nb);
+    attach(nb);
+    return PCSF_OK;
+}
+
 int ensure_tables(pcsf_ctx* ctx, Model& m, int scale, int level) {
     if (level == 0 || ctx->n_tab2 == 0 || m.nscales > 8) return PCSF_OK;
     if (level == 4 && ctx->n_tab4 == 0) level = 3;
@@ -469,6 +634,8 @@ int pt_build_device(pcsf_ctx* ctx, Model& m, int nscales, const double* scales) 
     for (int i = 0; i < nscales; i++) jobs[i] = PtJob{m.d_params, scales[i]};
     TRY(pt_build_jobs(ctx, jobs, m.tables, m.d_status, m.status));
     m.nscales = nscales;
+    m.scales.assign(scales, scales + nscales);
+    tab_release(m);
     m.cherry_built.assign(nscales, 0);  // the cherry tables belonged to the previous P(t)
     return PCSF_OK;
 }
@@ -536,6 +703,7 @@ int pcsf_create(int device_id, pcsf_ctx** out) {
     if (const char* e = getenv("PCSF_WIDE")) ctx->wide = atoi(e);
     if (const char* e = getenv("PCSF_CHERRY_TABLES")) ctx->cherry_mode = atoi(e);
     if (const char* e = getenv("PCSF_RESCALE")) ctx->rescale = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("PCSF_SHARE_TABLES")) ctx->share_tables = atoi(e) ? 1 : 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->stream = ctx->own_stream;
     for (auto& ev : ctx->ev)
@@ -553,6 +721,7 @@ void pcsf_destroy(pcsf_ctx* ctx) {
         b.p = nullptr;
     };
     for (auto& m : ctx->models) {
+        tab_release(m);
         if (m.d_params && m.owns_params) cudaFree(m.d_params);
         fr(m.tables);
         fr(m.d_scales);
@@ -638,7 +807,8 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
     pb.ops.push_back({OP_ROOT, 0, 0, 0});
     if (pb.max_height > MAX_STACK_LEVELS) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: tree needs more than 16 parked partials");
     ctx->n_leaves = 0;  // from here to the last upload the context has no tree (check_ready fails if an upload does)
-    for (auto& m : ctx->models) { m.nscales = 0; m.cherry_built.clear(); }  // tables belong to the previous tree
+    for (auto& m : ctx->models) { m.nscales = 0; m.cherry_built.clear(); tab_release(m); }  // tables belong to the previous tree
+    ctx->tree_hash = fnv1a(branch_len, sizeof(double) * (n - 1), fnv1a(children, sizeof(int32_t) * 2 * (n_leaves - 1)));
     ctx->n_branches = n - 1;
     ctx->children = new_children;
     ctx->branch_len.assign(branch_len, branch_len + (n - 1));
@@ -808,6 +978,9 @@ int pcsf_model_set(pcsf_ctx* ctx, int model_id, const double* S, const double* S
     CU(cudaMemcpy(m.d_params, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
     m.set = true;
     m.nscales = 0;
+    tab_release(m);
+    m.params_hash = fnv1a(h.data(), sizeof(double) * (8192 + 64));
+    if (m.params_hash == 0) m.params_hash = 1;
     return PCSF_OK;
 }
 
@@ -964,7 +1137,13 @@ int pcsf_lpr_all(pcsf_ctx* ctx, int n_models, const int32_t* model_ids, const in
     for (int m = 0; m < n_models; m++) {
         const int sc = scale_idx ? scale_idx[m] : 0;
         TRY(check_model(ctx, model_ids[m], sc));
-        TRY(ensure_tables(ctx, ctx->models[model_ids[m]], sc, want_table_level(ctx, ctx->total_cols)));
+        {
+            Model& mm = ctx->models[model_ids[m]];
+            if (ctx->share_tables && mm.nscales == 1 && mm.params_hash && ctx->cherry_mode != 1 && ctx->wide != 0 && ctx->n_tab2 > 0)
+                TRY(ensure_tables_shared(ctx, mm, ctx->total_cols));
+            else
+                TRY(ensure_tables(ctx, mm, sc, want_table_level(ctx, ctx->total_cols)));
+        }
         psets.push_back(make_pset(ctx, model_ids[m], sc));
         spans.push_back(Span{0, (int64_t)m * ctx->total_cols, 0, (int32_t)0, m});
         spans.back().ncols = (int32_t)ctx->total_cols;
@@ -1016,7 +1195,13 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
     for (int m = 0; m < n_models; m++) {
         const int sc = scale_idx ? scale_idx[m] : 0;
         TRY(check_model(ctx, model_ids[m], sc));
-        TRY(ensure_tables(ctx, ctx->models[model_ids[m]], sc, want_table_level(ctx, est_cols)));
+        {
+            Model& mm = ctx->models[model_ids[m]];
+            if (ctx->share_tables && mm.nscales == 1 && mm.params_hash && ctx->cherry_mode != 1 && ctx->wide != 0 && ctx->n_tab2 > 0)
+                TRY(ensure_tables_shared(ctx, mm, est_cols));
+            else
+                TRY(ensure_tables(ctx, mm, sc, want_table_level(ctx, est_cols)));
+        }
         psets.push_back(make_pset(ctx, model_ids[m], sc));
     }
     if (!ctx->copy_stream) {
@@ -1197,6 +1382,8 @@ int pcsf_models_set(pcsf_ctx* ctx, int first_id, int n, const double* S, const d
         m.d_params = (double*)ctx->d_batch_params.p + per * i;
         m.set = true;
         m.nscales = 0;
+        m.params_hash = 0;  // not shareable: the block of parameters is rewritten per round
+        tab_release(m);
     }
     ctx->pair_model.clear();
     return PCSF_OK;
@@ -1270,6 +1457,8 @@ int pcsf_omega_models_set_cached(pcsf_ctx* ctx, int first_id, int n, const doubl
         m.d_params = (double*)ctx->d_batch_params.p + per * i;
         m.set = true;  // a failed model keeps its slot (contents undefined); the caller sees its status
         m.nscales = 0;
+        m.params_hash = 0;
+        tab_release(m);
         if (status) status[i] = st[i];
         bad |= st[i] != 0;
     }
@@ -1589,6 +1778,7 @@ int pcsf_table_level(const pcsf_ctx* ctx, int model_id, int scale_idx) {
     if (!ctx || model_id < 0 || model_id >= (int)ctx->models.size() || !ctx->models[model_id].set) return PCSF_ERR_INVALID_ARG;
     const Model& m = ctx->models[model_id];
     if (scale_idx < 0 || scale_idx >= m.nscales) return PCSF_ERR_INVALID_ARG;
+    if (m.tab) return ctx->cherry_mode == 1 ? 0 : std::min(m.tab->level, ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : 4);
     return scale_idx < (int)m.cherry_built.size() ? (int)m.cherry_built[scale_idx] : 0;
 }
 

@@ -395,3 +395,67 @@ def test_omega_pipeline_against_the_beagle_pinned_nucleotide_model(kappa):
     lpr, _, st = ctx.lpr_pairs([0], [0])
     assert st[0] == 0 and abs(lpr[0] - ll_nt) < 1e-9 * abs(ll_nt), (lpr[0], ll_nt)
     ctx.close()
+
+
+def test_subtree_tables_are_shared_between_contexts_and_follow_the_cumulative_rule(params_base, monkeypatch):
+    """Two contexts on one GPU with the same tree, model and scale use ONE set of subtree tables (the second context
+    launches no table kernels), results are bit-identical to a context that builds its own, the block outlives the
+    context that built it, and a P set whose batches are each too small for a level gets it once it has scored enough
+    columns in total."""
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host
+
+    hp = host.ParamSet(os.path.join(params_base, "PhyloCSF_Parameters", "29mammals"))
+    ops = H.oracle_paramset(params_base, "29mammals")
+    rng = np.random.default_rng(77)
+    regs = [o.simulate_columns(ops.model.coding_model.model(1.0), 300, rng), o.simulate_columns(ops.model.noncoding_model.model(1.0), 200, rng)]
+    off, codes = H.regions_to_batch(regs)
+
+    def fresh():
+        c = pb.Context(0)
+        hp.install(c)
+        c.pt_build(0, [1.0])
+        c.pt_build(1, [1.0])
+        c.option_set(pb.Context.OPT_PRUNE_FORM, pb.Context.FORM_WIDE)
+        c.batch_upload(off, codes)
+        return c
+
+    a, b = fresh(), fresh()
+    a.option_set(pb.Context.OPT_CHERRY_TABLES, 2)  # always, up to level 3
+    b.option_set(pb.Context.OPT_CHERRY_TABLES, 2)
+    l0 = a.launch_count
+    ra = a.lpr_all([0, 1])
+    built = a.launch_count - l0
+    l0 = b.launch_count
+    rb = b.lpr_all([0, 1])
+    reused = b.launch_count - l0
+    assert a.table_level(0) == 3 and b.table_level(0) == 3 and b.last_launch_info()["table_level"] == 3
+    assert built > reused and reused == 3, (built, reused)  # pruning + segments + reduction, no table kernels
+    assert all(np.array_equal(x, y) for x, y in zip(ra, rb))
+    a.close()  # the block lives on while b holds it
+    rb2 = b.lpr_all([0, 1])
+    assert all(np.array_equal(x, y) for x, y in zip(rb, rb2))
+    monkeypatch.setenv("PCSF_SHARE_TABLES", "0")
+    c = fresh()
+    c.option_set(pb.Context.OPT_CHERRY_TABLES, 2)
+    rc = c.lpr_all([0, 1])
+    assert c.table_level(0) == 3 and all(np.array_equal(x, y) for x, y in zip(rb, rc))
+    c.option_set(pb.Context.OPT_CHERRY_TABLES, 1)  # never: the plain program, same bits
+    rc1 = c.lpr_all([0, 1])
+    assert c.last_launch_info()["table_level"] == 0 and all(np.array_equal(x, y) for x, y in zip(rb, rc1))
+    c.close()
+    b.close()
+    monkeypatch.delenv("PCSF_SHARE_TABLES")
+    # cumulative rule: 500-column batches never reach the 50,000-column threshold of level 2 in one call; after 400,000
+    # columns in total the P set gets its cherry tables (and keeps giving the same bits)
+    d = fresh()
+    first = d.lpr_all([0, 1])
+    assert d.table_level(0) == 0
+    for _ in range(900):
+        d.lpr_all([0])
+        if d.table_level(0):
+            break
+    assert d.table_level(0) == 2
+    again = d.lpr_all([0, 1])
+    assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+    d.close()
