@@ -80,9 +80,12 @@ int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
  * the 65^3 code triples (140.6 MB each); and above every caterpillar of four leaves over the 65^4 quadruples (9.14 GB
  * each). The tables are computed with the pruning kernel's own instruction sequence, so a lookup is bit-identical
  * to the computation it replaces. 0 (default) = built by pcsf_lpr_all / pcsf_score_alignments when the wide form runs
- * and a P set scores >= 50,000 columns (cherries) / >= 1,000,000 (3 leaves) / >= 5,000,000 (4 leaves), the larger
+ * and a P set scores >= 50,000 columns (cherries) / >= 1,000,000 (3 leaves) / >= 5,000,000 (4 leaves) in one call, or
+ * has scored eight times that in total (a level pays for itself over a run, not only over one batch), the larger
  * ones only while device memory allows; 1 = never; 2 = always, up to 3 leaves; 3 = always, cherries only;
  * 4 = always, up to 4 leaves. PCSF_CHERRY_TABLES in the environment sets it for every new context.
+ * The tables of a one-scale model set with pcsf_model_set are shared by all contexts of the process on the same GPU
+ * that hold the same tree, model and scale (PCSF_SHARE_TABLES=0 in the environment: one private copy per context).
  */
 #define PCSF_OPT_CHERRY_TABLES 3
 int pcsf_option_set(pcsf_ctx *ctx, int option, int64_t value);

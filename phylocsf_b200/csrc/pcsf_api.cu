@@ -79,6 +79,11 @@ void tab_release_locked(TabBlock* b) {  // g_tab_mu held
     if (--b->refs > 0) return;
     for (size_t i = 0; i < g_tab_blocks.size(); i++)
         if (g_tab_blocks[i] == b) { g_tab_blocks.erase(g_tab_blocks.begin() + i); break; }
+    bool other = false;  // the P set's history goes with its last block: a later context starts from zero, like a new process
+    for (TabBlock* q : g_tab_blocks) other |= q->device == b->device && q->key == b->key;
+    if (!other)
+        for (size_t i = 0; i < g_tab_keys.size(); i++)
+            if (g_tab_keys[i].device == b->device && g_tab_keys[i].key == b->key) { g_tab_keys.erase(g_tab_keys.begin() + i); break; }
     cudaSetDevice(b->device);
     if (b->p) cudaFree(b->p);  // (synchronises the device: nothing in flight still reads the block)
     if (b->ready) cudaEventDestroy(b->ready);
@@ -411,7 +416,7 @@ PSet make_pset(const pcsf_ctx* ctx, int model_id, int scale) {
         const int cap = ctx->cherry_mode == 2 ? 3 : ctx->cherry_mode == 3 ? 2 : 4;  // PCSF_OPT_CHERRY_TABLES: "always, up to ..."
         ps.cherry = (const double*)m.tab->p;
         ps.tab_level = std::min(m.tab->level, cap);
-    } else if (scale < (int)m.cherry_built.size() && m.cherry_built[scale]) {
+    } else if (!m.tab && ctx->cherry_mode != 1 && scale < (int)m.cherry_built.size() && m.cherry_built[scale]) {
         ps.cherry = (const double*)m.cherry.p + (size_t)scale * table_block_doubles(ctx, m.cherry_level);
         ps.tab_level = m.cherry_built[scale];
     }
