@@ -219,19 +219,7 @@ int main(int argc, char** argv) {
         const size_t chunk = 32, n_chunks = (n_files + chunk - 1) / chunk;
         const size_t window = std::max<size_t>(4, 4 * (size_t)nthreads);  // chunks in flight
         std::vector<Chunk> ring(window);
-        const bool use_pinned = opt.strategy != STRAT_NOP && !std::getenv("PCSF_PAGEABLE");  // PCSF_PAGEABLE=1: A/B runs
-        PinnedArena::instance().use_pinned(use_pinned);
-        std::thread pin_thread;
-        struct PinJoin {  // every way out of this scope (aborts included) joins the start-up thread
-            std::thread& t;
-            ~PinJoin() { if (t.joinable()) t.join(); }
-        } pin_join{pin_thread};
-        if (use_pinned && opt.orf == AsIs && opt.strategy != STRAT_OMEGA && fns.size() > 64) {
-            // what the batches in flight will hold (two per scoring context + the one being filled), at most 4 GB
-            const size_t per_batch = (size_t)opt.batch_cols * 64 * 3 / (size_t)opt.frames + ((size_t)8 << 20);
-            const size_t want = std::min<size_t>((size_t)4 << 30, per_batch * (2 * devices.size() + 1));
-            pin_thread = std::thread([want] { PinnedArena::instance().prealloc(want); });
-        }
+        PinnedArena::instance().use_pinned(opt.strategy != STRAT_NOP && !std::getenv("PCSF_PAGEABLE"));  // PCSF_PAGEABLE=1: A/B runs
         BufferPool nt_pool;
         std::vector<char> ready(window, 0);
         std::mutex mu;
@@ -330,7 +318,6 @@ int main(int argc, char** argv) {
             }
             t_append += now() - t1;
         }
-        if (pin_thread.joinable()) pin_thread.join();
         shut();
         if (host_profile) {
             const double t2 = now();

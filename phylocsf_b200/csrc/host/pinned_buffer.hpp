@@ -4,9 +4,8 @@
 // thread at a few GB/s, with the device idle meanwhile (measured on the GPU box: the host pipeline alone parses 620 k
 // alignments/s on 16 cores, but with scoring switched on the run spent its time in "batch hand-off"). Page-locked
 // buffers are copied by DMA at PCIe speed while the host goes on.
-// cudaHostAlloc is expensive (a driver call that pins pages), so memory is taken in slabs through the C ABI
-// (pcsf_host_alloc; one large slab at start-up, 32 MB ones after that) and handed out in power-of-two size classes with
-// free lists; buffers are recycled by the caller's
+// cudaHostAlloc is expensive (a driver call that pins pages), so memory is taken in 32 MB slabs through the C ABI
+// (pcsf_host_alloc) and handed out in power-of-two size classes with free lists; buffers are recycled by the caller's
 // pool, so after the first few batches nothing is allocated any more. Without a CUDA device (--strategy=nop) the slabs
 // are ordinary memory.
 #pragma once
@@ -36,46 +35,26 @@ class PinnedArena {
         while (((size_t)65536 << k) < bytes) k++;
         return k;
     }
-    // One big slab up front (called from a start-up thread, next to the creation of the scoring contexts): pinning a
-    // gigabyte takes a few hundred milliseconds, and doing it piecemeal from the reader threads - 32 MB at a time, behind
-    // one lock - made the readers wait for the driver (measured: the first version of this arena was slower than
-    // pageable buffers).
-    void prealloc(size_t bytes) {
-        uint8_t* p = (uint8_t*)raw_alloc(bytes);
-        std::lock_guard<std::mutex> lk(mu);
-        if (p) {  // becomes the current slab (what is left of a small slab the readers opened meanwhile stays unused)
-            slab = p;
-            slab_left = bytes;
-        }
-    }
     // a block of at least `bytes`; cap receives its real size
     uint8_t* get(size_t bytes, size_t& cap) {
         const int k = size_class(bytes);
         cap = (size_t)65536 << k;
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            if ((size_t)k < free_.size() && !free_[k].empty()) {
-                uint8_t* p = free_[k].back();
-                free_[k].pop_back();
-                return p;
-            }
-            if (cap <= slab_left) {
-                uint8_t* p = slab;
-                slab += cap;
-                slab_left -= cap;
-                return p;
-            }
-        }
-        // a new slab, allocated outside the lock (the rest of the old one stays unused: at most one block's worth)
-        const size_t want = cap > kSlab ? cap : kSlab;
-        uint8_t* fresh = (uint8_t*)raw_alloc(want);
-        if (!fresh) return nullptr;
         std::lock_guard<std::mutex> lk(mu);
-        if (want - cap > slab_left) {
-            slab = fresh + cap;
-            slab_left = want - cap;
+        if ((size_t)k < free_.size() && !free_[k].empty()) {
+            uint8_t* p = free_[k].back();
+            free_[k].pop_back();
+            return p;
         }
-        return fresh;
+        if (cap > slab_left) {  // the rest of the old slab stays unused (at most one block's worth per slab)
+            const size_t want = cap > kSlab ? cap : kSlab;
+            slab = (uint8_t*)raw_alloc(want);
+            slab_left = slab ? want : 0;
+            if (!slab) return nullptr;
+        }
+        uint8_t* p = slab;
+        slab += cap;
+        slab_left -= cap;
+        return p;
     }
     void put(uint8_t* p, size_t cap) {
         if (!p) return;
@@ -92,7 +71,7 @@ class PinnedArena {
     std::vector<std::vector<uint8_t*>> free_;
     uint8_t* slab = nullptr;
     size_t slab_left = 0;
-    void* raw_alloc(size_t bytes) {  // (called without the lock: `pinned` only ever goes from true to false)
+    void* raw_alloc(size_t bytes) {
         if (pinned) {
             void* p = pcsf_host_alloc(bytes);
             if (p) return p;
