@@ -19,7 +19,6 @@
 #ifndef PHYLOCSF_B200_H
 #define PHYLOCSF_B200_H
 
-#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -58,11 +57,6 @@ const char *pcsf_last_error(const pcsf_ctx *ctx);
 /* Run all work of this context on an existing cudaStream_t (so a caller can bracket calls with its
  * own CUDA events). NULL restores the context's own stream. */
 int pcsf_stream_set(pcsf_ctx *ctx, void *cuda_stream);
-/* Page-locked host memory for staging buffers (cudaHostAlloc, portable across the process's contexts): host buffers passed
- * to the upload / scoring entry points are copied by DMA at PCIe speed when they come from here, through the driver's
- * bounce buffer otherwise. Returns NULL when no CUDA device is usable or the driver refuses. */
-void *pcsf_host_alloc(size_t bytes);
-void pcsf_host_free(void *p);
 
 /*
  * Options (no reference analogue). PCSF_OPT_RESCALE = 1: rescue per-column partials from underflow by

@@ -14,7 +14,7 @@ SYMBOLS = [
     "pcsf_version", "pcsf_device_count", "pcsf_create", "pcsf_destroy", "pcsf_last_error", "pcsf_stream_set", "pcsf_option_set",
     "pcsf_tree_set", "pcsf_model_set", "pcsf_pt_build", "pcsf_pt_get", "pcsf_batch_upload",
     "pcsf_batch_upload_alignments", "pcsf_batch_upload_alignments_parts", "pcsf_batch_nregions", "pcsf_batch_ncols", "pcsf_lpr_all", "pcsf_score_alignments", "pcsf_lpr",
-    "pcsf_models_set", "pcsf_omega_models_set", "pcsf_model_get", "pcsf_pt_build_pairs", "pcsf_lpr_pairs", "pcsf_column_terms", "pcsf_maximize_lpr", "pcsf_maximize_lpr_multi", "pcsf_last_ms", "pcsf_launch_count", "pcsf_table_level", "pcsf_last_launch_info", "pcsf_tree_n_leaves", "pcsf_total_ms", "pcsf_posteriors", "pcsf_host_alloc", "pcsf_host_free", "pcsf_counter", "pcsf_omega_cache_reset", "pcsf_omega_models_set_cached",
+    "pcsf_models_set", "pcsf_omega_models_set", "pcsf_model_get", "pcsf_pt_build_pairs", "pcsf_lpr_pairs", "pcsf_column_terms", "pcsf_maximize_lpr", "pcsf_maximize_lpr_multi", "pcsf_last_ms", "pcsf_launch_count", "pcsf_table_level", "pcsf_last_launch_info", "pcsf_tree_n_leaves", "pcsf_total_ms", "pcsf_posteriors", "pcsf_counter", "pcsf_omega_cache_reset", "pcsf_omega_models_set_cached",
 ]
 
 PCSF_OK = 0
@@ -70,10 +70,6 @@ def load():
     L.pcsf_maximize_lpr_multi.argtypes = [vp, ctypes.c_int, vp, dbl, dbl, dbl, dbl, vp, vp, vp, vp, vp]
     L.pcsf_last_ms.argtypes = [vp, ctypes.c_int]
     L.pcsf_last_ms.restype = dbl
-    L.pcsf_host_alloc.argtypes = [ctypes.c_size_t]
-    L.pcsf_host_alloc.restype = vp
-    L.pcsf_host_free.argtypes = [vp]
-    L.pcsf_host_free.restype = None
     L.pcsf_posteriors.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     L.pcsf_counter.argtypes = [vp, ctypes.c_int]
     L.pcsf_counter.restype = i64

@@ -210,7 +210,7 @@ int main(int argc, char** argv) {
         };
         struct Chunk {
             std::vector<Slot> slots;
-            std::shared_ptr<NtBuffer> nt;  // nucleotide rows of the chunk's alignments (fast form): handed to the batch, not copied
+            std::shared_ptr<std::vector<uint8_t>> nt;  // nucleotide rows of the chunk's alignments (fast form): handed to the batch, not copied
         };
         unsigned nthreads = std::max(1u, std::thread::hardware_concurrency());
         if (opt.procs > 1) nthreads = (unsigned)opt.procs;
@@ -219,14 +219,13 @@ int main(int argc, char** argv) {
         const size_t chunk = 32, n_chunks = (n_files + chunk - 1) / chunk;
         const size_t window = std::max<size_t>(4, 4 * (size_t)nthreads);  // chunks in flight
         std::vector<Chunk> ring(window);
-        PinnedArena::instance().use_pinned(opt.strategy != STRAT_NOP && !std::getenv("PCSF_PAGEABLE"));  // PCSF_PAGEABLE=1: A/B runs
         BufferPool nt_pool;
         std::vector<char> ready(window, 0);
         std::mutex mu;
         std::condition_variable cv_ready, cv_space;
         size_t next_chunk = 0, consumed = 0;  // under mu
         bool stop = false;
-        auto prepare_one = [&](size_t i, Slot& sl, NtBuffer& nt_buf) {
+        auto prepare_one = [&](size_t i, Slot& sl, std::vector<uint8_t>& nt_buf) {
             const std::string& fn = fns[i];
             const std::string name = fn.empty() ? "(STDIN)" : fn;
             static thread_local std::vector<char> text;  // reused: no allocation per file

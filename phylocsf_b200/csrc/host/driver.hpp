@@ -34,7 +34,6 @@
 #include "alignment.hpp"
 #include "omega_strategy.hpp"
 #include "paramset.hpp"
-#include "pinned_buffer.hpp"
 
 namespace pcsf {
 namespace host {
@@ -93,8 +92,8 @@ struct ScoreRecord {
 // done, so after the first few batches no buffer is allocated (or page-faulted in) again.
 class BufferPool {
   public:
-    std::shared_ptr<NtBuffer> get() {
-        NtBuffer* v = nullptr;
+    std::shared_ptr<std::vector<uint8_t>> get() {
+        std::vector<uint8_t>* v = nullptr;
         {
             std::lock_guard<std::mutex> lk(st->mu);
             if (!st->free.empty()) {
@@ -102,10 +101,10 @@ class BufferPool {
                 st->free.pop_back();
             }
         }
-        if (!v) v = new NtBuffer();
+        if (!v) v = new std::vector<uint8_t>();
         v->clear();
         std::shared_ptr<State> keep = st;
-        return std::shared_ptr<NtBuffer>(v, [keep](NtBuffer* q) {
+        return std::shared_ptr<std::vector<uint8_t>>(v, [keep](std::vector<uint8_t>* q) {
             std::lock_guard<std::mutex> lk(keep->mu);
             keep->free.emplace_back(q);
         });
@@ -114,7 +113,7 @@ class BufferPool {
   private:
     struct State {
         std::mutex mu;
-        std::vector<std::unique_ptr<NtBuffer>> free;
+        std::vector<std::unique_ptr<std::vector<uint8_t>>> free;
     };
     std::shared_ptr<State> st = std::make_shared<State>();
 };
@@ -145,7 +144,7 @@ struct Batch {
     // side only until it lets go of them) as the pieces of pcsf_batch_upload_alignments_parts.
     bool nt_form = false;
     struct NtPart {
-        std::shared_ptr<NtBuffer> buf;
+        std::shared_ptr<std::vector<uint8_t>> buf;
         size_t begin, end;               // the bytes of `buf` this batch uses
     };
     std::vector<NtPart> parts;
@@ -462,7 +461,7 @@ class Driver {
     // needs the rows on the host, blank or padded lines, a character outside ACGTacgtNn-uU, an unknown or
     // repeated species, ragged rows, a gapped reference - returns false WITHOUT judging it: the caller then
     // runs prepare(), which applies the reference's checks in the reference's order with its messages.
-    bool prepare_fast(const std::string& name, const char* data, size_t n, Prepared& p, NtBuffer& nt_buf) const {
+    bool prepare_fast(const std::string& name, const char* data, size_t n, Prepared& p, std::vector<uint8_t>& nt_buf) const {
         if (opt.orf != AsIs || opt.strategy == STRAT_OMEGA || no_fast_reader) return false;
         if (opt.bls && !bls_table.usable()) return false;
         if (n == 0 || data[0] != '>') return false;
@@ -593,7 +592,7 @@ class Driver {
         return true;
     }
     // prepare() on raw text: the fast form when it applies, else the general one on the text's lines
-    Prepared prepare_text(const std::string& name, const char* data, size_t n, NtBuffer& nt_buf) const {
+    Prepared prepare_text(const std::string& name, const char* data, size_t n, std::vector<uint8_t>& nt_buf) const {
         Prepared p;
         if (prepare_fast(name, data, n, p, nt_buf)) {
             n_fast++;
@@ -669,7 +668,7 @@ class Driver {
     // Appends a prepared alignment to the current batch (in input order). Returns false when the run
     // must stop (the alignment aborted: src/PhyloCSF.ml:381-388 exits -1).
     // `nt_buf`: the buffer prepare_text filled for this alignment (nucleotide form only).
-    bool append(Prepared&& p, std::ostream& out, const std::shared_ptr<NtBuffer>& nt_buf = nullptr) {
+    bool append(Prepared&& p, std::ostream& out, const std::shared_ptr<std::vector<uint8_t>>& nt_buf = nullptr) {
         if (!p.abort.empty()) {
             finish(out);
             out << p.job.name << "\tabort\t" << p.abort << "\n";

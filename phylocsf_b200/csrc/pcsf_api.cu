@@ -758,19 +758,6 @@ void pcsf_destroy(pcsf_ctx* ctx) {
     delete ctx;
 }
 
-void* pcsf_host_alloc(size_t bytes) {
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    return p;
-}
-
-void pcsf_host_free(void* p) {
-    if (p) cudaFreeHost(p);
-}
-
 const char* pcsf_last_error(const pcsf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int pcsf_stream_set(pcsf_ctx* ctx, void* cuda_stream) {
