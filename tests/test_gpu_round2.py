@@ -459,3 +459,56 @@ def test_subtree_tables_are_shared_between_contexts_and_follow_the_cumulative_ru
     again = d.lpr_all([0, 1])
     assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
     d.close()
+
+
+def _all_sets():
+    from tools import golden_params as gp
+
+    return gp.set_names()
+
+
+@pytest.mark.parametrize("pset", _all_sets())
+def test_fixed_and_posteriors_on_every_shipped_parameter_set(params_base, pset):
+    """All 14 shipped parameter sets (7 to 120 species; 20flies has a zero-length branch, 23flies / 26worms / 7yeast
+    frequencies that sum to 1 +- 2e-6): fixed-strategy scores in both kernel forms and the outside pass against the oracle."""
+    import phylocsf_b200 as pb
+
+    ps = H.oracle_paramset(params_base, pset)
+    n = ps.tree.n_leaves
+    rng = np.random.default_rng(abs(hash(pset)) % 1000)
+    regs = [o.simulate_columns(ps.model.coding_model.model(1.0), 21, rng), o.simulate_columns(ps.model.noncoding_model.model(1.0), 12, rng)]
+    regs[0][2, n // 2:] = 64
+    lo, eo = H.oracle_fixed(ps, regs)
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    ctx.pt_build(1, [1.0])
+    off, codes = H.regions_to_batch(regs)
+    ctx.batch_upload(off, codes)
+    for form in (pb.Context.FORM_NARROW, pb.Context.FORM_WIDE):
+        ctx.option_set(pb.Context.OPT_PRUNE_FORM, form)
+        lpr, elpr, st = ctx.lpr_all([0, 1])
+        assert (st == 0).all()
+        assert np.abs(H.DB * (lpr - lo)).max() < 1e-7 and np.abs(H.DB * (elpr - eo)).max() < 1e-7
+    post, ec, z = ctx.posteriors(1, 0, nodes=[2 * n - 2, n])
+    zo, po, eco = o.posteriors_columns(ps.model.noncoding_model.model(1.0), codes)
+    np.testing.assert_allclose(z, zo, rtol=1e-10, atol=0)
+    np.testing.assert_allclose(post[0], po[:, 2 * n - 2], atol=2e-12)
+    np.testing.assert_allclose(ec, eco, atol=1e-10)
+    ctx.close()
+
+
+def test_negative_offsets_are_rejected(params_base):
+    """Round-1 advisor finding: a negative aln_off made the library read host memory before the caller's buffer."""
+    import phylocsf_b200 as pb
+
+    ps = H.oracle_paramset(params_base, "12flies")
+    ctx = H.make_context(ps)
+    ctx.pt_build(0, [1.0])
+    nt = np.full((2, 12, 30), ord("A"), dtype=np.uint8)
+    for call in (lambda: ctx.batch_upload_alignments([0, -360], [30, 30], nt, 3),
+                 lambda: ctx.score_alignments([0, -360], [30, 30], nt, 3, [0]),
+                 lambda: ctx.batch_upload_alignments([0, 360], [30, -1], nt, 3)):
+        with pytest.raises(pb.PcsfError) as e:
+            call()
+        assert e.value.code == -1
+    ctx.close()
