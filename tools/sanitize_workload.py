@@ -76,5 +76,21 @@ from phylocsf_b200 import host  # noqa: E402
 if not ONLY_NEW:
     sc, dg, st = host.omega_score(ctx, off[:3], codes[: off[2]])
     assert (st == 0).all() and np.isfinite(sc).all()
+# shared subtree tables: a second context on the same GPU attaches to the first one's block, the first one goes away
+ctx.option_set(2, 2)
+ctx.option_set(3, 2)
+ctx.pt_build(0, [1.0])
+ctx.batch_upload(off, codes)
+ra = ctx.lpr_all([0])
+ctx2 = H.make_context(ps)
+ctx2.option_set(2, 2)
+ctx2.option_set(3, 2)
+ctx2.pt_build(0, [1.0])
+ctx2.batch_upload(off, codes)
+rb = ctx2.lpr_all([0])
+assert ctx2.table_level(0) == ctx.table_level(0) == 3 and np.array_equal(ra[0], rb[0])
 ctx.close()
+rc = ctx2.lpr_all([0])
+assert np.array_equal(rb[0], rc[0])
+ctx2.close()
 print("sanitize workload ok")
