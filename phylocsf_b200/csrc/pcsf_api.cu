@@ -126,7 +126,7 @@ struct pcsf_ctx {
     DevBuf d_eig_cache, d_eig_valid, d_eig_slots, d_eig_sweeps;  // K5 warm starts (pcsf_omega_models_set_cached)
     int64_t eig_slots = 0;
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // pcsf_counter: 0 K1 slots built, 1 codon-column evaluations pruned, 2 K5 matrices, 3 K5 sweeps, 4 tiles
-    DevBuf d_out_tree, d_out_scratch, d_out_gacc, d_out_post, d_out_ecounts, d_out_z, d_out_nodes;  // K6 (pcsf_posteriors)
+    DevBuf d_out_tree, d_out_scratch, d_out_gacc, d_out_post, d_out_ecounts, d_out_z, d_out_nodes, d_out_images;  // K6 (pcsf_posteriors)
     // pcsf_score_alignments: double-buffered chunk staging on a second stream
     DevBuf pipe_nt[2], pipe_aln_off[2], pipe_aln_len[2], pipe_codes[2], pipe_roff[2];
     cudaStream_t copy_stream = nullptr;
@@ -154,6 +154,7 @@ struct pcsf_ctx {
     int rescale = 0;  // PCSF_OPT_RESCALE
     uint64_t tree_hash = 0;
     int share_tables = 1;  // PCSF_SHARE_TABLES=0: every context builds its own subtree tables (as in round 1)
+    int k6_plain = 0;      // PCSF_K6_PLAIN=1: pcsf_posteriors runs the plain-FP64 form of K6 instead of the DMMA form
     int last_form = 0, last_level = 0, last_grid = 0;  // what the most recent pruning launch ran (pcsf_last_launch_info)
     int64_t last_tiles = 0;
     void* timeline = nullptr;  // PCSF_TIMELINE debug builds (tools/timeline.py)
@@ -709,6 +710,7 @@ int pcsf_create(int device_id, pcsf_ctx** out) {
     if (const char* e = getenv("PCSF_CHERRY_TABLES")) ctx->cherry_mode = atoi(e);
     if (const char* e = getenv("PCSF_RESCALE")) ctx->rescale = atoi(e) ? 1 : 0;
     if (const char* e = getenv("PCSF_SHARE_TABLES")) ctx->share_tables = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("PCSF_K6_PLAIN")) ctx->k6_plain = atoi(e) ? 1 : 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     ctx->stream = ctx->own_stream;
     for (auto& ev : ctx->ev)
@@ -1604,6 +1606,8 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
     // two CTAs per SM (~105 KB of shared memory each): the walk is a chain of short products separated by barriers, so
     // co-resident CTAs are what hides its latencies
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, 2LL * ctx->num_sms));
+    static_assert(OUT_TC == OD_TC, "both forms of K6 walk 64-column tiles and share the scratch blocks");
+    const bool plain = ctx->k6_plain != 0;  // PCSF_K6_PLAIN=1: the plain-FP64 form (A/B runs, differential tests)
     TRY(reserve(ctx, ctx->d_out_tree, tree.size() * sizeof(int32_t)));
     TRY(reserve(ctx, ctx->d_out_scratch, sizeof(double) * (size_t)grid * 3 * ni * OUT_TC * 64));
     if (out_ecounts) {
@@ -1616,6 +1620,7 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
         CU(cudaMemcpyAsync(ctx->d_out_nodes.p, nodes, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (out_z) TRY(reserve(ctx, ctx->d_out_z, sizeof(double) * std::max<int64_t>(total, 1)));
+    if (!plain) TRY(reserve(ctx, ctx->d_out_images, sizeof(double) * (size_t)std::max(1, nl - 2) * 4096));
     CU(cudaMemcpyAsync(ctx->d_out_tree.p, tree.data(), tree.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     OutsideParams p;
     memset(&p, 0, sizeof(p));
@@ -1633,16 +1638,27 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
     p.post_nodes = (const int32_t*)ctx->d_out_nodes.p;
     p.post_out = (double*)ctx->d_out_post.p;
     p.z_out = out_z ? (double*)ctx->d_out_z.p : nullptr;
-    const int smem = (4096 + 2 * OUT_TC * OUT_XS + OUT_TC) * (int)sizeof(double) + r16(OUT_TC * nl);
+    p.pt_images = (const double*)ctx->d_out_images.p;
+    const int smem = plain ? (4096 + 2 * OUT_TC * OUT_XS + OUT_TC) * (int)sizeof(double) + r16(OUT_TC * nl) : OD_SMEM_FIXED + r16(OD_TC * nl);
     if (smem > ctx->prune_smem_optin) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_posteriors: tree too large for the kernel's shared memory");
-    CU(cudaFuncSetAttribute(outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    outside_kernel<<<grid, OUT_THREADS, smem, ctx->stream>>>(p);
+    if (plain) {
+        CU(cudaFuncSetAttribute(outside_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        outside_kernel<<<grid, OUT_THREADS, smem, ctx->stream>>>(p);
+    } else {
+        if (nl > 2) {
+            outside_transpose_kernel<<<(unsigned)(((size_t)(nl - 2) * 4096 + 255) / 256), 256, 0, ctx->stream>>>(p.tables, nl, nl - 2, (double*)ctx->d_out_images.p);
+            CU(cudaGetLastError());
+            ctx->launches++;
+        }
+        CU(cudaFuncSetAttribute(outside_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        outside_dmma_kernel<<<grid, OD_THREADS, smem, ctx->stream>>>(p);
+    }
     CU(cudaGetLastError());
     ctx->launches++;
     if (out_ecounts) {
         outside_reduce_kernel<<<(unsigned)(((size_t)nbr * 4096 + 255) / 256), 256, 0, ctx->stream>>>(
-            (const double*)ctx->d_out_gacc.p, grid, nbr, nl, p.tables, (double*)ctx->d_out_ecounts.p);
+            (const double*)ctx->d_out_gacc.p, grid, nbr, nl, p.tables, (double*)ctx->d_out_ecounts.p, plain ? 0 : 1);
         CU(cudaGetLastError());
         ctx->launches++;
     }

@@ -1478,6 +1478,7 @@ struct OutsideParams {
     const int32_t* post_nodes;
     double* post_out;        // [n_post][total_cols][64]
     double* z_out;           // [total_cols] or null
+    const double* pt_images; // [n_leaves - 2][4096]: transposed fragment images of the internal edges (DMMA form)
 };
 
 __device__ __forceinline__ double out_p_entry(const double* slot, bool leaf, int a, int b) {
@@ -1701,14 +1702,280 @@ __global__ void __launch_bounds__(OUT_THREADS, 2) outside_kernel(const OutsidePa
     }
 }
 
-// ecounts[br][a][b] = P_br[a][b] * sum over CTAs (ascending) of G[cta][br][a][b]
+// ---- K6 on the DMMA pipe ---------------------------------------------------------------------------
+// Same walk, same scratch blocks, four warps per CTA with 16 columns each held in the accumulator layout of the pruning
+// kernels (column 8T + g, states 8j + 2t, 8j + 2t + 1), two CTAs per SM:
+//   inside  msg_i = alpha_i x P_i^T   the pruning contraction: A fragments are the alpha registers, B the fragment-ordered
+//                                     image of the slot, brought into shared memory by one bulk copy (TMA)
+//   outside beta_i = inter x P_i      the same loop over the transposed image (outside_transpose_kernel, once per call)
+//   G_i    += U^T V                   warp w owns rows 16w .. 16w+15 of G: U = inter / z and V = alpha_i (or the leaf's
+//                                     indicator rows) go through shared memory (row stride 68: fragment loads are
+//                                     conflict-free), 256 DMMAs per warp like a contraction
+// alpha, msg, beta and the G blocks are stored in the owning thread's register order (32 consecutive double2 per warp
+// instruction); outside_reduce_kernel undoes the order of G. Two barriers per node: one before the image / U / V are
+// overwritten, one before G's fragments are read.
+constexpr int OD_THREADS = 128;
+constexpr int OD_TC = 64;
+constexpr int OD_TS = 68;
+constexpr int OD_SMEM_FIXED = FRAG_BYTES + 2 * OD_TC * OD_TS * 8 + 16;  // image, U, V, one mbarrier
+
+// transposed fragment images of the internal edges: out[i][frag_index(x, y)] = P_i[y][x]
+__global__ void outside_transpose_kernel(const double* __restrict__ tables, int n_leaves, int n_images, double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_images * 4096) return;
+    const int i = (int)(idx >> 12), e = (int)(idx & 4095);
+    const int j = e >> 9, s = (e >> 5) & 15, ln = e & 31;  // inverse of frag_index: e = frag_index(x, y)
+    const int x = 8 * j + (ln >> 2), y = 8 * (s >> 1) + 2 * (ln & 3) + (s & 1);
+    out[idx] = tables[(size_t)(n_leaves + i) * PT_SLOT + frag_index(y, x)];
+}
+
+__global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const OutsideParams p) {
+    extern __shared__ __align__(128) unsigned char odsm[];
+    double* Pimg = reinterpret_cast<double*>(odsm);
+    double* U = Pimg + 4096;
+    double* V = U + OD_TC * OD_TS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(V + OD_TC * OD_TS);
+    uint8_t* codes_s = reinterpret_cast<uint8_t*>(bar + 2);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int nl = p.n_leaves, n = 2 * nl - 1, ni = nl - 1;
+    // scratch blocks of this CTA in register order: kind 0 alpha, 1 msg, 2 beta; element (T, j) at + (T * 8 + j) * 32
+    double2* sc = reinterpret_cast<double2*>(p.scratch + (size_t)blockIdx.x * 3 * ni * OD_TC * 64) + w * 512 + lane;
+    auto blk = [&](int kind, int node) { return sc + (size_t)(kind * ni + node - nl) * 2048; };
+    double2* gacc = p.gacc ? reinterpret_cast<double2*>(p.gacc + (size_t)blockIdx.x * (n - 1) * 4096) + w * 512 + lane : nullptr;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (p.gacc) {
+        double2* z2 = reinterpret_cast<double2*>(p.gacc + (size_t)blockIdx.x * (n - 1) * 4096);
+        for (size_t i = tid; i < (size_t)(n - 1) * 2048; i += OD_THREADS) z2[i] = make_double2(0.0, 0.0);
+    }
+    uint32_t phase = 0;
+    double2 pri[8];  // prior at this lane's states
+#pragma unroll
+    for (int j = 0; j < 8; j++) pri[j] = *reinterpret_cast<const double2*>(p.prior + 8 * j + 2 * t);
+
+    // every thread is past its reads of the image, U and V; thread 0 starts the next image's copy
+    auto turn = [&](const double* image) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (image && tid == 0) {
+            mbar_expect_tx(bar, FRAG_BYTES);
+            tma_bulk_g2s(Pimg, image, FRAG_BYTES, bar);
+        }
+    };
+    auto load_msg = [&](int node, double2 (&m)[2][8]) {
+        if (node < nl) {
+#pragma unroll
+            for (int T = 0; T < 2; T++) {
+                int code = codes_s[(16 * w + 8 * T + g) * nl + node];
+                code = code > 64 ? 64 : code;
+                const double2* row = reinterpret_cast<const double2*>(p.tables + (size_t)node * PT_SLOT + code * 64 + 2 * t);
+#pragma unroll
+                for (int j = 0; j < 8; j++) m[T][j] = __ldg(row + 4 * j);
+            }
+        } else {
+            const double2* b = blk(1, node);
+#pragma unroll
+            for (int T = 0; T < 2; T++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) m[T][j] = b[(T * 8 + j) * 32];
+        }
+    };
+    auto store_blk = [&](double2* b, const double2 (&v)[2][8]) {
+#pragma unroll
+        for (int T = 0; T < 2; T++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) b[(T * 8 + j) * 32] = v[T][j];
+    };
+    // y[c][o] = sum_k x[c][k] * M[o][k], M's fragment-ordered image in shared memory
+    auto contract = [&](const double2 (&x)[2][8], double2 (&y)[2][8]) {
+        const double* Pb = Pimg + lane;
+#pragma unroll
+        for (int T = 0; T < 2; T++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) y[T][j] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int s = 0; s < 16; s++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double bf = Pb[(j * 16 + s) * 32];
+#pragma unroll
+                for (int T = 0; T < 2; T++) dmma(y[T][j].x, y[T][j].y, (s & 1) ? x[T][s >> 1].y : x[T][s >> 1].x, bf);
+            }
+        }
+    };
+
+    const int64_t n_tiles = (p.total_cols + OD_TC - 1) / OD_TC;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t col0 = tile * OD_TC;
+        const int ncols = (int)min((int64_t)OD_TC, p.total_cols - col0);
+        __syncthreads();
+        for (int i = tid; i < OD_TC * nl; i += OD_THREADS) codes_s[i] = i < ncols * nl ? p.codes[(size_t)col0 * nl + i] : (uint8_t)64;
+        // ---------------- inside ----------------
+        double2 cur[2][8];
+        for (int i = nl; i < n; i++) {
+            turn(i < n - 1 ? p.tables + (size_t)i * PT_SLOT : nullptr);  // (the first turn also publishes the tile's codes)
+            double2 ml[2][8], mr[2][8];
+            load_msg(p.children[2 * (i - nl)], ml);
+            load_msg(p.children[2 * (i - nl) + 1], mr);
+#pragma unroll
+            for (int T = 0; T < 2; T++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) cur[T][j] = make_double2(ml[T][j].x * mr[T][j].x, ml[T][j].y * mr[T][j].y);
+            store_blk(blk(0, i), cur);
+            if (i == n - 1) break;
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            double2 y[2][8];
+            contract(cur, y);
+            store_blk(blk(1, i), y);
+        }
+        // ---------------- root: z = alpha_root . prior ----------------
+        double z[2];
+        bool live[2];
+#pragma unroll
+        for (int T = 0; T < 2; T++) {
+            double zp = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                zp += cur[T][j].x * pri[j].x;
+                zp += cur[T][j].y * pri[j].y;
+            }
+            zp += __shfl_xor_sync(0xffffffffu, zp, 1);
+            zp += __shfl_xor_sync(0xffffffffu, zp, 2);
+            z[T] = zp;
+            const int c = 16 * w + 8 * T + g;
+            live[T] = c < ncols && zp > 0.0;
+            if (p.z_out && t == 0 && c < ncols) p.z_out[col0 + c] = zp;
+        }
+        // ---------------- outside + expected counts, node by node from the top ----------------
+        for (int i = n - 2; i >= 0; i--) {
+            const int par = p.parent[i], sib = p.sibling[i];
+            turn(i >= nl ? p.pt_images + (size_t)(i - nl) * 4096 : nullptr);
+            double2 inter[2][8];
+            load_msg(sib, inter);
+            if (par == n - 1) {
+#pragma unroll
+                for (int T = 0; T < 2; T++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        inter[T][j].x *= pri[j].x;
+                        inter[T][j].y *= pri[j].y;
+                    }
+            } else {
+                const double2* bp = blk(2, par);
+#pragma unroll
+                for (int T = 0; T < 2; T++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double2 b = bp[(T * 8 + j) * 32];
+                        inter[T][j].x *= b.x;
+                        inter[T][j].y *= b.y;
+                    }
+            }
+            if (gacc) {  // U[c][a] = inter / z on live columns, V[c][b] = alpha_i (a leaf: its indicator row)
+#pragma unroll
+                for (int T = 0; T < 2; T++) {
+                    const int c = 16 * w + 8 * T + g;
+                    double2* ur = reinterpret_cast<double2*>(U + c * OD_TS + 2 * t);
+                    double2* vr = reinterpret_cast<double2*>(V + c * OD_TS + 2 * t);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        ur[4 * j] = live[T] ? make_double2(inter[T][j].x / z[T], inter[T][j].y / z[T]) : make_double2(0.0, 0.0);
+                    if (i < nl) {
+                        const int code = codes_s[c * nl + i];
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            vr[4 * j] = make_double2((code >= 64 || code == 8 * j + 2 * t) ? 1.0 : 0.0,
+                                                     (code >= 64 || code == 8 * j + 2 * t + 1) ? 1.0 : 0.0);
+                    } else {
+                        const double2* ai = blk(0, i);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) vr[4 * j] = ai[(T * 8 + j) * 32];
+                    }
+                }
+            }
+            if (i >= nl) {  // beta_i[b] = sum_a inter[a] P_i[a][b]
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                double2 y[2][8];
+                contract(inter, y);
+                store_blk(blk(2, i), y);
+            }
+            if (gacc) {
+                __syncthreads();
+                double2 ga[2][8];
+#pragma unroll
+                for (int M = 0; M < 2; M++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) ga[M][j] = make_double2(0.0, 0.0);
+                const double* ua = U + t * OD_TS + 16 * w + g;
+                const double* vb = V + t * OD_TS + g;
+#pragma unroll
+                for (int s = 0; s < 16; s++) {
+                    const double a0 = ua[4 * s * OD_TS], a1 = ua[4 * s * OD_TS + 8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double bf = vb[4 * s * OD_TS + 8 * j];
+                        dmma(ga[0][j].x, ga[0][j].y, a0, bf);
+                        dmma(ga[1][j].x, ga[1][j].y, a1, bf);
+                    }
+                }
+                double2* G = gacc + (size_t)i * 2048;
+#pragma unroll
+                for (int M = 0; M < 2; M++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        double2 v = G[(M * 8 + j) * 32];
+                        v.x += ga[M][j].x;
+                        v.y += ga[M][j].y;
+                        G[(M * 8 + j) * 32] = v;
+                    }
+            }
+        }
+        // ---------------- node posteriors (PhyloLik.ml:127-138) ----------------
+        for (int q = 0; q < p.n_post; q++) {
+            const int node = p.post_nodes[q];
+#pragma unroll
+            for (int T = 0; T < 2; T++) {
+                const int c = 16 * w + 8 * T + g;
+                if (c >= ncols) continue;
+                double2* out = reinterpret_cast<double2*>(p.post_out + ((size_t)q * p.total_cols + col0 + c) * 64 + 2 * t);
+                const double zc = z[T];
+                if (node < nl) {
+                    const int code = codes_s[c * nl + node];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        out[4 * j] = zc == 0.0 ? make_double2(0.0, 0.0)
+                                               : make_double2((code >= 64 || code == 8 * j + 2 * t) ? 1.0 : 0.0,
+                                                              (code >= 64 || code == 8 * j + 2 * t + 1) ? 1.0 : 0.0);
+                } else {
+                    const double2* ai = blk(0, node);
+                    const double2* bi = blk(2, node);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const double2 a = ai[(T * 8 + j) * 32];
+                        const double2 b = node == n - 1 ? pri[j] : bi[(T * 8 + j) * 32];
+                        out[4 * j] = zc == 0.0 ? make_double2(0.0, 0.0) : make_double2(a.x * b.x / zc, a.y * b.y / zc);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ecounts[br][a][b] = P_br[a][b] * sum over CTAs (ascending) of G[cta][br][a][b]; reg_order: the G blocks are in the
+// register order of outside_dmma_kernel (warp a / 16, m-tile (a / 8) % 2, n-tile b / 8, lane 4 (a % 8) + (b / 2) % 4, b % 2)
 __global__ void outside_reduce_kernel(const double* __restrict__ gacc, int n_cta, int n_branches, int n_leaves,
-                                      const double* __restrict__ tables, double* __restrict__ ecounts) {
+                                      const double* __restrict__ tables, double* __restrict__ ecounts, int reg_order) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_branches * 4096) return;
     const int br = (int)(i >> 12), a = (int)((i >> 6) & 63), b = (int)(i & 63);
+    const int e = reg_order ? (((((a >> 4) * 2 + ((a >> 3) & 1)) * 8 + (b >> 3)) * 32 + ((a & 7) * 4 + ((b >> 1) & 3))) * 2 + (b & 1)) : a * 64 + b;
     double s = 0.0;
-    for (int k = 0; k < n_cta; k++) s += gacc[((size_t)k * n_branches + br) * 4096 + a * 64 + b];
+    for (int k = 0; k < n_cta; k++) s += gacc[((size_t)k * n_branches + br) * 4096 + e];
     ecounts[i] = out_p_entry(tables + (size_t)br * PT_SLOT, br < n_leaves, a, b) * s;
 }
 

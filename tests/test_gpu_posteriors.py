@@ -101,3 +101,30 @@ def test_posteriors_empty_batch(params_base):
     post, ec, z = ctx.posteriors(0, 0, nodes=[22, 3])
     assert post.shape == (2, 0, 64) and z.size == 0 and (ec == 0).all()
     ctx.close()
+
+
+def test_posteriors_both_forms_of_the_kernel_agree(params_base, monkeypatch):
+    """pcsf_posteriors runs K6 on the DMMA pipe; PCSF_K6_PLAIN=1 (read when the context is created) selects the plain-FP64
+    form. Same walk, different summation order inside the 64-term products: z, posteriors and expected counts agree to
+    rounding on 29mammals columns spanning several tiles and CTAs, gaps and an impossible column included."""
+    ps = H.oracle_paramset(params_base, "29mammals")
+    rng = np.random.default_rng(21)
+    regs = [o.simulate_columns(ps.model.coding_model.model(1.0), 700, rng), o.simulate_columns(ps.model.noncoding_model.model(1.0), 333, rng)]
+    regs[0][rng.random(regs[0].shape) < 0.05] = 64
+    regs[1][5, :] = rng.integers(0, 64, size=29)
+    off, codes = H.regions_to_batch(regs)
+    nodes = list(range(ps.tree.size))
+    res = []
+    for plain in ("0", "1"):
+        monkeypatch.setenv("PCSF_K6_PLAIN", plain)
+        ctx = H.make_context(ps)
+        ctx.batch_upload(off, codes)
+        ctx.pt_build(0, [1.1])
+        res.append(ctx.posteriors(0, 0, nodes=nodes))
+        ctx.close()
+    (p0, e0, z0), (p1, e1, z1) = res
+    np.testing.assert_allclose(z0, z1, rtol=1e-13, atol=0)
+    assert ((z0 == 0) == (z1 == 0)).all()
+    np.testing.assert_allclose(p0, p1, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(e0, e1, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(e0.sum(axis=(1, 2)), float((z0 > 0).sum()), rtol=1e-11)
