@@ -1789,6 +1789,14 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
 #pragma unroll
             for (int j = 0; j < 8; j++) b[(T * 8 + j) * 32] = v[T][j];
     };
+    // ask L2 for a block this thread will read a node later (blocks written during the inside pass have long left L2 when
+    // the outside pass comes back for them: 296 CTAs x 9 MB of scratch against 126 MB)
+    auto prefetch_blk = [&](const double2* b) {
+        if ((lane & 7) == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + k * 32));
+        }
+    };
     // y[c][o] = sum_k x[c][k] * M[o][k], M's fragment-ordered image in shared memory
     auto contract = [&](const double2 (&x)[2][8], double2 (&y)[2][8]) {
         const double* Pb = Pimg + lane;
@@ -1833,7 +1841,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             store_blk(blk(1, i), y);
         }
         // ---------------- root: z = alpha_root . prior ----------------
-        double z[2];
+        double z[2], zinv[2];
         bool live[2];
 #pragma unroll
         for (int T = 0; T < 2; T++) {
@@ -1848,6 +1856,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             z[T] = zp;
             const int c = 16 * w + 8 * T + g;
             live[T] = c < ncols && zp > 0.0;
+            zinv[T] = live[T] ? 1.0 / zp : 0.0;  // one division per column: 32 per thread and branch cost a third of the kernel
             if (p.z_out && t == 0 && c < ncols) p.z_out[col0 + c] = zp;
         }
         // ---------------- outside + expected counts, node by node from the top ----------------
@@ -1875,7 +1884,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                         inter[T][j].y *= b.y;
                     }
             }
-            if (gacc) {  // U[c][a] = inter / z on live columns, V[c][b] = alpha_i (a leaf: its indicator row)
+            if (gacc) {  // U[c][a] = inter / z on live columns (else 0), V[c][b] = alpha_i (a leaf: its indicator row)
 #pragma unroll
                 for (int T = 0; T < 2; T++) {
                     const int c = 16 * w + 8 * T + g;
@@ -1883,7 +1892,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                     double2* vr = reinterpret_cast<double2*>(V + c * OD_TS + 2 * t);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
-                        ur[4 * j] = live[T] ? make_double2(inter[T][j].x / z[T], inter[T][j].y / z[T]) : make_double2(0.0, 0.0);
+                        ur[4 * j] = make_double2(inter[T][j].x * zinv[T], inter[T][j].y * zinv[T]);
                     if (i < nl) {
                         const int code = codes_s[c * nl + i];
 #pragma unroll
@@ -1896,6 +1905,11 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                         for (int j = 0; j < 8; j++) vr[4 * j] = ai[(T * 8 + j) * 32];
                     }
                 }
+            }
+            if (i >= 1) {  // the next node's operands
+                const int sn = p.sibling[i - 1];
+                if (sn >= nl) prefetch_blk(blk(1, sn));
+                if (i - 1 >= nl && gacc) prefetch_blk(blk(0, i - 1));
             }
             if (i >= nl) {  // beta_i[b] = sum_a inter[a] P_i[a][b]
                 mbar_wait(bar, phase);
@@ -1923,15 +1937,15 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                         dmma(ga[1][j].x, ga[1][j].y, a1, bf);
                     }
                 }
-                double2* G = gacc + (size_t)i * 2048;
+                // this CTA's block, this thread's elements, tile after tile: reductions without a return value keep the
+                // order (and the bits) of a load-add-store and do not wait for the line
+                double* G = reinterpret_cast<double*>(gacc + (size_t)i * 2048);
 #pragma unroll
                 for (int M = 0; M < 2; M++)
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        double2 v = G[(M * 8 + j) * 32];
-                        v.x += ga[M][j].x;
-                        v.y += ga[M][j].y;
-                        G[(M * 8 + j) * 32] = v;
+                        atomicAdd(G + (M * 8 + j) * 64, ga[M][j].x);
+                        atomicAdd(G + (M * 8 + j) * 64 + 1, ga[M][j].y);
                     }
             }
         }

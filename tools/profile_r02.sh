@@ -30,8 +30,8 @@ for part in $parts; do
       $NCU_FULL -k regex:subtree_table -c 3 -f -o gpurun_out/r02_subtree_tables \
         python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/r02_tables.log 2>&1 ;;
     outside)    # K6
-      $NCU_FULL -k regex:outside_kernel -c 1 -f -o gpurun_out/r02_outside \
-        python tools/bench_posteriors.py 20000 > gpurun_out/r02_outside.log 2>&1 ;;
+      $NCU_FULL -k regex:outside_dmma -s 1 -c 1 -f -o gpurun_out/r02_outside_dmma \
+        python tools/bench_posteriors.py 200000 > gpurun_out/r02_outside.log 2>&1 ;;
   esac
 done
 ls -la gpurun_out/*.ncu-rep 2>/dev/null
