@@ -1591,7 +1591,7 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
     const int64_t total = ctx->total_cols;
     const Model& m = ctx->models[model_id];
     if (m.status[scale_idx] != 0) return fail(ctx, PCSF_ERR_NUMERIC, "pcsf_posteriors: the P set failed its checks (see pcsf_pt_build)");
-    std::vector<int32_t> tree(2 * (nl - 1) + 2 * n, -1);  // children | parent | sibling
+    std::vector<int32_t> tree(2 * (nl - 1) + 2 * n + 3 * (n - 1), -1);  // children | parent | sibling | steps of the outside pass
     int32_t* par = tree.data() + 2 * (nl - 1);
     int32_t* sib = par + n;
     for (int i = nl; i < n; i++) {
@@ -1601,6 +1601,37 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
         par[l] = par[r] = i;
         sib[l] = r;
         sib[r] = l;
+    }
+    {
+        // outside pass of the DMMA form, depth first: under each node its leaf children, then an internal child whose beta is
+        // parked, last the internal child the walk descends into with beta in registers (OUT_STEP_*, pcsf_kernels.cuh)
+        int32_t* steps = sib + n;
+        int ns = 0;
+        std::vector<std::pair<int, bool>> stack{{n - 1, false}};  // (node, its beta is in registers)
+        while (!stack.empty()) {
+            const auto [v, carried] = stack.back();
+            stack.pop_back();
+            int kids[2] = {tree[2 * (v - nl)], tree[2 * (v - nl) + 1]};
+            if (kids[0] >= nl && kids[1] < nl) std::swap(kids[0], kids[1]);  // leaves first
+            for (int q = 0; q < 2; q++) {
+                const int c = kids[q];
+                int fl = (q == 0 && !carried) ? OUT_STEP_LOADB : 0;
+                if (c >= nl) {
+                    const bool last = q == 1;
+                    fl |= last ? OUT_STEP_CARRY : OUT_STEP_STOREB;
+                    if (n_nodes > 0) fl |= OUT_STEP_STOREB;
+                }
+                steps[3 * ns] = c;
+                steps[3 * ns + 1] = fl;
+                ns++;
+            }
+            if (kids[0] >= nl) stack.push_back({kids[0], false});  // popped after the carried subtree is done
+            if (kids[1] >= nl) stack.push_back({kids[1], true});
+        }
+        for (int k = n - 2, next = -1; k >= 0; k--) {  // the first internal node at or after each step
+            if (steps[3 * k] >= nl) next = steps[3 * k];
+            steps[3 * k + 2] = next;
+        }
     }
     const int64_t n_tiles = (total + OUT_TC - 1) / OUT_TC;
     // two CTAs per SM (~105 KB of shared memory each): the walk is a chain of short products separated by barriers, so
@@ -1639,7 +1670,8 @@ int pcsf_posteriors(pcsf_ctx* ctx, int model_id, int scale_idx, int n_nodes, con
     p.post_out = (double*)ctx->d_out_post.p;
     p.z_out = out_z ? (double*)ctx->d_out_z.p : nullptr;
     p.pt_images = (const double*)ctx->d_out_images.p;
-    const int smem = plain ? (4096 + 2 * OUT_TC * OUT_XS + OUT_TC) * (int)sizeof(double) + r16(OUT_TC * nl) : OD_SMEM_FIXED + r16(OD_TC * nl);
+    p.steps = p.sibling + n;
+    const int smem = plain ? (4096 + 2 * OUT_TC * OUT_XS + OUT_TC) * (int)sizeof(double) + r16(OUT_TC * nl) : OD_SMEM_FIXED + od_tree_ints(nl) * 2 + r16(OD_TC * nl);
     if (smem > ctx->prune_smem_optin) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_posteriors: tree too large for the kernel's shared memory");
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (plain) {

@@ -1479,7 +1479,12 @@ struct OutsideParams {
     double* post_out;        // [n_post][total_cols][64]
     double* z_out;           // [total_cols] or null
     const double* pt_images; // [n_leaves - 2][4096]: transposed fragment images of the internal edges (DMMA form)
+    const int32_t* steps;    // [2 n_leaves - 2][3]: (node, OUT_STEP_* flags, the first internal node at or after this step or -1):
+                             // the outside pass of the DMMA form in depth-first order; children | parent | sibling | steps are one array
 };
+constexpr int OUT_STEP_LOADB = 1;   // beta of the node's parent is not in registers: read it back (the root's is the prior)
+constexpr int OUT_STEP_STOREB = 2;  // park beta_i: a later step (or a node posterior) reads it
+constexpr int OUT_STEP_CARRY = 4;   // the walk visits this node's children next: beta_i stays in registers
 
 __device__ __forceinline__ double out_p_entry(const double* slot, bool leaf, int a, int b) {
     return leaf ? slot[b * 64 + a] : slot[frag_index(a, b)];  // leaf slots hold P^T, internal ones the fragment-ordered image
@@ -1718,6 +1723,9 @@ constexpr int OD_THREADS = 128;
 constexpr int OD_TC = 64;
 constexpr int OD_TS = 68;
 constexpr int OD_SMEM_FIXED = FRAG_BYTES + 2 * OD_TC * OD_TS * 8 + 16;  // image, U, V, one mbarrier
+__host__ __device__ constexpr int od_tree_ints(int nl) {  // children | parent | sibling | steps as int16, rounded to 16 bytes
+    return (2 * (nl - 1) + 2 * (2 * nl - 1) + 3 * (2 * nl - 2) + 7) & ~7;
+}
 
 // transposed fragment images of the internal edges: out[i][frag_index(x, y)] = P_i[y][x]
 __global__ void outside_transpose_kernel(const double* __restrict__ tables, int n_leaves, int n_images, double* __restrict__ out) {
@@ -1735,9 +1743,15 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
     double* U = Pimg + 4096;
     double* V = U + OD_TC * OD_TS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(V + OD_TC * OD_TS);
-    uint8_t* codes_s = reinterpret_cast<uint8_t*>(bar + 2);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const int nl = p.n_leaves, n = 2 * nl - 1, ni = nl - 1;
+    // the tree and the outside program next to the operands: a step's loads hang off a chain of these lookups
+    int16_t* children_s = reinterpret_cast<int16_t*>(bar + 2);
+    int16_t* parent_s = children_s + 2 * ni;
+    int16_t* sibling_s = parent_s + n;
+    int16_t* steps_s = sibling_s + n;
+    uint8_t* codes_s = reinterpret_cast<uint8_t*>(children_s + od_tree_ints(nl));
+    for (int i = tid; i < 2 * ni + 2 * n + 3 * (n - 1); i += OD_THREADS) children_s[i] = (int16_t)p.children[i];
     // scratch blocks of this CTA in register order: kind 0 alpha, 1 msg, 2 beta; element (T, j) at + (T * 8 + j) * 32
     double2* sc = reinterpret_cast<double2*>(p.scratch + (size_t)blockIdx.x * 3 * ni * OD_TC * 64) + w * 512 + lane;
     auto blk = [&](int kind, int node) { return sc + (size_t)(kind * ni + node - nl) * 2048; };
@@ -1765,23 +1779,22 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             tma_bulk_g2s(Pimg, image, FRAG_BYTES, bar);
         }
     };
-    auto load_msg = [&](int node, double2 (&m)[2][8]) {
+    auto load_msg_half = [&](int node, int T, double2 (&m)[8]) {  // the message of `node` for columns 8T + g of this warp
         if (node < nl) {
+            int code = codes_s[(16 * w + 8 * T + g) * nl + node];
+            code = code > 64 ? 64 : code;
+            const double2* row = reinterpret_cast<const double2*>(p.tables + (size_t)node * PT_SLOT + code * 64 + 2 * t);
 #pragma unroll
-            for (int T = 0; T < 2; T++) {
-                int code = codes_s[(16 * w + 8 * T + g) * nl + node];
-                code = code > 64 ? 64 : code;
-                const double2* row = reinterpret_cast<const double2*>(p.tables + (size_t)node * PT_SLOT + code * 64 + 2 * t);
-#pragma unroll
-                for (int j = 0; j < 8; j++) m[T][j] = __ldg(row + 4 * j);
-            }
+            for (int j = 0; j < 8; j++) m[j] = __ldg(row + 4 * j);
         } else {
             const double2* b = blk(1, node);
 #pragma unroll
-            for (int T = 0; T < 2; T++)
-#pragma unroll
-                for (int j = 0; j < 8; j++) m[T][j] = b[(T * 8 + j) * 32];
+            for (int j = 0; j < 8; j++) m[j] = b[(T * 8 + j) * 32];
         }
+    };
+    auto load_msg = [&](int node, double2 (&m)[2][8]) {
+        load_msg_half(node, 0, m[0]);
+        load_msg_half(node, 1, m[1]);
     };
     auto store_blk = [&](double2* b, const double2 (&v)[2][8]) {
 #pragma unroll
@@ -1826,13 +1839,13 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
         for (int i = nl; i < n; i++) {
             turn(i < n - 1 ? p.tables + (size_t)i * PT_SLOT : nullptr);  // (the first turn also publishes the tile's codes)
             double2 ml[2][8], mr[2][8];
-            load_msg(p.children[2 * (i - nl)], ml);
-            load_msg(p.children[2 * (i - nl) + 1], mr);
+            load_msg(children_s[2 * (i - nl)], ml);
+            load_msg(children_s[2 * (i - nl) + 1], mr);
 #pragma unroll
             for (int T = 0; T < 2; T++)
 #pragma unroll
                 for (int j = 0; j < 8; j++) cur[T][j] = make_double2(ml[T][j].x * mr[T][j].x, ml[T][j].y * mr[T][j].y);
-            store_blk(blk(0, i), cur);
+            if (p.n_post) store_blk(blk(0, i), cur);  // only the node posteriors read alpha back
             if (i == n - 1) break;
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -1859,64 +1872,94 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             zinv[T] = live[T] ? 1.0 / zp : 0.0;  // one division per column: 32 per thread and branch cost a third of the kernel
             if (p.z_out && t == 0 && c < ncols) p.z_out[col0 + c] = zp;
         }
-        // ---------------- outside + expected counts, node by node from the top ----------------
-        for (int i = n - 2; i >= 0; i--) {
-            const int par = p.parent[i], sib = p.sibling[i];
-            turn(i >= nl ? p.pt_images + (size_t)(i - nl) * 4096 : nullptr);
+        // ---------------- outside + expected counts: the host's depth-first program (OUT_STEP_*) ----------------
+        // beta of the node whose children are being visited stays in registers: a node's leaf children come first, then an
+        // internal child whose beta is parked in scratch for later, last the internal child the walk descends into next
+        double2 bv[2][8];
+        bool pending = false;  // an image is in the buffer (or on its way) and not yet used
+        for (int k = 0; k < n - 1; k++) {
+            const int i = steps_s[3 * k], fl = steps_s[3 * k + 1];
+            const int par = parent_s[i], sib = sibling_s[i];
+            // the image buffer is free from the barrier after a contraction: the next internal step's image is asked for at
+            // once, steps ahead of its use when leaf steps come in between
+            const int ahead = pending ? -1 : steps_s[3 * k + 2];
+            turn(ahead >= 0 ? p.pt_images + (size_t)(ahead - nl) * 4096 : nullptr);
+            pending |= ahead >= 0;
+            if (fl & OUT_STEP_LOADB) {
+                if (par == n - 1) {
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) bv[T][j] = pri[j];
+                } else {
+                    const double2* bp = blk(2, par);
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) bv[T][j] = bp[(T * 8 + j) * 32];
+                }
+            }
             double2 inter[2][8];
             load_msg(sib, inter);
-            if (par == n - 1) {
 #pragma unroll
-                for (int T = 0; T < 2; T++)
+            for (int T = 0; T < 2; T++)
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        inter[T][j].x *= pri[j].x;
-                        inter[T][j].y *= pri[j].y;
-                    }
-            } else {
-                const double2* bp = blk(2, par);
-#pragma unroll
-                for (int T = 0; T < 2; T++)
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const double2 b = bp[(T * 8 + j) * 32];
-                        inter[T][j].x *= b.x;
-                        inter[T][j].y *= b.y;
-                    }
-            }
+                for (int j = 0; j < 8; j++) {
+                    inter[T][j].x *= bv[T][j].x;
+                    inter[T][j].y *= bv[T][j].y;
+                }
             if (gacc) {  // U[c][a] = inter / z on live columns (else 0), V[c][b] = alpha_i (a leaf: its indicator row)
 #pragma unroll
                 for (int T = 0; T < 2; T++) {
                     const int c = 16 * w + 8 * T + g;
                     double2* ur = reinterpret_cast<double2*>(U + c * OD_TS + 2 * t);
-                    double2* vr = reinterpret_cast<double2*>(V + c * OD_TS + 2 * t);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         ur[4 * j] = make_double2(inter[T][j].x * zinv[T], inter[T][j].y * zinv[T]);
-                    if (i < nl) {
+                }
+                if (i < nl) {
+#pragma unroll
+                    for (int T = 0; T < 2; T++) {
+                        const int c = 16 * w + 8 * T + g;
+                        double2* vr = reinterpret_cast<double2*>(V + c * OD_TS + 2 * t);
                         const int code = codes_s[c * nl + i];
 #pragma unroll
                         for (int j = 0; j < 8; j++)
                             vr[4 * j] = make_double2((code >= 64 || code == 8 * j + 2 * t) ? 1.0 : 0.0,
                                                      (code >= 64 || code == 8 * j + 2 * t + 1) ? 1.0 : 0.0);
-                    } else {
-                        const double2* ai = blk(0, i);
+                    }
+                } else {
+                    // alpha_i again from its children's messages (the same product, the same bits): the children's blocks
+                    // are the ones the next steps read as sibling messages anyway, alpha's own block need not exist
+                    const int lc = children_s[2 * (i - nl)], rc = children_s[2 * (i - nl) + 1];
+#pragma unroll 1
+                    for (int T = 0; T < 2; T++) {
+                        double2 ml[8], mr[8];
+                        load_msg_half(lc, T, ml);
+                        load_msg_half(rc, T, mr);
+                        double2* vr = reinterpret_cast<double2*>(V + (16 * w + 8 * T + g) * OD_TS + 2 * t);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) vr[4 * j] = ai[(T * 8 + j) * 32];
+                        for (int j = 0; j < 8; j++) vr[4 * j] = make_double2(ml[j].x * mr[j].x, ml[j].y * mr[j].y);
                     }
                 }
             }
-            if (i >= 1) {  // the next node's operands
-                const int sn = p.sibling[i - 1];
+            if (k + 1 < n - 1) {  // the next step's sibling message
+                const int sn = sibling_s[steps_s[3 * k + 3]];
                 if (sn >= nl) prefetch_blk(blk(1, sn));
-                if (i - 1 >= nl && gacc) prefetch_blk(blk(0, i - 1));
             }
             if (i >= nl) {  // beta_i[b] = sum_a inter[a] P_i[a][b]
                 mbar_wait(bar, phase);
                 phase ^= 1;
                 double2 y[2][8];
                 contract(inter, y);
-                store_blk(blk(2, i), y);
+                if (fl & OUT_STEP_STOREB) store_blk(blk(2, i), y);
+                pending = false;
+                if (fl & OUT_STEP_CARRY) {
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) bv[T][j] = y[T][j];
+                }
             }
             if (gacc) {
                 __syncthreads();
