@@ -9,7 +9,7 @@ under the shipped 58mammals tree (half from the coding ECM, half from the noncod
 One step = one full pass of the hot path over that batch. Inputs are larger than L2 (1.7 GB of
 leaf codes per pass), so no L2 flush is needed between iterations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--only headline|cfg5|mle|omega]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--only headline|cfg5|mle|omega|outside]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 value   = device-resident throughput (leaf codes already in HBM), CUDA events, max over ranks
@@ -26,7 +26,8 @@ extra   = the other BASELINE.json configurations, measured in the same run so th
           cfg5_strong_scaling (58mammals, fixed, 6 frames, 10 M codon columns in total split over the N ranks: strong
           scaling, end to end from host buffers, subtree tables rebuilt once inside the timed region),
           mle_cfg3 (120mammals, mle, 10,000 x 100 codons; N = 1 only), omega_cfg4 (100vertebrates, omega, 1,000 exon-length
-          alignments x 3 frames through pcsf_omega_score; N = 1 only)
+          alignments x 3 frames through pcsf_omega_score; N = 1 only), outside_k6 (58mammals, outside algorithm + expected counts
+          of all branches over 1 M resident columns; N = 1 only)
 """
 import argparse
 import json
@@ -645,6 +646,50 @@ def run_omega(args, env):
     return res
 
 
+def run_outside(args, env):
+    """K6 (pcsf_posteriors: outside algorithm + expected substitution counts of every branch; PhyloLik.ml:96-180) on simulated
+    58mammals columns resident on the device. Not on the command line's path: reported so that the row has a
+    driver-witnessed figure. A product is one 64 x 64 x columns contraction; (4 n_leaves - 6) of them per column."""
+    import torch
+
+    import phylocsf_b200 as pb
+    from phylocsf_b200 import host, simulate
+
+    N = args.outside_columns
+    ps = host.ParamSet(os.path.join(env["base"], "PhyloCSF_Parameters", PSET))
+    ctx = pb.Context(env["local_rank"])
+    ps.install(ctx)
+    ctx.pt_build(0, [1.0])
+    gen = torch.Generator(device=env["dev"])
+    gen.manual_seed(5)
+    nbr = 2 * ps.n_leaves - 2
+    P = np.stack([ctx.pt_get(0, 0, br) for br in range(nbr)])
+    codes = simulate.simulate_codes(P, ps.qdiag(0)["prior"], simulate.parents_from_children(ps.n_leaves, ps.children), ps.n_leaves, N,
+                                    gen, env["dev"]).cpu().numpy()
+    ctx.batch_upload(np.array([0, N], dtype=np.int64), codes)
+    for _ in range(2):
+        ctx.posteriors(0, 0, nodes=[], ecounts=True, z=False)
+    ms = []
+    l0 = ctx.launch_count
+    for _ in range(3):
+        _, ec, _ = ctx.posteriors(0, 0, nodes=[], ecounts=True, z=False)
+        ms.append(ctx.last_ms(0))
+    launches = ctx.launch_count - l0
+    ctx.close()
+    t = float(np.median(ms)) * 1e-3
+    flop = N * (4 * ps.n_leaves - 6) * 8192.0
+    peak, src = dmma_peak_tflops()
+    total = float(ec.sum())
+    if abs(total - N * nbr) > 1e-6 * N * nbr:  # every branch's expected counts sum to the number of (possible) columns
+        raise RuntimeError("expected counts sum to %r, not %r" % (total, N * nbr))
+    return {"workload": "58mammals, %d simulated codon columns, expected counts of all %d branches" % (N, nbr), "columns_per_s": N / t,
+            "kernel_ms": t * 1e3, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": flop / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flop / t / 1e12 / peak,
+                         "peak_source": src, "flop_per_column": (4 * ps.n_leaves - 6) * 8192},
+            "path": "pcsf_posteriors on a staged batch (transposed images + outside_dmma_kernel + outside_reduce_kernel), CUDA events "
+                    "around the kernels; PCSF_K6_PLAIN=1 selects the plain-FP64 form"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -657,7 +702,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="headline only")
     ap.add_argument("--data", default="simulated", choices=["simulated", "realistic"],
                     help="realistic: the simulated alignments with 10 %% random substitutions, missing species and gap runs (headline only)")
-    ap.add_argument("--only", default="", choices=["", "headline", "cfg5", "mle", "omega"], help="run one part only (prints that part's JSON)")
+    ap.add_argument("--only", default="", choices=["", "headline", "cfg5", "mle", "omega", "outside"], help="run one part only (prints that part's JSON)")
+    ap.add_argument("--outside-columns", type=int, default=1000000)
     ap.add_argument("--cfg5-alignments", type=int, default=1000, help="alignments of 5,001 nt in the strong-scaling job (1000 = 10 M codon columns)")
     ap.add_argument("--mle-alignments", type=int, default=10000)
     ap.add_argument("--omega-alignments", type=int, default=1000)
@@ -714,6 +760,8 @@ def main():
             guarded("mle_cfg3", run_mle)
         if world == 1 and args.only in ("", "omega"):
             guarded("omega_cfg4", run_omega)
+        if world == 1 and args.only in ("", "outside"):
+            guarded("outside_k6", run_outside)
     if rank == 0:
         if line is None:
             line = {"only": args.only, "n_gpus": world}

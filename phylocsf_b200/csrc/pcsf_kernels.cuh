@@ -1448,6 +1448,7 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
 //     (lib/CamlPaml/PhyloLik.ml:96-180: ensure_beta, node_posterior, add_branch_posteriors)
 // =================================================================================================
 // Not on the scoring path of the command line: this is the E step PhyloEM-style ECM training needs.
+// Two forms: outside_kernel (this one, plain FP64, PCSF_K6_PLAIN=1) and outside_dmma_kernel (below, what pcsf_posteriors runs).
 // CTAs walk tiles of 64 codon columns. Per tile, with msg_i = P_i x alpha_i the message of node i to its parent
 // (a leaf's message is a row of its P^T table, as in the pruning kernels):
 //   inside   (i ascending, internal nodes): alpha_i = msg_lc * msg_rc; msg_i kept for the way down
@@ -1719,7 +1720,12 @@ __global__ void __launch_bounds__(OUT_THREADS, 2) outside_kernel(const OutsidePa
 // alpha, msg, beta and the G blocks are stored in the owning thread's register order (32 consecutive double2 per warp
 // instruction); outside_reduce_kernel undoes the order of G. Two barriers per node: one before the image / U / V are
 // overwritten, one before G's fragments are read.
-constexpr int OD_THREADS = 128;
+#ifndef PCSF_OD_T
+#define PCSF_OD_T 2
+#endif
+constexpr int OD_T = PCSF_OD_T;          // 8-column m-tiles per warp: 2 = four warps per CTA, 1 = eight
+constexpr int OD_WC = 8 * OD_T;          // columns per warp (= rows of G per warp)
+constexpr int OD_THREADS = 32 * 8 / OD_T;
 constexpr int OD_TC = 64;
 constexpr int OD_TS = 68;
 constexpr int OD_SMEM_FIXED = FRAG_BYTES + 2 * OD_TC * OD_TS * 8 + 16;  // image, U, V, one mbarrier
@@ -1753,9 +1759,9 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
     uint8_t* codes_s = reinterpret_cast<uint8_t*>(children_s + od_tree_ints(nl));
     for (int i = tid; i < 2 * ni + 2 * n + 3 * (n - 1); i += OD_THREADS) children_s[i] = (int16_t)p.children[i];
     // scratch blocks of this CTA in register order: kind 0 alpha, 1 msg, 2 beta; element (T, j) at + (T * 8 + j) * 32
-    double2* sc = reinterpret_cast<double2*>(p.scratch + (size_t)blockIdx.x * 3 * ni * OD_TC * 64) + w * 512 + lane;
+    double2* sc = reinterpret_cast<double2*>(p.scratch + (size_t)blockIdx.x * 3 * ni * OD_TC * 64) + w * (OD_T * 256) + lane;
     auto blk = [&](int kind, int node) { return sc + (size_t)(kind * ni + node - nl) * 2048; };
-    double2* gacc = p.gacc ? reinterpret_cast<double2*>(p.gacc + (size_t)blockIdx.x * (n - 1) * 4096) + w * 512 + lane : nullptr;
+    double2* gacc = p.gacc ? reinterpret_cast<double2*>(p.gacc + (size_t)blockIdx.x * (n - 1) * 4096) + w * (OD_T * 256) + lane : nullptr;
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1766,9 +1772,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
         for (size_t i = tid; i < (size_t)(n - 1) * 2048; i += OD_THREADS) z2[i] = make_double2(0.0, 0.0);
     }
     uint32_t phase = 0;
-    double2 pri[8];  // prior at this lane's states
-#pragma unroll
-    for (int j = 0; j < 8; j++) pri[j] = *reinterpret_cast<const double2*>(p.prior + 8 * j + 2 * t);
+    const double2* pri = reinterpret_cast<const double2*>(p.prior + 2 * t);  // prior at this lane's states: pri[4 j]
 
     // every thread is past its reads of the image, U and V; thread 0 starts the next image's copy
     auto turn = [&](const double* image) {
@@ -1781,7 +1785,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
     };
     auto load_msg_half = [&](int node, int T, double2 (&m)[8]) {  // the message of `node` for columns 8T + g of this warp
         if (node < nl) {
-            int code = codes_s[(16 * w + 8 * T + g) * nl + node];
+            int code = codes_s[(OD_WC * w + 8 * T + g) * nl + node];
             code = code > 64 ? 64 : code;
             const double2* row = reinterpret_cast<const double2*>(p.tables + (size_t)node * PT_SLOT + code * 64 + 2 * t);
 #pragma unroll
@@ -1792,13 +1796,13 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             for (int j = 0; j < 8; j++) m[j] = b[(T * 8 + j) * 32];
         }
     };
-    auto load_msg = [&](int node, double2 (&m)[2][8]) {
-        load_msg_half(node, 0, m[0]);
-        load_msg_half(node, 1, m[1]);
-    };
-    auto store_blk = [&](double2* b, const double2 (&v)[2][8]) {
+    auto load_msg = [&](int node, double2 (&m)[OD_T][8]) {
 #pragma unroll
-        for (int T = 0; T < 2; T++)
+        for (int T = 0; T < OD_T; T++) load_msg_half(node, T, m[T]);
+    };
+    auto store_blk = [&](double2* b, const double2 (&v)[OD_T][8]) {
+#pragma unroll
+        for (int T = 0; T < OD_T; T++)
 #pragma unroll
             for (int j = 0; j < 8; j++) b[(T * 8 + j) * 32] = v[T][j];
     };
@@ -1811,10 +1815,10 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
         }
     };
     // y[c][o] = sum_k x[c][k] * M[o][k], M's fragment-ordered image in shared memory
-    auto contract = [&](const double2 (&x)[2][8], double2 (&y)[2][8]) {
+    auto contract = [&](const double2 (&x)[OD_T][8], double2 (&y)[OD_T][8]) {
         const double* Pb = Pimg + lane;
 #pragma unroll
-        for (int T = 0; T < 2; T++)
+        for (int T = 0; T < OD_T; T++)
 #pragma unroll
             for (int j = 0; j < 8; j++) y[T][j] = make_double2(0.0, 0.0);
 #pragma unroll
@@ -1823,7 +1827,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             for (int j = 0; j < 8; j++) {
                 const double bf = Pb[(j * 16 + s) * 32];
 #pragma unroll
-                for (int T = 0; T < 2; T++) dmma(y[T][j].x, y[T][j].y, (s & 1) ? x[T][s >> 1].y : x[T][s >> 1].x, bf);
+                for (int T = 0; T < OD_T; T++) dmma(y[T][j].x, y[T][j].y, (s & 1) ? x[T][s >> 1].y : x[T][s >> 1].x, bf);
             }
         }
     };
@@ -1835,39 +1839,40 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
         __syncthreads();
         for (int i = tid; i < OD_TC * nl; i += OD_THREADS) codes_s[i] = i < ncols * nl ? p.codes[(size_t)col0 * nl + i] : (uint8_t)64;
         // ---------------- inside ----------------
-        double2 cur[2][8];
+        double2 cur[OD_T][8];
         for (int i = nl; i < n; i++) {
             turn(i < n - 1 ? p.tables + (size_t)i * PT_SLOT : nullptr);  // (the first turn also publishes the tile's codes)
-            double2 ml[2][8], mr[2][8];
+            double2 ml[OD_T][8], mr[OD_T][8];
             load_msg(children_s[2 * (i - nl)], ml);
             load_msg(children_s[2 * (i - nl) + 1], mr);
 #pragma unroll
-            for (int T = 0; T < 2; T++)
+            for (int T = 0; T < OD_T; T++)
 #pragma unroll
                 for (int j = 0; j < 8; j++) cur[T][j] = make_double2(ml[T][j].x * mr[T][j].x, ml[T][j].y * mr[T][j].y);
             if (p.n_post) store_blk(blk(0, i), cur);  // only the node posteriors read alpha back
             if (i == n - 1) break;
             mbar_wait(bar, phase);
             phase ^= 1;
-            double2 y[2][8];
+            double2 y[OD_T][8];
             contract(cur, y);
             store_blk(blk(1, i), y);
         }
         // ---------------- root: z = alpha_root . prior ----------------
-        double z[2], zinv[2];
-        bool live[2];
+        double z[OD_T], zinv[OD_T];
+        bool live[OD_T];
 #pragma unroll
-        for (int T = 0; T < 2; T++) {
+        for (int T = 0; T < OD_T; T++) {
             double zp = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                zp += cur[T][j].x * pri[j].x;
-                zp += cur[T][j].y * pri[j].y;
+                const double2 pj = __ldg(pri + 4 * j);
+                zp += cur[T][j].x * pj.x;
+                zp += cur[T][j].y * pj.y;
             }
             zp += __shfl_xor_sync(0xffffffffu, zp, 1);
             zp += __shfl_xor_sync(0xffffffffu, zp, 2);
             z[T] = zp;
-            const int c = 16 * w + 8 * T + g;
+            const int c = OD_WC * w + 8 * T + g;
             live[T] = c < ncols && zp > 0.0;
             zinv[T] = live[T] ? 1.0 / zp : 0.0;  // one division per column: 32 per thread and branch cost a third of the kernel
             if (p.z_out && t == 0 && c < ncols) p.z_out[col0 + c] = zp;
@@ -1875,7 +1880,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
         // ---------------- outside + expected counts: the host's depth-first program (OUT_STEP_*) ----------------
         // beta of the node whose children are being visited stays in registers: a node's leaf children come first, then an
         // internal child whose beta is parked in scratch for later, last the internal child the walk descends into next
-        double2 bv[2][8];
+        double2 bv[OD_T][8];
         bool pending = false;  // an image is in the buffer (or on its way) and not yet used
         for (int k = 0; k < n - 1; k++) {
             const int i = steps_s[3 * k], fl = steps_s[3 * k + 1];
@@ -1888,21 +1893,21 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             if (fl & OUT_STEP_LOADB) {
                 if (par == n - 1) {
 #pragma unroll
-                    for (int T = 0; T < 2; T++)
+                    for (int T = 0; T < OD_T; T++)
 #pragma unroll
-                        for (int j = 0; j < 8; j++) bv[T][j] = pri[j];
+                        for (int j = 0; j < 8; j++) bv[T][j] = __ldg(pri + 4 * j);
                 } else {
                     const double2* bp = blk(2, par);
 #pragma unroll
-                    for (int T = 0; T < 2; T++)
+                    for (int T = 0; T < OD_T; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) bv[T][j] = bp[(T * 8 + j) * 32];
                 }
             }
-            double2 inter[2][8];
+            double2 inter[OD_T][8];
             load_msg(sib, inter);
 #pragma unroll
-            for (int T = 0; T < 2; T++)
+            for (int T = 0; T < OD_T; T++)
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     inter[T][j].x *= bv[T][j].x;
@@ -1910,8 +1915,8 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                 }
             if (gacc) {  // U[c][a] = inter / z on live columns (else 0), V[c][b] = alpha_i (a leaf: its indicator row)
 #pragma unroll
-                for (int T = 0; T < 2; T++) {
-                    const int c = 16 * w + 8 * T + g;
+                for (int T = 0; T < OD_T; T++) {
+                    const int c = OD_WC * w + 8 * T + g;
                     double2* ur = reinterpret_cast<double2*>(U + c * OD_TS + 2 * t);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
@@ -1919,8 +1924,8 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                 }
                 if (i < nl) {
 #pragma unroll
-                    for (int T = 0; T < 2; T++) {
-                        const int c = 16 * w + 8 * T + g;
+                    for (int T = 0; T < OD_T; T++) {
+                        const int c = OD_WC * w + 8 * T + g;
                         double2* vr = reinterpret_cast<double2*>(V + c * OD_TS + 2 * t);
                         const int code = codes_s[c * nl + i];
 #pragma unroll
@@ -1933,11 +1938,11 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
                     // are the ones the next steps read as sibling messages anyway, alpha's own block need not exist
                     const int lc = children_s[2 * (i - nl)], rc = children_s[2 * (i - nl) + 1];
 #pragma unroll 1
-                    for (int T = 0; T < 2; T++) {
+                    for (int T = 0; T < OD_T; T++) {
                         double2 ml[8], mr[8];
                         load_msg_half(lc, T, ml);
                         load_msg_half(rc, T, mr);
-                        double2* vr = reinterpret_cast<double2*>(V + (16 * w + 8 * T + g) * OD_TS + 2 * t);
+                        double2* vr = reinterpret_cast<double2*>(V + (OD_WC * w + 8 * T + g) * OD_TS + 2 * t);
 #pragma unroll
                         for (int j = 0; j < 8; j++) vr[4 * j] = make_double2(ml[j].x * mr[j].x, ml[j].y * mr[j].y);
                     }
@@ -1950,41 +1955,43 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
             if (i >= nl) {  // beta_i[b] = sum_a inter[a] P_i[a][b]
                 mbar_wait(bar, phase);
                 phase ^= 1;
-                double2 y[2][8];
+                double2 y[OD_T][8];
                 contract(inter, y);
                 if (fl & OUT_STEP_STOREB) store_blk(blk(2, i), y);
                 pending = false;
                 if (fl & OUT_STEP_CARRY) {
 #pragma unroll
-                    for (int T = 0; T < 2; T++)
+                    for (int T = 0; T < OD_T; T++)
 #pragma unroll
                         for (int j = 0; j < 8; j++) bv[T][j] = y[T][j];
                 }
             }
             if (gacc) {
                 __syncthreads();
-                double2 ga[2][8];
+                double2 ga[OD_T][8];
 #pragma unroll
-                for (int M = 0; M < 2; M++)
+                for (int M = 0; M < OD_T; M++)
 #pragma unroll
                     for (int j = 0; j < 8; j++) ga[M][j] = make_double2(0.0, 0.0);
-                const double* ua = U + t * OD_TS + 16 * w + g;
+                const double* ua = U + t * OD_TS + OD_WC * w + g;
                 const double* vb = V + t * OD_TS + g;
 #pragma unroll
                 for (int s = 0; s < 16; s++) {
-                    const double a0 = ua[4 * s * OD_TS], a1 = ua[4 * s * OD_TS + 8];
+                    double af[OD_T];
+#pragma unroll
+                    for (int M = 0; M < OD_T; M++) af[M] = ua[4 * s * OD_TS + 8 * M];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const double bf = vb[4 * s * OD_TS + 8 * j];
-                        dmma(ga[0][j].x, ga[0][j].y, a0, bf);
-                        dmma(ga[1][j].x, ga[1][j].y, a1, bf);
+#pragma unroll
+                        for (int M = 0; M < OD_T; M++) dmma(ga[M][j].x, ga[M][j].y, af[M], bf);
                     }
                 }
                 // this CTA's block, this thread's elements, tile after tile: reductions without a return value keep the
                 // order (and the bits) of a load-add-store and do not wait for the line
                 double* G = reinterpret_cast<double*>(gacc + (size_t)i * 2048);
 #pragma unroll
-                for (int M = 0; M < 2; M++)
+                for (int M = 0; M < OD_T; M++)
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         atomicAdd(G + (M * 8 + j) * 64, ga[M][j].x);
@@ -1996,8 +2003,8 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
         for (int q = 0; q < p.n_post; q++) {
             const int node = p.post_nodes[q];
 #pragma unroll
-            for (int T = 0; T < 2; T++) {
-                const int c = 16 * w + 8 * T + g;
+            for (int T = 0; T < OD_T; T++) {
+                const int c = OD_WC * w + 8 * T + g;
                 if (c >= ncols) continue;
                 double2* out = reinterpret_cast<double2*>(p.post_out + ((size_t)q * p.total_cols + col0 + c) * 64 + 2 * t);
                 const double zc = z[T];
@@ -2014,7 +2021,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const double2 a = ai[(T * 8 + j) * 32];
-                        const double2 b = node == n - 1 ? pri[j] : bi[(T * 8 + j) * 32];
+                        const double2 b = node == n - 1 ? __ldg(pri + 4 * j) : bi[(T * 8 + j) * 32];
                         out[4 * j] = zc == 0.0 ? make_double2(0.0, 0.0) : make_double2(a.x * b.x / zc, a.y * b.y / zc);
                     }
                 }
@@ -2024,13 +2031,13 @@ __global__ void __launch_bounds__(OD_THREADS, 2) outside_dmma_kernel(const Outsi
 }
 
 // ecounts[br][a][b] = P_br[a][b] * sum over CTAs (ascending) of G[cta][br][a][b]; reg_order: the G blocks are in the
-// register order of outside_dmma_kernel (warp a / 16, m-tile (a / 8) % 2, n-tile b / 8, lane 4 (a % 8) + (b / 2) % 4, b % 2)
+// register order of outside_dmma_kernel (m-tile a / 8, n-tile b / 8, lane 4 (a % 8) + (b / 2) % 4, b % 2)
 __global__ void outside_reduce_kernel(const double* __restrict__ gacc, int n_cta, int n_branches, int n_leaves,
                                       const double* __restrict__ tables, double* __restrict__ ecounts, int reg_order) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_branches * 4096) return;
     const int br = (int)(i >> 12), a = (int)((i >> 6) & 63), b = (int)(i & 63);
-    const int e = reg_order ? (((((a >> 4) * 2 + ((a >> 3) & 1)) * 8 + (b >> 3)) * 32 + ((a & 7) * 4 + ((b >> 1) & 3))) * 2 + (b & 1)) : a * 64 + b;
+    const int e = reg_order ? ((((a >> 3) * 8 + (b >> 3)) * 32 + ((a & 7) * 4 + ((b >> 1) & 3))) * 2 + (b & 1)) : a * 64 + b;
     double s = 0.0;
     for (int k = 0; k < n_cta; k++) s += gacc[((size_t)k * n_branches + br) * 4096 + e];
     ecounts[i] = out_p_entry(tables + (size_t)br * PT_SLOT, br < n_leaves, a, b) * s;
