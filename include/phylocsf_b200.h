@@ -157,6 +157,10 @@ int pcsf_batch_upload_alignments(pcsf_ctx *ctx, int64_t nalign, const int64_t *a
 int pcsf_batch_upload_alignments_parts(pcsf_ctx *ctx, int64_t nalign, const int64_t *aln_off, const int32_t *aln_len,
                                        int64_t nparts, const uint8_t *const *part_ptr, const int64_t *part_bytes,
                                        int frames);
+/* The staged batch's leaf codes, codes_out[col * n_leaves + leaf] for pcsf_batch_ncols() columns: what pleaves
+ * (src/PhyloCSF.ml:219-246) returned for each region, back on the host - after pcsf_batch_upload_alignments this is
+ * the output of the device pleaves (K0), which the parity tests compare byte for byte with the reference's. */
+int pcsf_batch_codes_get(pcsf_ctx *ctx, uint8_t *codes_out);
 int64_t pcsf_batch_nregions(const pcsf_ctx *ctx);
 int64_t pcsf_batch_ncols(const pcsf_ctx *ctx);
 

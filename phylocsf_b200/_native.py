@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PCSF_LIB") or os.path.join(_HERE, "libphylocsf_b200.s
 SYMBOLS = [
     "pcsf_version", "pcsf_device_count", "pcsf_create", "pcsf_destroy", "pcsf_last_error", "pcsf_stream_set", "pcsf_option_set",
     "pcsf_tree_set", "pcsf_model_set", "pcsf_pt_build", "pcsf_pt_get", "pcsf_batch_upload",
-    "pcsf_batch_upload_alignments", "pcsf_batch_upload_alignments_parts", "pcsf_batch_nregions", "pcsf_batch_ncols", "pcsf_lpr_all", "pcsf_score_alignments", "pcsf_lpr",
+    "pcsf_batch_upload_alignments", "pcsf_batch_upload_alignments_parts", "pcsf_batch_nregions", "pcsf_batch_ncols", "pcsf_batch_codes_get", "pcsf_lpr_all", "pcsf_score_alignments", "pcsf_lpr",
     "pcsf_models_set", "pcsf_omega_models_set", "pcsf_model_get", "pcsf_pt_build_pairs", "pcsf_lpr_pairs", "pcsf_column_terms", "pcsf_maximize_lpr", "pcsf_maximize_lpr_multi", "pcsf_last_ms", "pcsf_launch_count", "pcsf_table_level", "pcsf_last_launch_info", "pcsf_tree_n_leaves", "pcsf_total_ms", "pcsf_posteriors", "pcsf_counter", "pcsf_omega_cache_reset", "pcsf_omega_models_set_cached",
 ]
 
@@ -53,6 +53,7 @@ def load():
     L.pcsf_batch_upload.argtypes = [vp, i64, vp, vp]
     L.pcsf_batch_upload_alignments.argtypes = [vp, i64, vp, vp, vp, ctypes.c_int]
     L.pcsf_batch_upload_alignments_parts.argtypes = [vp, i64, vp, vp, i64, vp, vp, ctypes.c_int]
+    L.pcsf_batch_codes_get.argtypes = [vp, vp]
     L.pcsf_batch_nregions.argtypes = [vp]
     L.pcsf_batch_nregions.restype = i64
     L.pcsf_batch_ncols.argtypes = [vp]

@@ -112,6 +112,13 @@ class Context:
     def ncols(self):
         return int(self._L.pcsf_batch_ncols(self._h))
 
+    def batch_codes(self):
+        """pcsf_batch_codes_get: the staged leaf codes [total_cols, n_leaves] (after batch_upload_alignments: the
+        device pleaves' output)."""
+        out = np.empty((self.ncols, self.n_leaves), dtype=np.uint8)
+        self._check(self._L.pcsf_batch_codes_get(self._h, N.ptr(out)))
+        return out
+
     def lpr_all(self, model_ids, scale_idx=None, out=None):
         mids = np.ascontiguousarray(model_ids, dtype=np.int32)
         sidx = None if scale_idx is None else np.ascontiguousarray(scale_idx, dtype=np.int32)

@@ -1047,6 +1047,28 @@ int pcsf_batch_upload(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off
     return PCSF_OK;
 }
 
+// K0 (pcsf_k0.cuh): pleaves for `nalign` staged alignments. Grid = (alignments, tiles of the longest one), dynamic shared
+// memory = one tile of codon codes (all rows x tile positions). d_nt and d_codes are device allocations (aligned); the kernel
+// reads d_nt in whole words up to ceil(nt_bytes / 4), which reserve()'s head room covers.
+static int launch_frame_codes(pcsf_ctx* ctx, const void* d_nt, int64_t nt_bytes, const void* d_aln_off, const void* d_aln_len,
+                              const void* d_roff, int64_t nalign, int max_len, int frames, void* d_codes) {
+    if (nalign <= 0 || max_len < 3) return PCSF_OK;  // no codon anywhere
+    const int tile = k0::choose_tile_pos(max_len, ctx->n_leaves);
+    const size_t smem = k0::smem_bytes(tile, ctx->n_leaves);
+    if (smem > (size_t)227 * 1024) return fail(ctx, PCSF_ERR_INVALID_ARG, "pleaves on the device: too many leaves for one shared-memory tile");
+    if (smem > (size_t)48 * 1024)
+        CU(cudaFuncSetAttribute(frame_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (nalign > INT32_MAX) return fail(ctx, PCSF_ERR_INVALID_ARG, "pleaves on the device: too many alignments in one batch");
+    const int64_t tiles = ((int64_t)max_len + tile - 1) / tile;
+    const dim3 grid((unsigned)nalign, (unsigned)std::min<int64_t>(tiles, 65535));
+    frame_codes_kernel<<<grid, k0::THREADS, smem, ctx->stream>>>((const uint8_t*)d_nt, nt_bytes, (const int64_t*)d_aln_off,
+                                                                  (const int32_t*)d_aln_len, (const int64_t*)d_roff, frames,
+                                                                  ctx->n_leaves, tile, (uint8_t*)d_codes);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return PCSF_OK;
+}
+
 int pcsf_batch_upload_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off, const int32_t* aln_len,
                                  const uint8_t* nt, int frames) {
     int64_t nt_bytes = 0;
@@ -1072,10 +1094,12 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     const int64_t nregions = nalign * frames;
     std::vector<int64_t> roff(nregions + 1, 0);
     int64_t nt_bytes = 0;
+    int max_len = 0;
     for (int64_t a = 0; a < nalign; a++) {
         if (aln_len[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment length");
         if (aln_off[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment offset");
         nt_bytes = std::max<int64_t>(nt_bytes, aln_off[a] + (int64_t)aln_len[a] * ctx->n_leaves);
+        max_len = std::max(max_len, aln_len[a]);
         for (int f = 0; f < frames; f++) {
             const int rem = aln_len[a] - (f % 3);
             roff[a * frames + f + 1] = roff[a * frames + f] + (rem >= 3 ? rem / 3 : 0);  // pos+2 <= hi, PhyloCSF.ml:226
@@ -1114,13 +1138,8 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     }
     CU(cudaMemcpyAsync(ctx->d_region_off.p, roff.data(), sizeof(int64_t) * (nregions + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev[7], ctx->stream));
-    if (nregions > 0) {
-        frame_codes_kernel<<<(unsigned)nregions, 128, 0, ctx->stream>>>(
-            (const uint8_t*)ctx->d_nt.p, (const int64_t*)ctx->d_aln_off.p, (const int32_t*)ctx->d_aln_len.p,
-            (const int64_t*)ctx->d_region_off.p, nregions, frames, ctx->n_leaves, (uint8_t*)ctx->d_codes.p);
-        CU(cudaGetLastError());
-        ctx->launches++;
-    }
+    TRY(launch_frame_codes(ctx, ctx->d_nt.p, nt_bytes, ctx->d_aln_off.p, ctx->d_aln_len.p, ctx->d_region_off.p, nalign, max_len,
+                           frames, ctx->d_codes.p));
     ctx->region_off = roff;
     ctx->nregions = nregions;
     ctx->total_cols = total;
@@ -1128,6 +1147,16 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     float t;
     CU(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
     ctx->ms[3] = t;
+    return PCSF_OK;
+}
+
+int pcsf_batch_codes_get(pcsf_ctx* ctx, uint8_t* codes_out) {
+    TRY(check_ready(ctx, false));
+    if (ctx->total_cols > 0 && !codes_out) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_batch_codes_get: null buffer");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->total_cols > 0)
+        CU(cudaMemcpy(codes_out, ctx->d_codes.p, (size_t)ctx->total_cols * ctx->n_leaves, cudaMemcpyDeviceToHost));
     return PCSF_OK;
 }
 
@@ -1242,9 +1271,11 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
         const int64_t a0 = chunk_begin[k], a1 = chunk_begin[k + 1], na = a1 - a0;
         if (na == 0) continue;
         int64_t lo = INT64_MAX, hi = 0;
+        int max_len = 0;
         for (int64_t a = a0; a < a1; a++) {
             lo = std::min(lo, aln_off[a]);
             hi = std::max(hi, aln_off[a] + (int64_t)aln_len[a] * ctx->n_leaves);
+            max_len = std::max(max_len, aln_len[a]);
         }
         if (hi > lo && !nt) return fail(ctx, PCSF_ERR_INVALID_ARG, "null nucleotide buffer");
         // the host-side staging vectors of buffer b may still feed an in-flight pageable copy of chunk k-2
@@ -1273,11 +1304,8 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
         CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
         // ---- compute stream: pleaves, pruning, reduction, results back ----
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-        frame_codes_kernel<<<(unsigned)nreg, 128, 0, ctx->stream>>>(
-            (const uint8_t*)ctx->pipe_nt[b].p, (const int64_t*)ctx->pipe_aln_off[b].p, (const int32_t*)ctx->pipe_aln_len[b].p,
-            (const int64_t*)ctx->pipe_roff[b].p, nreg, frames, ctx->n_leaves, (uint8_t*)ctx->pipe_codes[b].p);
-        CU(cudaGetLastError());
-        ctx->launches++;
+        TRY(launch_frame_codes(ctx, ctx->pipe_nt[b].p, hi - lo, ctx->pipe_aln_off[b].p, ctx->pipe_aln_len[b].p, ctx->pipe_roff[b].p,
+                               na, max_len, frames, ctx->pipe_codes[b].p));
         std::vector<Span> spans;
         for (int m = 0; m < n_models; m++) spans.push_back(Span{0, (int64_t)m * total, 0, (int32_t)total, m});
         const int64_t n_segs = nreg * n_models;

@@ -1,0 +1,237 @@
+// K0: pleaves on the device - packed leaf codes per codon column and reading frame from nucleotide rows
+// (src/PhyloCSF.ml:219-246 `pleaves` over the AsIs `candidate_regions` of :198-205; Code.ml:39-51 for the
+// reverse complement). Byte work, bound by HBM on paper: per codon column and strand 3 n nucleotides in (the three
+// frames of a strand share them) and n codes out per frame.
+//
+// Round 1's kernel was one thread per (column, leaf) with three byte loads each: 483 us per 2 M-column chunk = 410 GB/s,
+// 6 % of the HBM peak, bound by its load instructions (profiles/r02_frame_codes_ncu_summary.json). This one moves whole
+// words on both sides of a shared-memory tile:
+//   stage 1  a thread takes 16 consecutive positions of one row: six aligned 32-bit loads (rows start at any byte
+//            offset), funnel shifts to the row's phase, four characters decoded per instruction (SIMD within a word),
+//            and for every position p the code of the forward codon starting there, cc[l][p] = 0..63 or 64, stored as
+//            four words into the tile (one byte per position and row);
+//   stage 2  the codes of a (tile, frame) are one contiguous run of the output (column-major over leaves): a thread
+//            owns an aligned 16-byte group of it, picks its 16 bytes out of the tile (frame f, column c, leaf l reads
+//            cc[l][f + 3c]; the reverse strand reads cc[l][len-3-f-3c] and reverse-complements the code with bit
+//            operations: complement = 3 - index) and writes one 16-byte store; the unaligned head and tail of a run
+//            go out as bytes.
+// Everything that indexes is in the PCSF_HD functions below so that the same code runs, thread by thread, in a CPU
+// emulation (tests/k0_emul.cpp, tests/test_k0_emulation.py) against the oracle's pleaves on ragged inputs.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define PCSF_HD __host__ __device__ __forceinline__
+#else
+#define PCSF_HD inline
+#endif
+
+namespace pcsf {
+namespace k0 {
+
+constexpr int THREADS = 256;
+constexpr int MAX_FRAMES = 6;
+
+// low word of (hi:lo) >> sh, sh = 0, 8, 16 or 24
+PCSF_HD uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+
+// four characters -> four bytes: nucleotide index A 0, C 1, G 2, T 3 (either case), bit 2 set for anything else.
+// 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54: bits 1-2 of the upper-cased character give the index (G and T swapped: the
+// xor); a character is one of the four iff its other bits are those of 'A' - or those of 'T' when bits 2:1 are 10.
+PCSF_HD uint32_t decode4(uint32_t w) {
+    const uint32_t u = w & 0xDFDFDFDFu;
+    const uint32_t x = (u >> 1) & 0x03030303u;
+    const uint32_t idx = x ^ ((x >> 1) & 0x01010101u);
+    const uint32_t t = (u >> 2) & ~(u >> 1) & 0x01010101u;
+    const uint32_t bad = ((w & 0xD9D9D9D9u) ^ 0x41414141u) ^ (t * 0x11u);
+    const uint32_t nz = (((bad & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | bad) & 0x80808080u;
+    return idx | (nz >> 5);
+}
+
+// four codons at once: a, b, c = the indices at positions p, p+1, p+2 (bytes). 16 a + 4 b + c, or 64 if any is not ACGT.
+PCSF_HD uint32_t codon4(uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t inv = ((a | b | c) & 0x04040404u) << 4;
+    const uint32_t code = ((a & 0x03030303u) << 4) | ((b & 0x03030303u) << 2) | (c & 0x03030303u);
+    return (code & ~(inv - (inv >> 6))) | inv;
+}
+
+// codes of the reverse complements of four forward codons: (i1, i2, i3) -> (3 - i3, 3 - i2, 3 - i1); 64 stays 64
+PCSF_HD uint32_t revcomp4(uint32_t w) {
+    const uint32_t y = w ^ 0x3F3F3F3Fu;
+    const uint32_t r = ((y & 0x03030303u) << 4) | (y & 0x0C0C0C0Cu) | ((y >> 4) & 0x03030303u);
+    const uint32_t m = w & 0x40404040u;
+    return (r & ~(m - (m >> 6))) | m;
+}
+
+PCSF_HD int floordiv3(int x) { return x >= 0 ? x / 3 : -((2 - x) / 3); }
+
+// Positions of a tile: [p0, p0 + tile_pos); tile_pos is a multiple of 16; a row of the tile is `pitch` bytes.
+PCSF_HD int pitch_of(int tile_pos) { return tile_pos + 4; }
+
+// stage 1, one item: positions p0 + 16 k .. + 15 of the row that starts at byte `row_byte` of the buffer
+// (row_byte = aln_off + l * len + p0 + 16 k). Reads whole words only, never past word `nwords` - 1.
+PCSF_HD void stage1_item(const uint32_t* ntw, int64_t nwords, int64_t row_byte, uint32_t* dst) {
+    const int64_t w0 = row_byte >> 2;
+    const uint32_t sh = (uint32_t)(row_byte & 3) * 8u;
+    uint32_t w[6];
+#pragma unroll
+    for (int m = 0; m < 6; m++) w[m] = (w0 + m < nwords) ? ntw[w0 + m] : 0u;
+    uint32_t I[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) I[m] = decode4(fsr(w[m], w[m + 1], sh));
+#pragma unroll
+    for (int m = 0; m < 4; m++) dst[m] = codon4(I[m], fsr(I[m], I[m + 1], 8u), fsr(I[m], I[m + 1], 16u));
+}
+
+// The codes a (tile, frame) contributes: columns [cA, cB) of region r, `nbytes` bytes from byte g0 of the output.
+struct Seg {
+    int64_t g0;      // (region_off[r] + cA) * n_leaves
+    int32_t nbytes;  // (cB - cA) * n_leaves
+    int32_t pcol0;   // position of column cA's forward codon inside the tile
+    int32_t step;    // +3 (frames 0-2) or -3 (frames 3-5) positions per column
+    int32_t ngroups; // aligned 16-byte groups the run touches
+};
+
+// frame f of an alignment of `len` positions whose region holds ncols columns starting at output column c0
+PCSF_HD Seg make_seg(int f, int len, int64_t c0, int ncols, int p0, int tile_pos, int n_leaves) {
+    const int ofs = f % 3;
+    const bool rc = f >= 3;
+    int cA, cB, pcol0;
+    if (!rc) {  // column c reads the codon at ofs + 3 c
+        cA = floordiv3(p0 - ofs + 2);              // ceil((p0 - ofs) / 3)
+        cB = floordiv3(p0 + tile_pos - ofs + 2);   // ceil((p1 - ofs) / 3)
+    } else {    // column c reads the codon at q = len - 3 - ofs - 3 c: q in [p0, p1)  <=>  c in ((top - p1) / 3, (top - p0) / 3]
+        const int top = len - 3 - ofs;
+        cA = floordiv3(top - (p0 + tile_pos)) + 1;
+        cB = floordiv3(top - p0) + 1;
+    }
+    if (cA < 0) cA = 0;
+    if (cB > ncols) cB = ncols;
+    if (cB < cA) cB = cA;
+    pcol0 = (rc ? len - 3 - ofs - 3 * cA : ofs + 3 * cA) - p0;
+    Seg s;
+    s.g0 = (c0 + cA) * (int64_t)n_leaves;
+    s.nbytes = (cB - cA) * n_leaves;
+    s.pcol0 = pcol0;
+    s.step = rc ? -3 : 3;
+    s.ngroups = s.nbytes > 0 ? (int32_t)(((s.g0 + s.nbytes + 15) >> 4) - (s.g0 >> 4)) : 0;
+    return s;
+}
+
+// stage 2, one item: group gi of a run. cc = the tile, codes = the output (16-byte aligned base).
+PCSF_HD void stage2_group(const Seg& s, int gi, const uint8_t* cc, int pitch, int n_leaves, uint8_t* codes) {
+    const int64_t A = (s.g0 & ~(int64_t)15) + 16 * (int64_t)gi;
+    const int j0 = (int)(A - s.g0);  // >= -15
+    const int lo = j0 < 0 ? -j0 : 0;
+    const int hi = s.nbytes - j0 < 16 ? s.nbytes - j0 : 16;
+    const int js = j0 + lo;
+    int c = js / n_leaves;
+    int l = js - c * n_leaves;
+    int src = l * pitch + s.pcol0 + s.step * c;
+    const int wrap = s.step - n_leaves * pitch;
+    const bool rc = s.step < 0;
+    if (lo == 0 && hi == 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                v |= (uint32_t)cc[src] << (8 * b);
+                src += pitch;
+                if (++l == n_leaves) { l = 0; src += wrap; }
+            }
+            w[m] = rc ? revcomp4(v) : v;
+        }
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint4*>(codes + A) = make_uint4(w[0], w[1], w[2], w[3]);
+#else
+        for (int m = 0; m < 4; m++)
+            for (int b = 0; b < 4; b++) codes[A + 4 * m + b] = (uint8_t)(w[m] >> (8 * b));
+#endif
+    } else {
+        for (int i = lo; i < hi; i++) {
+            const uint32_t v = cc[src];
+            codes[A + i] = (uint8_t)(rc ? revcomp4(v) : v);
+            src += pitch;
+            if (++l == n_leaves) { l = 0; src += wrap; }
+        }
+    }
+}
+
+// What one CTA does for one (alignment, tile); `tid` strides by `nthreads`. The two loops are separated by a
+// barrier in the kernel (and by running all threads of the first before the second in the emulation).
+PCSF_HD void stage1_thread(int tid, int nthreads, const uint32_t* ntw, int64_t nwords, int64_t aln_byte, int len, int n_leaves,
+                           int p0, int tile_pos, uint32_t* ccw) {
+    const int npos = (len - p0 < tile_pos ? len - p0 : tile_pos);  // positions of this tile inside the row
+    const int nchunk = (npos + 15) >> 4;
+    const int pitch_w = pitch_of(tile_pos) >> 2;
+    const int nitems = nchunk * n_leaves;
+    for (int it = tid; it < nitems; it += nthreads) {
+        const int l = it / nchunk, k = it - l * nchunk;
+        stage1_item(ntw, nwords, aln_byte + (int64_t)l * len + p0 + 16 * k, ccw + l * pitch_w + 4 * k);
+    }
+}
+
+PCSF_HD void stage2_thread(int tid, int nthreads, const Seg* segs, int frames, const uint8_t* cc, int tile_pos, int n_leaves,
+                           uint8_t* codes) {
+    int total = 0;
+    for (int f = 0; f < frames; f++) total += segs[f].ngroups;
+    const int pitch = pitch_of(tile_pos);
+    for (int g = tid; g < total; g += nthreads) {
+        int f = 0, gi = g;
+        while (gi >= segs[f].ngroups) gi -= segs[f++].ngroups;
+        stage2_group(segs[f], gi, cc, pitch, n_leaves, codes);
+    }
+}
+
+// tile size (positions) for a batch: the whole alignment when it fits `budget` bytes of shared memory, else the
+// largest multiple of 16 that does (at least 48)
+inline int choose_tile_pos(int max_len, int n_leaves, int budget = 40 * 1024) {
+    int whole = ((max_len > 1 ? max_len : 1) + 15) & ~15;
+    int fit = (budget / (n_leaves > 0 ? n_leaves : 1) - 4) & ~15;
+    if (fit < 48) fit = 48;
+    return whole < fit ? whole : fit;
+}
+inline size_t smem_bytes(int tile_pos, int n_leaves) { return (size_t)n_leaves * pitch_of(tile_pos); }
+
+}  // namespace k0
+
+#if defined(__CUDACC__)
+// grid (alignments, tiles per alignment): CTA (a, y) does tiles y, y + gridDim.y, ... of alignment a.
+// nt: 4-byte aligned buffer of nt_bytes bytes (reads are whole words inside [0, ceil(nt_bytes / 4))); codes: 16-byte aligned.
+__global__ void __launch_bounds__(k0::THREADS) frame_codes_kernel(const uint8_t* __restrict__ nt, int64_t nt_bytes,
+                                                                  const int64_t* __restrict__ aln_off,
+                                                                  const int32_t* __restrict__ aln_len,
+                                                                  const int64_t* __restrict__ region_off, int frames,
+                                                                  int n_leaves, int tile_pos, uint8_t* __restrict__ codes) {
+    extern __shared__ uint4 k0_smem[];
+    __shared__ k0::Seg segs[k0::MAX_FRAMES];
+    const int64_t a = blockIdx.x;
+    const int len = aln_len[a];
+    const int64_t aln_byte = aln_off[a];
+    const int64_t nwords = (nt_bytes + 3) >> 2;
+    for (int64_t q0 = (int64_t)blockIdx.y * tile_pos; q0 + 3 <= len; q0 += (int64_t)gridDim.y * tile_pos) {
+        const int p0 = (int)q0;
+        k0::stage1_thread((int)threadIdx.x, k0::THREADS, reinterpret_cast<const uint32_t*>(nt), nwords, aln_byte, len, n_leaves,
+                          p0, tile_pos, reinterpret_cast<uint32_t*>(k0_smem));
+        if ((int)threadIdx.x < frames) {
+            const int64_t r = a * frames + threadIdx.x;
+            const int64_t c0 = region_off[r];
+            segs[threadIdx.x] = k0::make_seg((int)threadIdx.x, len, c0, (int)(region_off[r + 1] - c0), p0, tile_pos, n_leaves);
+        }
+        __syncthreads();
+        k0::stage2_thread((int)threadIdx.x, k0::THREADS, segs, frames, reinterpret_cast<const uint8_t*>(k0_smem), tile_pos,
+                          n_leaves, codes);
+        __syncthreads();
+    }
+}
+#endif
+
+}  // namespace pcsf

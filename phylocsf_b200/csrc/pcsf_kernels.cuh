@@ -2043,57 +2043,6 @@ __global__ void outside_reduce_kernel(const double* __restrict__ gacc, int n_cta
     ecounts[i] = out_p_entry(tables + (size_t)br * PT_SLOT, br < n_leaves, a, b) * s;
 }
 
-// =================================================================================================
-// K0: pleaves on the device. One thread per (region column, leaf).
-// =================================================================================================
-__device__ __forceinline__ int nt_index(uint8_t c) {
-    switch (c) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        default: return -1;
-    }
-}
-__device__ __forceinline__ uint8_t nt_comp(uint8_t c) {  // Code.ml:39-51 (validated on the host)
-    switch (c) {
-        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
-        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
-        default: return c;
-    }
-}
-// region r = alignment a, frame f: columns at lo = f%3, strand = f/3 (src/PhyloCSF.ml:198-205,219-246)
-// One CTA per region, one thread per (column, leaf). ncu (profiles/r02_frame_codes_ncu_summary.json): 482 us for 40,000
-// alignments x 3 frames, 117 MB read + 80 MB written = 410 GB/s, 6 % of the HBM peak - the kernel is bound by its
-// byte-granular load instructions (three LDG.U8 per code), not by sectors: a version that read along the rows and
-// transposed 32-column tiles through shared memory moved the same bytes in 613 us (two barriers per tile, the same byte
-// loads). K0 is 0.3 % of a fixed-strategy step; a faster one would decode 16-byte row chunks per thread.
-__global__ void frame_codes_kernel(const uint8_t* __restrict__ nt, const int64_t* __restrict__ aln_off,
-                                   const int32_t* __restrict__ aln_len, const int64_t* __restrict__ region_off,
-                                   int64_t nregions, int frames, int n_leaves, uint8_t* __restrict__ codes) {
-    const int64_t r = blockIdx.x;
-    if (r >= nregions) return;
-    const int64_t a = r / frames;
-    const int f = (int)(r - a * frames);
-    const int ofs = f % 3;
-    const bool rc = f >= 3;
-    const int len = aln_len[a];
-    const uint8_t* base = nt + aln_off[a];
-    const int64_t c0 = region_off[r];
-    const int ncols = (int)(region_off[r + 1] - c0);
-    for (int idx = threadIdx.x; idx < ncols * n_leaves; idx += blockDim.x) {
-        const int c = idx / n_leaves, l = idx - c * n_leaves;
-        const int pos = ofs + 3 * c;
-        const uint8_t* row = base + (size_t)l * len;
-        uint8_t n1, n2, n3;
-        if (!rc) {
-            n1 = row[pos]; n2 = row[pos + 1]; n3 = row[pos + 2];
-        } else {
-            n1 = nt_comp(row[len - 1 - pos]); n2 = nt_comp(row[len - 2 - pos]); n3 = nt_comp(row[len - 3 - pos]);
-        }
-        const int i1 = nt_index(n1), i2 = nt_index(n2), i3 = nt_index(n3);
-        codes[(size_t)(c0 + c) * n_leaves + l] = (i1 < 0 || i2 < 0 || i3 < 0) ? (uint8_t)64 : (uint8_t)(16 * i1 + 4 * i2 + i3);
-    }
-}
-
 }  // namespace pcsf
+
+#include "pcsf_k0.cuh"  // K0: pleaves on the device (frame_codes_kernel)

@@ -512,3 +512,35 @@ def test_negative_offsets_are_rejected(params_base):
             call()
         assert e.value.code == -1
     ctx.close()
+
+
+@pytest.mark.parametrize("pset", ["12flies", "29mammals", "120mammals"])
+def test_k0_codes_bit_exact_against_oracle_pleaves(params_base, pset):
+    """K0 on the device (pcsf_k0.cuh) against the oracle's pleaves (src/PhyloCSF.ml:219-246, Code.ml:39-51), byte for
+    byte through pcsf_batch_codes_get: ragged lengths (0, 1, 2 ... several shared-memory tiles), alignments at any byte
+    offset of the buffer, 1 / 3 / 6 frames, 12 / 29 / 120 leaves (fewer and more than one 16-byte group per column).
+    The same inputs run through the CPU emulation of the kernel in tests/test_k0_emulation.py."""
+    import test_k0_emulation as E
+
+    ps = H.oracle_paramset(params_base, pset)
+    n = ps.tree.n_leaves
+    ctx = H.make_context(ps)
+    rng = np.random.default_rng(n)
+    alphabet = np.array(list("ACGTacgtNn-"))
+    lens = [0, 1, 2, 3, 4, 5, 15, 16, 17, 18, 47, 48, 49, 50, 97, 300, 301, 302, 333, 2500 if n > 100 else 5001]
+    alns = [["".join(alphabet[rng.integers(0, len(alphabet), size=L)]) for _ in range(n)] for L in lens]
+    nt, off = E.pack(alns, rng)
+    for frames in (1, 3, 6):
+        want, roff = E.oracle_frames(alns, frames)
+        ctx.batch_upload_alignments(off, lens, nt, frames)
+        assert ctx.nregions == frames * len(lens) and ctx.ncols == int(roff[-1])
+        got = ctx.batch_codes()
+        assert np.array_equal(got, want), (pset, frames, np.argwhere(got != want)[:5])
+    # a second, shorter batch into the same (larger) buffers, and an empty one
+    want, roff = E.oracle_frames(alns[5:9], 6)
+    nt2, off2 = E.pack(alns[5:9], rng)
+    ctx.batch_upload_alignments(off2, lens[5:9], nt2, 6)
+    assert np.array_equal(ctx.batch_codes(), want)
+    ctx.batch_upload_alignments(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint8), 3)
+    assert ctx.ncols == 0 and ctx.batch_codes().shape == (0, n)
+    ctx.close()
