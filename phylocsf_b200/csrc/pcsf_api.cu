@@ -1259,7 +1259,9 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
             if (aln_off[a] < 0) return fail(ctx, PCSF_ERR_INVALID_ARG, "negative alignment offset");
             int64_t c = 0;
             for (int f = 0; f < frames; f++) { const int rem = aln_len[a] - (f % 3); c += rem >= 3 ? rem / 3 : 0; }
-            if (cols > 0 && cols + c > chunk_cols) { chunk_begin.push_back(a); cols = 0; }
+            // the first chunk is an eighth of the others: its host->device copy is the only one nothing overlaps
+            const int64_t limit = chunk_begin.size() == 1 ? std::max<int64_t>(1, chunk_cols / 8) : chunk_cols;
+            if (cols > 0 && cols + c > limit) { chunk_begin.push_back(a); cols = 0; }
             cols += c;
         }
         chunk_begin.push_back(nalign);

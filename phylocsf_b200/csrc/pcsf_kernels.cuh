@@ -1369,10 +1369,27 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
                 double c = 1.0, s = 0.0;
                 // the second test: after a warm start most pairs are already negligible in the first sweeps
                 if (apq != 0.0 && !((sweep > 4 || warm) && fabs(apq) <= 1e-20 * fabs(app) && fabs(apq) <= 1e-20 * fabs(aqq))) {
-                    const double theta = (aqq - app) / (2.0 * apq);
-                    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    c = 1.0 / sqrt(t * t + 1.0);
-                    s = t * c;
+                    // The rotation's angle phi (|phi| <= pi/4, tan 2 phi = 2 a_pq / (a_qq - a_pp)) from two reciprocal square
+                    // roots instead of the textbook's three divisions and two square roots: the other seven warps of the CTA wait for
+                    // this dependent chain 63 times per sweep, and it was ~70 % of a round.
+                    //   cos 2phi = |d| / r, sin 2phi = +-b / r (r = hypot(d, b));  cos^2 phi = (1 + cos 2phi) / 2 =: h;
+                    //   cos phi = h / sqrt(h), sin phi = sin 2phi / (2 cos phi).   c^2 + s^2 = 1 to rounding, like the textbook's.
+                    const double d = aqq - app, b = 2.0 * apq;
+                    const double r2 = d * d + b * b;
+                    if (r2 > 1e-280 && r2 < 1e280) {
+                        const double ir = rsqrt(r2);
+                        const double c2 = fabs(d) * ir;
+                        const double s2 = (d >= 0.0 ? b : -b) * ir;
+                        const double h = 0.5 + 0.5 * c2;
+                        const double ic = rsqrt(h);
+                        c = h * ic;
+                        s = 0.5 * s2 * ic;
+                    } else {  // squares out of range: the textbook form, which only divides
+                        const double theta = d / b;
+                        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                    }
                 }
                 rc[tid] = c;
                 rs[tid] = s;
