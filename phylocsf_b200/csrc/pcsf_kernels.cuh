@@ -1361,8 +1361,12 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
         sweeps++;
         for (int r = 0; r < 63; r++) {
             if (tid < 32) {  // pairing of round r and its rotations
-                int a = tid == 0 ? 63 : (r + tid) % 63, b = tid == 0 ? r : (r - tid + 63) % 63;
-                const int p_ = a < b ? a : b, q_ = a < b ? b : a;
+                // Pair t = ((r + t) mod 63, (r - t) mod 63), pair 0 = (63, r) - kept in that order, NOT sorted: over the lanes
+                // of a warp the first members are then consecutive columns and the second members consecutive descending ones,
+                // so the lane-indexed accesses A[row][p(lane)], V[row][q(lane)] below fall into distinct banks (row stride 65).
+                // Sorted pairs scattered them (~3-way conflicts on every access), and this kernel is bound by shared-memory
+                // wavefronts: ncu had the pipe 50-65 % busy with ONE CTA per SM, which is why three CTAs per SM bought so little.
+                const int p_ = tid == 0 ? 63 : (r + tid) % 63, q_ = tid == 0 ? r : (r - tid + 63) % 63;
                 pp[tid] = p_;
                 pq[tid] = q_;
                 const double apq = A[p_ * 65 + q_], app = A[p_ * 65 + p_], aqq = A[q_ * 65 + q_];
@@ -1371,7 +1375,7 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
                 if (apq != 0.0 && !((sweep > 4 || warm) && fabs(apq) <= 1e-20 * fabs(app) && fabs(apq) <= 1e-20 * fabs(aqq))) {
                     // The rotation's angle phi (|phi| <= pi/4, tan 2 phi = 2 a_pq / (a_qq - a_pp)) from two reciprocal square
                     // roots instead of the textbook's three divisions and two square roots: the other seven warps of the CTA wait for
-                    // this dependent chain 63 times per sweep, and it was ~70 % of a round.
+                    // this dependent chain 63 times per sweep.
                     //   cos 2phi = |d| / r, sin 2phi = +-b / r (r = hypot(d, b));  cos^2 phi = (1 + cos 2phi) / 2 =: h;
                     //   cos phi = h / sqrt(h), sin phi = sin 2phi / (2 cos phi).   c^2 + s^2 = 1 to rounding, like the textbook's.
                     const double d = aqq - app, b = 2.0 * apq;
@@ -1396,12 +1400,15 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
             }
             __syncthreads();
             // A <- J^T A J in one pass: the 2 x 2 block (rows of pair ki, columns of pair kj) only needs the two pairs'
-            // rotations and belongs to one thread; columns first, then rows, as two separate passes would do it
+            // rotations and belongs to one thread; columns first, then rows, as two separate passes would do it.
+            // A thread's column pair is the same in all its blocks and in its share of V (kj = lane): loaded once per round.
+            const int lane = tid & 31;
+            const int pj_ = pp[lane], qj_ = pq[lane];
+            const double cj = rc[lane], sj = rs[lane];
 #pragma unroll 2
-            for (int b = tid; b < 1024; b += EIG_THREADS) {
-                const int ki = b >> 5, kj = b & 31;
-                const int pi_ = pp[ki], qi_ = pq[ki], pj_ = pp[kj], qj_ = pq[kj];
-                const double ci = rc[ki], si = rs[ki], cj = rc[kj], sj = rs[kj];
+            for (int ki = tid >> 5; ki < 32; ki += EIG_THREADS / 32) {
+                const int pi_ = pp[ki], qi_ = pq[ki];
+                const double ci = rc[ki], si = rs[ki];
                 const double a_pp = A[pi_ * 65 + pj_], a_pq = A[pi_ * 65 + qj_], a_qp = A[qi_ * 65 + pj_], a_qq = A[qi_ * 65 + qj_];
                 const double t_pp = cj * a_pp - sj * a_pq, t_pq = sj * a_pp + cj * a_pq;
                 const double t_qp = cj * a_qp - sj * a_qq, t_qq = sj * a_qp + cj * a_qq;
@@ -1410,21 +1417,18 @@ __global__ void __launch_bounds__(EIG_THREADS) omega_eig_kernel(const double* __
                 // the rotated pair itself ends up exactly zero (annihilated, or flushed when it no longer registers
                 // against the diagonal), as in the host's Jacobi: without this the off-diagonal norm stalls at
                 // rounding level above the stopping threshold and every matrix runs all 40 sweeps instead of ~9
-                if (ki == kj) { n_pq = 0.0; n_qp = 0.0; }
+                if (ki == lane) { n_pq = 0.0; n_qp = 0.0; }
                 A[pi_ * 65 + pj_] = n_pp;
                 A[pi_ * 65 + qj_] = n_pq;
                 A[qi_ * 65 + pj_] = n_qp;
                 A[qi_ * 65 + qj_] = n_qq;
             }
-            // V <- V J (pair k touches columns p, q of every row)
+            // V <- V J (pair `lane` touches columns p, q of every row)
 #pragma unroll 4
-            for (int idx = tid; idx < 2048; idx += EIG_THREADS) {
-                const int k = idx & 31, row = idx >> 5;
-                const int p_ = pp[k], q_ = pq[k];
-                const double c = rc[k], s = rs[k];
-                const double vkp = V[row * 65 + p_], vkq = V[row * 65 + q_];
-                V[row * 65 + p_] = c * vkp - s * vkq;
-                V[row * 65 + q_] = s * vkp + c * vkq;
+            for (int row = tid >> 5; row < 64; row += EIG_THREADS / 32) {
+                const double vkp = V[row * 65 + pj_], vkq = V[row * 65 + qj_];
+                V[row * 65 + pj_] = cj * vkp - sj * vkq;
+                V[row * 65 + qj_] = sj * vkp + cj * vkq;
             }
             __syncthreads();
         }
