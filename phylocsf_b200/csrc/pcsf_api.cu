@@ -1050,7 +1050,7 @@ int pcsf_batch_upload(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off
 // K0 (pcsf_k0.cuh): pleaves for `nalign` staged alignments. Grid = (alignments, tiles of the longest one), dynamic shared
 // memory = one tile of codon codes (all rows x tile positions). d_nt and d_codes are device allocations (aligned); the kernel
 // reads d_nt in whole words up to ceil(nt_bytes / 4), which reserve()'s head room covers.
-static int launch_frame_codes(pcsf_ctx* ctx, const void* d_nt, int64_t nt_bytes, const void* d_aln_off, const void* d_aln_len,
+static int launch_frame_codes(pcsf_ctx* ctx, void* d_nt, int64_t nt_bytes, const void* d_aln_off, const void* d_aln_len,
                               const void* d_roff, int64_t nalign, int max_len, int frames, void* d_codes) {
     if (nalign <= 0 || max_len < 3) return PCSF_OK;  // no codon anywhere
     const int tile = k0::choose_tile_pos(max_len, ctx->n_leaves);
@@ -1059,6 +1059,8 @@ static int launch_frame_codes(pcsf_ctx* ctx, const void* d_nt, int64_t nt_bytes,
     if (smem > (size_t)48 * 1024)
         CU(cudaFuncSetAttribute(frame_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (nalign > INT32_MAX) return fail(ctx, PCSF_ERR_INVALID_ARG, "pleaves on the device: too many alignments in one batch");
+    // the kernel reads the buffer's last word whole: give its bytes past the end a value (they never reach a code)
+    if (nt_bytes & 3) CU(cudaMemsetAsync((uint8_t*)d_nt + nt_bytes, 0, 4 - (nt_bytes & 3), ctx->stream));
     const int64_t tiles = ((int64_t)max_len + tile - 1) / tile;
     const dim3 grid((unsigned)nalign, (unsigned)std::min<int64_t>(tiles, 65535));
     frame_codes_kernel<<<grid, k0::THREADS, smem, ctx->stream>>>((const uint8_t*)d_nt, nt_bytes, (const int64_t*)d_aln_off,
