@@ -1048,13 +1048,13 @@ int pcsf_batch_upload(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off
 }
 
 // K0 (pcsf_k0.cuh): pleaves for `nalign` staged alignments. Grid = (alignments, tiles of the longest one), dynamic shared
-// memory = one tile of codon codes (all rows x tile positions). d_nt and d_codes are device allocations (aligned); the kernel
+// memory = the runs of codes the tile contributes to each frame. d_nt and d_codes are device allocations (aligned); the kernel
 // reads d_nt in whole words up to ceil(nt_bytes / 4), which reserve()'s head room covers.
 static int launch_frame_codes(pcsf_ctx* ctx, void* d_nt, int64_t nt_bytes, const void* d_aln_off, const void* d_aln_len,
                               const void* d_roff, int64_t nalign, int max_len, int frames, void* d_codes) {
     if (nalign <= 0 || max_len < 3) return PCSF_OK;  // no codon anywhere
-    const int tile = k0::choose_tile_pos(max_len, ctx->n_leaves);
-    const size_t smem = k0::smem_bytes(tile, ctx->n_leaves);
+    const int tile = k0::choose_tile_pos(max_len, ctx->n_leaves, frames);
+    const size_t smem = k0::smem_bytes(tile, ctx->n_leaves, frames);
     if (smem > (size_t)227 * 1024) return fail(ctx, PCSF_ERR_INVALID_ARG, "pleaves on the device: too many leaves for one shared-memory tile");
     if (smem > (size_t)48 * 1024)
         CU(cudaFuncSetAttribute(frame_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

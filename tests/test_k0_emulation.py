@@ -27,7 +27,7 @@ def emul(tmp_path_factory):
     for f, n in (("k0_decode4", 1), ("k0_codon4", 3), ("k0_revcomp4", 1)):
         getattr(L, f).argtypes = [ctypes.c_uint32] * n
         getattr(L, f).restype = ctypes.c_uint32
-    L.k0_choose_tile_pos.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.k0_choose_tile_pos.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.k0_choose_tile_pos.restype = ctypes.c_int
     return L
 
@@ -114,7 +114,7 @@ def test_emulated_kernel_matches_oracle_pleaves_on_ragged_batches(emul, frames, 
     alns = [["".join(alphabet[rng.integers(0, len(alphabet), size=L)]) for _ in range(n)] for L in lens]
     want, roff = oracle_frames(alns, frames)
     nt, off = pack(alns, rng)
-    for tile_pos, grid_y in ((16, 1), (48, 1), (48, 3), (64, 2), (emul.k0_choose_tile_pos(max(lens), n), 1), (352, 2)):
+    for tile_pos, grid_y in ((16, 1), (48, 1), (48, 3), (64, 2), (emul.k0_choose_tile_pos(max(lens), n, frames), 1), (352, 2)):
         got = run_emul(emul, nt, off, lens, roff, frames, n, tile_pos, grid_y)
         assert np.array_equal(got, want), (tile_pos, grid_y)
 
@@ -147,6 +147,6 @@ def test_emulated_kernel_any_byte_and_wide_trees(emul):
     want, roff = np.concatenate(want, axis=0), np.array(roff, dtype=np.int64)
     nt = np.concatenate([r.reshape(-1) for r in raw])
     off = np.array([0, raw[0].size, raw[0].size + raw[1].size], dtype=np.int64)
-    for tile_pos, grid_y in ((emul.k0_choose_tile_pos(max(lens), n), 16), (48, 5), (1024, 1)):
+    for tile_pos, grid_y in ((emul.k0_choose_tile_pos(max(lens), n, 6), 16), (48, 5), (1024, 1)):
         got = run_emul(emul, nt, off, lens, roff, 6, n, tile_pos, grid_y)
         assert np.array_equal(got, want), (tile_pos, grid_y)

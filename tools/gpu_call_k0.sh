@@ -1,5 +1,5 @@
 #!/bin/bash
-# one GPU call: K0 parity + the paths around it, headline bench (e2e is where K0 shows), chunk-size sweep, ncu of K0
+# one GPU call: K0 parity + the paths around it, headline bench (e2e is where K0 shows), ncu of K0
 set -u
 mkdir -p gpurun_out
 {
@@ -8,11 +8,9 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -k "pleaves or pipelined o
 timeout 900 python -m pytest tests/test_cli.py -x -q -m gpu -k "not omega and not multi_device and not launcher" 2>&1 | tail -5
 } > gpurun_out/k0_tests.log 2>&1
 timeout 600 python bench.py --no-extra --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/k0_bench_2m.json 2> gpurun_out/k0_bench_2m.err
-PCSF_CHUNK_COLS=4000000 timeout 600 python bench.py --no-extra --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/k0_bench_4m.json 2> gpurun_out/k0_bench_4m.err
-PCSF_CHUNK_COLS=1000000 timeout 600 python bench.py --no-extra --no-cpu-baseline --steps 5 --warmup 3 > gpurun_out/k0_bench_1m.json 2> gpurun_out/k0_bench_1m.err
 timeout 600 bash tools/profile_r02.sh k0 > gpurun_out/k0_profile.log 2>&1
 cat gpurun_out/k0_tests.log
-for f in gpurun_out/k0_bench_*.json; do python - "$f" <<'PY'
+for f in gpurun_out/k0_bench_2m.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
