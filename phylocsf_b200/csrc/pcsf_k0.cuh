@@ -16,9 +16,12 @@
 //            the byte goes to run[frame][column * n_leaves + leaf] (STS.U8, three running offsets per strand);
 //   stage 2  the runs leave as they are: LDS.128 -> STG.128 for every aligned 16-byte group, bytes for a run's
 //            unaligned head and tail.
+// Measured (profiles/r02_frame_codes_ncu_summary.json): 123.5 us per chunk = 1.89 TB/s = 29 % of the HBM peak, 3.9 x
+// the old kernel; issue slots 78 % busy - instruction-bound at ~28 instructions per nucleotide: per 16 positions ~146 for
+// the decode and the codons, ~100 for the 16 range-checked byte stores, ~115 of per-item overhead (item -> row / chunk,
+// 64-bit addresses, the three frames' run descriptors), and a seventh of the iterations idle (1,102 items over 256 threads).
 // An earlier form of this round kept the tile row-major (codes by leaf and position) and picked the output bytes out of
-// it in stage 2: 126.8 us per chunk, 29 instructions per nucleotide, 20 of them the per-byte column / leaf bookkeeping
-// of stage 2; this form does that bookkeeping with one add per byte.
+// it in stage 2 with per-byte column / leaf bookkeeping: 126.8 us - the same, so the simpler stage 2 stayed.
 // Everything that indexes is in the PCSF_HD functions below so that the same code runs, thread by thread, in a CPU
 // emulation (tests/k0_emul.cpp, tests/test_k0_emulation.py) against the oracle's pleaves on ragged inputs.
 #pragma once
