@@ -1050,8 +1050,8 @@ int pcsf_batch_upload(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off
 // K0 (pcsf_k0.cuh): pleaves for `nalign` staged alignments. Grid = (alignments, tiles of the longest one), dynamic shared
 // memory = the runs of codes the tile contributes to each frame. d_nt and d_codes are device allocations (aligned); the kernel
 // reads d_nt in whole words up to ceil(nt_bytes / 4), which reserve()'s head room covers.
-static int launch_frame_codes(pcsf_ctx* ctx, void* d_nt, int64_t nt_bytes, const void* d_aln_off, const void* d_aln_len,
-                              const void* d_roff, int64_t nalign, int max_len, int frames, void* d_codes) {
+static int launch_frame_codes(pcsf_ctx* ctx, cudaStream_t stream, void* d_nt, int64_t nt_bytes, const void* d_aln_off,
+                              const void* d_aln_len, const void* d_roff, int64_t nalign, int max_len, int frames, void* d_codes) {
     if (nalign <= 0 || max_len < 3) return PCSF_OK;  // no codon anywhere
     const int tile = k0::choose_tile_pos(max_len, ctx->n_leaves, frames);
     const size_t smem = k0::smem_bytes(tile, ctx->n_leaves, frames);
@@ -1060,10 +1060,10 @@ static int launch_frame_codes(pcsf_ctx* ctx, void* d_nt, int64_t nt_bytes, const
         CU(cudaFuncSetAttribute(frame_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (nalign > INT32_MAX) return fail(ctx, PCSF_ERR_INVALID_ARG, "pleaves on the device: too many alignments in one batch");
     // the kernel reads the buffer's last word whole: give its bytes past the end a value (they never reach a code)
-    if (nt_bytes & 3) CU(cudaMemsetAsync((uint8_t*)d_nt + nt_bytes, 0, 4 - (nt_bytes & 3), ctx->stream));
+    if (nt_bytes & 3) CU(cudaMemsetAsync((uint8_t*)d_nt + nt_bytes, 0, 4 - (nt_bytes & 3), stream));
     const int64_t tiles = ((int64_t)max_len + tile - 1) / tile;
     const dim3 grid((unsigned)nalign, (unsigned)std::min<int64_t>(tiles, 65535));
-    frame_codes_kernel<<<grid, k0::THREADS, smem, ctx->stream>>>((const uint8_t*)d_nt, nt_bytes, (const int64_t*)d_aln_off,
+    frame_codes_kernel<<<grid, k0::THREADS, smem, stream>>>((const uint8_t*)d_nt, nt_bytes, (const int64_t*)d_aln_off,
                                                                   (const int32_t*)d_aln_len, (const int64_t*)d_roff, frames,
                                                                   ctx->n_leaves, tile, (uint8_t*)d_codes);
     CU(cudaGetLastError());
@@ -1140,7 +1140,7 @@ int pcsf_batch_upload_alignments_parts(pcsf_ctx* ctx, int64_t nalign, const int6
     }
     CU(cudaMemcpyAsync(ctx->d_region_off.p, roff.data(), sizeof(int64_t) * (nregions + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev[7], ctx->stream));
-    TRY(launch_frame_codes(ctx, ctx->d_nt.p, nt_bytes, ctx->d_aln_off.p, ctx->d_aln_len.p, ctx->d_region_off.p, nalign, max_len,
+    TRY(launch_frame_codes(ctx, ctx->stream, ctx->d_nt.p, nt_bytes, ctx->d_aln_off.p, ctx->d_aln_len.p, ctx->d_region_off.p, nalign, max_len,
                            frames, ctx->d_codes.p));
     ctx->region_off = roff;
     ctx->nregions = nregions;
@@ -1305,11 +1305,15 @@ int pcsf_score_alignments(pcsf_ctx* ctx, int64_t nalign, const int64_t* aln_off,
         CU(cudaMemcpyAsync(ctx->pipe_aln_off[b].p, h_aoff[b].data(), sizeof(int64_t) * na, cudaMemcpyHostToDevice, ctx->copy_stream));
         CU(cudaMemcpyAsync(ctx->pipe_aln_len[b].p, aln_len + a0, sizeof(int32_t) * na, cudaMemcpyHostToDevice, ctx->copy_stream));
         CU(cudaMemcpyAsync(ctx->pipe_roff[b].p, h_roff[b].data(), sizeof(int64_t) * (nreg + 1), cudaMemcpyHostToDevice, ctx->copy_stream));
+        // pleaves (K0) rides on the copy stream behind its input: its CTAs cannot share an SM with the pruning kernel's (that
+        // one takes the whole register file), so they run on the SMs the previous chunk's pruning launch frees as it drains -
+        // inside its tail instead of between two pruning launches. Buffer b's codes were last read by the kernels of chunk k-2,
+        // which the wait on ev_done[b] above covers.
+        TRY(launch_frame_codes(ctx, ctx->copy_stream, ctx->pipe_nt[b].p, hi - lo, ctx->pipe_aln_off[b].p, ctx->pipe_aln_len[b].p,
+                               ctx->pipe_roff[b].p, na, max_len, frames, ctx->pipe_codes[b].p));
         CU(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-        // ---- compute stream: pleaves, pruning, reduction, results back ----
+        // ---- compute stream: pruning, reduction, results back ----
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-        TRY(launch_frame_codes(ctx, ctx->pipe_nt[b].p, hi - lo, ctx->pipe_aln_off[b].p, ctx->pipe_aln_len[b].p, ctx->pipe_roff[b].p,
-                               na, max_len, frames, ctx->pipe_codes[b].p));
         std::vector<Span> spans;
         for (int m = 0; m < n_models; m++) spans.push_back(Span{0, (int64_t)m * total, 0, (int32_t)total, m});
         const int64_t n_segs = nreg * n_models;
