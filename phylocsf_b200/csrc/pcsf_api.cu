@@ -922,6 +922,23 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         plain_items(op, ctx->items_t4);
     }
     ctx->n_tab4 = (int)quads.size();
+    // A push directly followed by its pop means the second subtree is a single lookup: nothing is parked, the first message
+    // stays in the registers and the lookup multiplies into it (OP_..._KEEP + OP_TAB_MUL). Same factors, same product.
+    // The producer's items do not change: a contraction still needs its P image, lookups never had items.
+    auto keep_in_registers = [](std::vector<Op>& ops) {
+        for (size_t i = 0; i + 1 < ops.size(); i++) {
+            const int k0 = ops[i].kind & 0xff, k1 = ops[i + 1].kind & 0xff;
+            if (k1 == OP_TAB_POP && (k0 == OP_GEMM_PUSH || k0 == OP_TAB_PUSH) && ops[i].c == ops[i + 1].c) {
+                ops[i].kind = k0 == OP_GEMM_PUSH ? (int)OP_GEMM_KEEP : (OP_TAB_KEEP | (ops[i].kind & ~0xff));
+                ops[i + 1].kind = OP_TAB_MUL | (ops[i + 1].kind & ~0xff);
+            }
+        }
+    };
+    if (!getenv("PCSF_NO_KEEP")) {  // A/B switch for the measurement in DESIGN section 3
+        keep_in_registers(ctx->ops_t);
+        keep_in_registers(ctx->ops_t3);
+        keep_in_registers(ctx->ops_t4);
+    }
     ctx->subtabs.insert(ctx->subtabs.end(), triples.begin(), triples.end());
     ctx->subtabs.insert(ctx->subtabs.end(), quads.begin(), quads.end());
     std::vector<long long> tab_off(ctx->subtabs.size());

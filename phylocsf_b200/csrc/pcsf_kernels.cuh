@@ -42,8 +42,17 @@ enum OpKind : int32_t {
     // of the usual epilogue
     OP_TAB_LEAF = 5,   // cur = W * G(c)
     OP_TAB_PUSH = 6,   // stack[c] = W
-    OP_TAB_POP = 7     // cur = W * stack[c]
+    OP_TAB_POP = 7,    // cur = W * stack[c]
+    // A push whose pop is the very next op - the sibling subtree is one table lookup - parks nothing: the message stays in
+    // registers and the lookup multiplies into it (same two factors, same product: bit-identical to push + pop).
+    OP_TAB_KEEP = 8,   // cur = W                                  (was OP_TAB_PUSH)
+    OP_TAB_MUL = 9,    // cur = cur * W                            (was OP_TAB_POP, right after a ..._KEEP)
+    OP_GEMM_KEEP = 10  // cur = P_a x cur                          (was OP_GEMM_PUSH)
 };
+__host__ __device__ inline bool op_is_table(int kind) {
+    const int k = kind & 0xff;
+    return k >= OP_TAB_LEAF && k <= OP_TAB_MUL;
+}
 struct Op {
     int32_t kind, a, b, c;
 };
@@ -908,7 +917,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
         if (warp_active)
             for (int oi = 0; oi < p.n_ops; oi++) {
                 const Op op = ops_s[oi];
-                if ((op.kind & 0xff) < OP_TAB_LEAF || (op.b & 0xffff) == 0xffff) continue;
+                if (!op_is_table(op.kind) || (op.b & 0xffff) == 0xffff) continue;
                 const double* W = reinterpret_cast<const double*>(scratch[2]) + p.tab_off[op.kind >> 8] + 16 * t;
                 uint32_t row0, row1;
                 table_rows(op, row0, row1);
@@ -988,9 +997,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
             }
             double acc[2][8][2];
             int ekind = op.kind;
-            if ((op.kind & 0xff) >= OP_TAB_LEAF) {
+            if (op_is_table(op.kind)) {
                 // -------------------- cherry + the edge above it: one 512-byte row of the cherry's table per column --------------------
-                ekind = (op.kind & 0xff) - OP_TAB_LEAF + OP_GEMM_LEAF;  // LEAF / PUSH / POP epilogue as after a contraction
+                const int tk = op.kind & 0xff;  // LEAF / PUSH / POP epilogue as after a contraction; KEEP / MUL: see OpKind
+                ekind = tk == OP_TAB_KEEP ? OP_GEMM_KEEP : tk == OP_TAB_MUL ? OP_TAB_MUL : tk - OP_TAB_LEAF + OP_GEMM_LEAF;
                 if (warp_active) {
                     const double* W = reinterpret_cast<const double*>(scratch[2]) + p.tab_off[op.kind >> 8] + 2 * t;
                     uint32_t row0, row1;
@@ -1031,7 +1041,28 @@ __global__ void __launch_bounds__(W_THREADS, 1) prune_wide_kernel(const PrunePar
             TL_MARK(oi * 8 + 2);
             }
             // ------------------------------ epilogue ------------------------------
-            if (ekind == OP_GEMM_PUSH) {  // park the message; only this thread ever touches these addresses
+            if (ekind == OP_GEMM_KEEP) {  // the sibling is the next op's lookup: the message stays where it is
+                if (warp_active) {
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            cur[T][j][0] = acc[T][j][0];
+                            cur[T][j][1] = acc[T][j][1];
+                        }
+                }
+            } else if (ekind == OP_TAB_MUL) {  // ... and the lookup multiplies into it
+                if (warp_active) {
+#pragma unroll
+                    for (int T = 0; T < 2; T++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            cur[T][j][0] = acc[T][j][0] * cur[T][j][0];
+                            cur[T][j][1] = acc[T][j][1] * cur[T][j][1];
+                        }
+                    if (RESCALE) rescale_columns(cur, esum);
+                }
+            } else if (ekind == OP_GEMM_PUSH) {  // park the message; only this thread ever touches these addresses
                 if (warp_active) {
                     double2* slot = reinterpret_cast<double2*>(park(op.c));
 #pragma unroll
