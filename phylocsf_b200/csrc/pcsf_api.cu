@@ -203,15 +203,17 @@ struct ProgramBuilder {
     int nl;
     const std::vector<int32_t>& ch;
     std::vector<Op> ops;
-    std::vector<int> need;
+    std::vector<int> need, leaves;
     int height = 0, max_height = 0, n_gemm = 0;
-    ProgramBuilder(int n_leaves, const std::vector<int32_t>& children) : nl(n_leaves), ch(children), need(2 * n_leaves - 1, 0) {}
+    ProgramBuilder(int n_leaves, const std::vector<int32_t>& children)
+        : nl(n_leaves), ch(children), need(2 * n_leaves - 1, 0), leaves(2 * n_leaves - 1, 1) {}
     int lc(int i) const { return ch[2 * (i - nl)]; }
     int rc(int i) const { return ch[2 * (i - nl) + 1]; }
     void compute_need() {
         for (int i = nl; i < 2 * nl - 1; i++) {  // children precede parents in T numbering
             const int l = lc(i), r = rc(i);
             const bool li = l >= nl, ri = r >= nl;
+            leaves[i] = leaves[l] + leaves[r];
             if (!li && !ri) need[i] = 1;
             else if (li && ri) {
                 const int a = std::max(need[l], need[r]), b = std::min(need[l], need[r]);
@@ -226,7 +228,11 @@ struct ProgramBuilder {
         if (!li && !ri) {
             ops.push_back({OP_CHERRY, l, r, 0});
         } else if (li && ri) {
-            const int first = need[l] >= need[r] ? l : r, second = first == l ? r : l;
+            // Sethi-Ullman: the child that needs more parked partials goes first. On a tie the one with more leaves does: with
+            // equal needs of 1 both are caterpillars, and the smaller one is the likelier to be a single table lookup, which as
+            // the SECOND subtree costs no stack round trip at all (OP_..._KEEP + OP_TAB_MUL below).
+            const int first = need[l] != need[r] ? (need[l] > need[r] ? l : r) : (leaves[l] >= leaves[r] ? l : r);
+            const int second = first == l ? r : l;
             emit(first);
             ops.push_back({OP_GEMM_PUSH, first, 0, height});
             n_gemm++;
