@@ -62,6 +62,20 @@ int pcsf_omega_q(const double *v, double *Q, double *pi, char *err, int errlen);
 int pcsf_omega_score(pcsf_ctx *ctx, int64_t nregions, const int64_t *region_off, const uint8_t *codes, double omega_H1,
                      double sigma_H1, double *out_score, double *out_diag, int32_t *out_status);
 
+/*
+ * The tree program pcsf_tree_set derives from T.children for the pruning kernels (csrc/pcsf_program.hpp), for inspection and
+ * for the CPU tests that interpret it against the reference's pruning (lib/CamlPaml/PhyloLik.ml:73-93). No GPU needed.
+ *   level     0 = the plain post-order program (Sethi-Ullman order), 2 / 3 / 4 = the table programs of the wide kernel
+ *   keep      non-zero: with the KEEP / MUL rewrite (the default of the library), 0: every push and pop in place
+ *   ops_out   4 ints per op: kind (| table << 8), a, b, c as in csrc/pcsf_program.hpp (OpKind)
+ *   tabs_out  5 ints per memoised subtree: leaf a, leaf b, joining leaf (-1: a cherry), node whose upward edge the table
+ *             includes, index of the table it extends (-1: a cherry); cherries first, then 3-leaf, then 4-leaf subtrees
+ *   info_out  n cherries, n 3-leaf subtrees, n 4-leaf subtrees, parked partials needed (4 ints; may be NULL)
+ * Returns the number of ops, or a negative error (bad tree, buffers too small).
+ */
+int pcsf_host_tree_program(int n_leaves, const int32_t *children, int level, int keep, int32_t *ops_out, int max_ops,
+                           int32_t *tabs_out, int max_tabs, int32_t *info_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,62 +195,6 @@ int reserve(pcsf_ctx* ctx, DevBuf& b, size_t bytes) {
         if (r_ != PCSF_OK) return r_; \
     } while (0)
 
-// ---- tree program ------------------------------------------------------------------------------
-// Post-order schedule that keeps the partial of the current subtree in registers. At a node with two
-// internal children the child needing more live partials goes first (Sethi-Ullman), its message is
-// parked on the stack while the other subtree is evaluated.
-struct ProgramBuilder {
-    int nl;
-    const std::vector<int32_t>& ch;
-    std::vector<Op> ops;
-    std::vector<int> need, leaves;
-    int height = 0, max_height = 0, n_gemm = 0;
-    ProgramBuilder(int n_leaves, const std::vector<int32_t>& children)
-        : nl(n_leaves), ch(children), need(2 * n_leaves - 1, 0), leaves(2 * n_leaves - 1, 1) {}
-    int lc(int i) const { return ch[2 * (i - nl)]; }
-    int rc(int i) const { return ch[2 * (i - nl) + 1]; }
-    void compute_need() {
-        for (int i = nl; i < 2 * nl - 1; i++) {  // children precede parents in T numbering
-            const int l = lc(i), r = rc(i);
-            const bool li = l >= nl, ri = r >= nl;
-            leaves[i] = leaves[l] + leaves[r];
-            if (!li && !ri) need[i] = 1;
-            else if (li && ri) {
-                const int a = std::max(need[l], need[r]), b = std::min(need[l], need[r]);
-                need[i] = std::max(a, b + 1);
-            } else need[i] = need[li ? l : r];
-        }
-    }
-    void emit(int i) {
-        // iterative post-order would also do; depth is bounded by the tree height (<= n_leaves)
-        const int l = lc(i), r = rc(i);
-        const bool li = l >= nl, ri = r >= nl;
-        if (!li && !ri) {
-            ops.push_back({OP_CHERRY, l, r, 0});
-        } else if (li && ri) {
-            // Sethi-Ullman: the child that needs more parked partials goes first. On a tie the one with more leaves does: with
-            // equal needs of 1 both are caterpillars, and the smaller one is the likelier to be a single table lookup, which as
-            // the SECOND subtree costs no stack round trip at all (OP_..._KEEP + OP_TAB_MUL below).
-            const int first = need[l] != need[r] ? (need[l] > need[r] ? l : r) : (leaves[l] >= leaves[r] ? l : r);
-            const int second = first == l ? r : l;
-            emit(first);
-            ops.push_back({OP_GEMM_PUSH, first, 0, height});
-            n_gemm++;
-            height++;
-            max_height = std::max(max_height, height);
-            emit(second);
-            height--;
-            ops.push_back({OP_GEMM_POP, second, 0, height});
-            n_gemm++;
-        } else {
-            const int inner = li ? l : r, leaf = li ? r : l;
-            emit(inner);
-            ops.push_back({OP_GEMM_LEAF, inner, leaf, 0});
-            n_gemm++;
-        }
-    }
-};
-
 int r16(int x) { return (x + 15) & ~15; }
 int prune_smem_for(int n_ops, int n_items, int n_leaves) {
     return P_STAGES * FRAG_BYTES + M_STAGES * STACK_LEVEL_BYTES + PRUNE_BAR_BYTES + r16(n_ops * (int)sizeof(Op)) +
@@ -814,146 +758,29 @@ int pcsf_tree_set(pcsf_ctx* ctx, int n_leaves, const int32_t* children, const do
         return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: too many leaves for the pruning kernel's shared memory");
     // every check comes before the context is touched: a call that fails leaves the previous tree in place
     const std::vector<int32_t> new_children(children, children + 2 * (n_leaves - 1));
-    ProgramBuilder pb(n_leaves, new_children);
-    pb.compute_need();
-    pb.emit(n - 1);
-    pb.ops.push_back({OP_ROOT, 0, 0, 0});
-    if (pb.max_height > MAX_STACK_LEVELS) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: tree needs more than 16 parked partials");
+    TreePrograms tp = build_tree_programs(n_leaves, new_children, getenv("PCSF_NO_KEEP") == nullptr);  // pcsf_program.hpp
+    if (tp.max_levels > MAX_STACK_LEVELS) return fail(ctx, PCSF_ERR_INVALID_ARG, "pcsf_tree_set: tree needs more than 16 parked partials");
     ctx->n_leaves = 0;  // from here to the last upload the context has no tree (check_ready fails if an upload does)
     for (auto& m : ctx->models) { m.nscales = 0; m.cherry_built.clear(); tab_release(m); }  // tables belong to the previous tree
     ctx->tree_hash = fnv1a(branch_len, sizeof(double) * (n - 1), fnv1a(children, sizeof(int32_t) * 2 * (n_leaves - 1)));
     ctx->n_branches = n - 1;
     ctx->children = new_children;
     ctx->branch_len.assign(branch_len, branch_len + (n - 1));
-    ctx->ops = pb.ops;
-    ctx->n_gemm = pb.n_gemm;
-    ctx->max_levels = pb.max_height;
-    ctx->items.clear();
-    for (const Op& op : ctx->ops) {
-        if (op.kind == OP_CHERRY) { ctx->items.push_back({ITEM_LEAF, op.a}); ctx->items.push_back({ITEM_LEAF, op.b}); }
-        else if (op.kind == OP_GEMM_LEAF) { ctx->items.push_back({ITEM_P, op.a}); ctx->items.push_back({ITEM_LEAF, op.b}); }
-        else if (op.kind == OP_GEMM_PUSH) ctx->items.push_back({ITEM_P, op.a});
-        else if (op.kind == OP_GEMM_POP) { ctx->items.push_back({ITEM_P, op.a}); ctx->items.push_back({ITEM_POP, op.c}); }
-    }
-    // The table programs. Level 2: (OP_CHERRY, the contraction over the edge above the cherry) -> one lookup in the
-    // cherry's table. Level 3: when the cherry's sibling is a leaf and the node above them has an edge of its own,
-    // (OP_CHERRY, OP_GEMM_LEAF, the contraction over that edge) -> one lookup in the 3-leaf table.
-    auto is_gemm = [](const Op& o) { return o.kind == OP_GEMM_LEAF || o.kind == OP_GEMM_PUSH || o.kind == OP_GEMM_POP; };
-    auto plain_items = [](const Op& op, std::vector<Item>& items) {
-        if (op.kind == OP_CHERRY) { items.push_back({ITEM_LEAF, op.a}); items.push_back({ITEM_LEAF, op.b}); }
-        else if (op.kind == OP_GEMM_LEAF) { items.push_back({ITEM_P, op.a}); items.push_back({ITEM_LEAF, op.b}); }
-        else if (op.kind == OP_GEMM_PUSH || op.kind == OP_GEMM_POP) items.push_back({ITEM_P, op.a});
-    };
-    auto table_op = [](const Op& g, int table, int la, int lb, int lc, int ld) {  // g: the contraction the lookup replaces last
-        const int kind = (g.kind == OP_GEMM_LEAF ? OP_TAB_LEAF : g.kind == OP_GEMM_PUSH ? OP_TAB_PUSH : OP_TAB_POP) | (table << 8);
-        const uint32_t b = (uint32_t)(lc < 0 ? 0xffff : lc) | ((uint32_t)(ld < 0 ? 0xffff : ld) << 16);
-        return Op{kind, la | (lb << 16), (int32_t)b, g.kind == OP_GEMM_LEAF ? g.b : g.c};
-    };
-    ctx->ops_t.clear();
-    ctx->items_t.clear();
-    ctx->ops_t3.clear();
-    ctx->items_t3.clear();
-    ctx->subtabs.clear();
-    std::vector<SubTab> triples, quads;
-    std::vector<int> cherry_table_at(ctx->ops.size(), -1), triple_table_at(ctx->ops.size(), -1);
-    ctx->ops_t4.clear();
-    ctx->items_t4.clear();
-    for (size_t i = 0; i + 1 < ctx->ops.size(); i++)
-        if (ctx->ops[i].kind == OP_CHERRY && is_gemm(ctx->ops[i + 1])) {
-            cherry_table_at[i] = (int)ctx->subtabs.size();
-            ctx->subtabs.push_back(SubTab{ctx->ops[i].a, ctx->ops[i].b, -1, ctx->ops[i + 1].a, -1, 0, 0});
-        }
-    ctx->n_tab2 = (int)ctx->subtabs.size();
-    for (size_t i = 0; i < ctx->ops.size(); i++) {  // level 2
-        const Op& op = ctx->ops[i];
-        if (cherry_table_at[i] >= 0) {
-            const Op& g = ctx->ops[i + 1];
-            ctx->ops_t.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1, -1));
-            if (g.kind == OP_GEMM_LEAF) ctx->items_t.push_back({ITEM_LEAF, g.b});
-            i++;
-            continue;
-        }
-        ctx->ops_t.push_back(op);
-        plain_items(op, ctx->items_t);
-    }
-    for (size_t i = 0; i < ctx->ops.size(); i++) {  // level 3
-        const Op& op = ctx->ops[i];
-        if (cherry_table_at[i] >= 0) {
-            const Op& g = ctx->ops[i + 1];
-            if (g.kind == OP_GEMM_LEAF && i + 2 < ctx->ops.size() && is_gemm(ctx->ops[i + 2])) {
-                const Op& g2 = ctx->ops[i + 2];  // the edge above the node that joins the cherry and the leaf g.b
-                const int ti = ctx->n_tab2 + (int)triples.size();
-                triple_table_at[i] = ti;
-                triples.push_back(SubTab{op.a, op.b, g.b, g2.a, cherry_table_at[i], 0, 0});
-                ctx->ops_t3.push_back(table_op(g2, ti, op.a, op.b, g.b, -1));
-                if (g2.kind == OP_GEMM_LEAF) ctx->items_t3.push_back({ITEM_LEAF, g2.b});
-                i += 2;
-                continue;
-            }
-            ctx->ops_t3.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1, -1));
-            if (g.kind == OP_GEMM_LEAF) ctx->items_t3.push_back({ITEM_LEAF, g.b});
-            i++;
-            continue;
-        }
-        ctx->ops_t3.push_back(op);
-        plain_items(op, ctx->items_t3);
-    }
-    ctx->n_tab3 = (int)triples.size();
-    for (size_t i = 0; i < ctx->ops.size(); i++) {  // level 4: a further leaf d joins the 3-leaf subtree
-        const Op& op = ctx->ops[i];
-        if (cherry_table_at[i] >= 0) {
-            const Op& g = ctx->ops[i + 1];
-            if (triple_table_at[i] >= 0) {
-                const Op& g2 = ctx->ops[i + 2];
-                if (g2.kind == OP_GEMM_LEAF && i + 3 < ctx->ops.size() && is_gemm(ctx->ops[i + 3])) {
-                    const Op& g3 = ctx->ops[i + 3];  // the edge above the node that joins the 3-leaf subtree and the leaf g2.b
-                    const int ti = ctx->n_tab2 + ctx->n_tab3 + (int)quads.size();
-                    quads.push_back(SubTab{op.a, op.b, g2.b, g3.a, triple_table_at[i], 0, 0});
-                    ctx->ops_t4.push_back(table_op(g3, ti, op.a, op.b, g.b, g2.b));
-                    if (g3.kind == OP_GEMM_LEAF) ctx->items_t4.push_back({ITEM_LEAF, g3.b});
-                    i += 3;
-                    continue;
-                }
-                ctx->ops_t4.push_back(table_op(g2, triple_table_at[i], op.a, op.b, g.b, -1));
-                if (g2.kind == OP_GEMM_LEAF) ctx->items_t4.push_back({ITEM_LEAF, g2.b});
-                i += 2;
-                continue;
-            }
-            ctx->ops_t4.push_back(table_op(g, cherry_table_at[i], op.a, op.b, -1, -1));
-            if (g.kind == OP_GEMM_LEAF) ctx->items_t4.push_back({ITEM_LEAF, g.b});
-            i++;
-            continue;
-        }
-        ctx->ops_t4.push_back(op);
-        plain_items(op, ctx->items_t4);
-    }
-    ctx->n_tab4 = (int)quads.size();
-    // A push directly followed by its pop means the second subtree is a single lookup: nothing is parked, the first message
-    // stays in the registers and the lookup multiplies into it (OP_..._KEEP + OP_TAB_MUL). Same factors, same product.
-    // The producer's items do not change: a contraction still needs its P image, lookups never had items.
-    auto keep_in_registers = [](std::vector<Op>& ops) {
-        for (size_t i = 0; i + 1 < ops.size(); i++) {
-            const int k0 = ops[i].kind & 0xff, k1 = ops[i + 1].kind & 0xff;
-            if (k1 == OP_TAB_POP && (k0 == OP_GEMM_PUSH || k0 == OP_TAB_PUSH) && ops[i].c == ops[i + 1].c) {
-                ops[i].kind = k0 == OP_GEMM_PUSH ? (int)OP_GEMM_KEEP : (OP_TAB_KEEP | (ops[i].kind & ~0xff));
-                ops[i + 1].kind = OP_TAB_MUL | (ops[i + 1].kind & ~0xff);
-            }
-        }
-    };
-    if (!getenv("PCSF_NO_KEEP")) {  // A/B switch for the measurement in DESIGN section 3
-        keep_in_registers(ctx->ops_t);
-        keep_in_registers(ctx->ops_t3);
-        keep_in_registers(ctx->ops_t4);
-    }
-    ctx->subtabs.insert(ctx->subtabs.end(), triples.begin(), triples.end());
-    ctx->subtabs.insert(ctx->subtabs.end(), quads.begin(), quads.end());
-    std::vector<long long> tab_off(ctx->subtabs.size());
-    for (size_t k = 0; k < ctx->subtabs.size(); k++) {
-        const long long k2 = std::min<long long>(k, ctx->n_tab2), k3 = std::min<long long>(std::max<long long>((long long)k - ctx->n_tab2, 0), ctx->n_tab3),
-                        k4 = std::max<long long>((long long)k - ctx->n_tab2 - ctx->n_tab3, 0);
-        tab_off[k] = k2 * CHERRY_TABLE + k3 * TRIPLE_TABLE + k4 * QUAD_TABLE;
-        ctx->subtabs[k].off = tab_off[k];
-    }
+    ctx->ops = std::move(tp.ops);
+    ctx->items = std::move(tp.items);
+    ctx->ops_t = std::move(tp.ops_t);
+    ctx->items_t = std::move(tp.items_t);
+    ctx->ops_t3 = std::move(tp.ops_t3);
+    ctx->items_t3 = std::move(tp.items_t3);
+    ctx->ops_t4 = std::move(tp.ops_t4);
+    ctx->items_t4 = std::move(tp.items_t4);
+    ctx->subtabs = std::move(tp.subtabs);
+    ctx->n_tab2 = tp.n_tab2;
+    ctx->n_tab3 = tp.n_tab3;
+    ctx->n_tab4 = tp.n_tab4;
+    ctx->n_gemm = tp.n_gemm;
+    ctx->max_levels = tp.max_levels;
+    const std::vector<long long>& tab_off = tp.tab_off;
     if (n_leaves > 0xfffe) { ctx->n_tab2 = ctx->n_tab3 = ctx->n_tab4 = 0; }  // leaf ids are packed into 16 bits, 0xffff = none
     CU(cudaStreamSynchronize(ctx->stream));
     for (void** q : {(void**)&ctx->d_branch_len, (void**)&ctx->d_ops, (void**)&ctx->d_items, (void**)&ctx->d_ops_t, (void**)&ctx->d_items_t,

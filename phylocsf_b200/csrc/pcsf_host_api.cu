@@ -5,6 +5,7 @@
 #include <set>
 #include <sstream>
 
+#include "pcsf_program.hpp"
 #include "host/omega_strategy.hpp"
 #include "host/paramset.hpp"
 
@@ -131,6 +132,43 @@ int pcsf_omega_score(pcsf_ctx* ctx, int64_t nregions, const int64_t* region_off,
     } catch (const std::exception&) {
         return PCSF_ERR_CUDA;  // pcsf_last_error(ctx) holds the message of the failing call
     }
+}
+
+int pcsf_host_tree_program(int n_leaves, const int32_t* children, int level, int keep, int32_t* ops_out, int max_ops,
+                           int32_t* tabs_out, int max_tabs, int32_t* info_out) {
+    if (n_leaves < 2 || !children || (level != 0 && level != 2 && level != 3 && level != 4)) return PCSF_ERR_INVALID_ARG;
+    const int n = 2 * n_leaves - 1;
+    std::vector<int> seen(n, 0);
+    for (int i = n_leaves; i < n; i++)
+        for (int k = 0; k < 2; k++) {
+            const int c = children[2 * (i - n_leaves) + k];
+            if (c < 0 || c >= i || seen[c]++) return PCSF_ERR_INVALID_ARG;  // the checks of pcsf_tree_set
+        }
+    const pcsf::TreePrograms tp =
+        pcsf::build_tree_programs(n_leaves, std::vector<int32_t>(children, children + 2 * (n_leaves - 1)), keep != 0);
+    const std::vector<pcsf::Op>& ops = level == 4 ? tp.ops_t4 : level == 3 ? tp.ops_t3 : level == 2 ? tp.ops_t : tp.ops;
+    if (info_out) {
+        info_out[0] = tp.n_tab2;
+        info_out[1] = tp.n_tab3;
+        info_out[2] = tp.n_tab4;
+        info_out[3] = tp.max_levels;
+    }
+    if ((int)ops.size() > max_ops || (int)tp.subtabs.size() > max_tabs || (!ops_out && max_ops > 0) || (!tabs_out && max_tabs > 0))
+        return PCSF_ERR_INVALID_ARG;
+    for (size_t i = 0; i < ops.size(); i++) {
+        ops_out[4 * i] = ops[i].kind;
+        ops_out[4 * i + 1] = ops[i].a;
+        ops_out[4 * i + 2] = ops[i].b;
+        ops_out[4 * i + 3] = ops[i].c;
+    }
+    for (size_t k = 0; k < tp.subtabs.size(); k++) {
+        tabs_out[5 * k] = tp.subtabs[k].la;
+        tabs_out[5 * k + 1] = tp.subtabs[k].lb;
+        tabs_out[5 * k + 2] = tp.subtabs[k].lnew;
+        tabs_out[5 * k + 3] = tp.subtabs[k].edge;
+        tabs_out[5 * k + 4] = tp.subtabs[k].src;
+    }
+    return (int)ops.size();
 }
 
 }  // extern "C"

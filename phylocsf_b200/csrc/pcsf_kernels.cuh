@@ -19,57 +19,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pcsf_program.hpp"  // Op / Item / SubTab and the host-side builder of the tree programs
+
 namespace pcsf {
 
 constexpr int K = 64;
 constexpr int PT_SLOT = 65 * 64;         // doubles per (scale, branch) table slot
 constexpr int PT_SLOT_BYTES = PT_SLOT * 8;
 constexpr int FRAG_BYTES = 64 * 64 * 8;  // fragment-ordered P image of an internal edge
-
-// ---- tree program (built on the host from T.children) -----------------------------------------
-enum OpKind : int32_t {
-    OP_CHERRY = 0,     // cur = G(a) * G(b)                       a, b leaves
-    OP_GEMM_LEAF = 1,  // cur = (P_a x cur) * G(b)                a internal child, b sibling leaf
-    OP_GEMM_PUSH = 2,  // stack[c] = P_a x cur                    sibling subtree still to come
-    OP_GEMM_POP = 3,   // cur = (P_a x cur) * stack[c]
-    OP_ROOT = 4,       // z = cur . prior, log z, root posterior . log prior
-    // table program (wide form, P sets that carry subtree tables): a cherry (leaves a, b) - or a cherry plus the
-    // leaf c next to it - and the contractions up to and including the edge above that subtree are one lookup,
-    //   W2[code_a][code_b][.]         = P_v x (G(a) * G(b))
-    //   W3[code_a][code_b][code_c][.] = P_u x (W2[code_a][code_b] * G(c))
-    //   W4[code_a][code_b][code_c][code_d] = P_w x (W3[code_a][code_b][code_c] * G(d))     (caterpillar of four)
-    // Encoding: kind | table << 8, a = leaf a | leaf b << 16, b = leaf c | leaf d << 16 (0xffff = none), c = operand
-    // of the usual epilogue
-    OP_TAB_LEAF = 5,   // cur = W * G(c)
-    OP_TAB_PUSH = 6,   // stack[c] = W
-    OP_TAB_POP = 7,    // cur = W * stack[c]
-    // A push whose pop is the very next op - the sibling subtree is one table lookup - parks nothing: the message stays in
-    // registers and the lookup multiplies into it (same two factors, same product: bit-identical to push + pop).
-    OP_TAB_KEEP = 8,   // cur = W                                  (was OP_TAB_PUSH)
-    OP_TAB_MUL = 9,    // cur = cur * W                            (was OP_TAB_POP, right after a ..._KEEP)
-    OP_GEMM_KEEP = 10  // cur = P_a x cur                          (was OP_GEMM_PUSH)
-};
-__host__ __device__ inline bool op_is_table(int kind) {
-    const int k = kind & 0xff;
-    return k >= OP_TAB_LEAF && k <= OP_TAB_MUL;
-}
-struct Op {
-    int32_t kind, a, b, c;
-};
-constexpr int CHERRY_ROWS = 65 * 65;              // code pairs, 64 = marginalise
-constexpr int CHERRY_TABLE = CHERRY_ROWS * 64;    // doubles per cherry table (2.16 MB)
-constexpr int TRIPLE_ROWS = 65 * 65 * 65;         // code triples
-constexpr long long TRIPLE_TABLE = (long long)TRIPLE_ROWS * 64;  // doubles per 3-leaf table (140.6 MB)
-constexpr int QUAD_ROWS = 65 * 65 * 65 * 65;      // code quadruples
-constexpr long long QUAD_TABLE = (long long)QUAD_ROWS * 64;      // doubles per 4-leaf table (9.14 GB)
-struct SubTab {          // one memoised subtree: a cherry, or the subtree of table `src` plus one more leaf
-    int32_t la, lb;      // cherries: the two leaves
-    int32_t lnew;        // deeper tables: the leaf that joins the subtree of table `src` (-1 for a cherry)
-    int32_t edge;        // the node whose upward edge the table includes
-    int32_t src;         // deeper tables: index of the table they are built from
-    int32_t pad;
-    long long off;       // offset of the table (doubles) in the P set's table block
-};
 
 // ---- work description --------------------------------------------------------------------------
 // A span = a run of codon columns scored under one P set (one model at one tree scale). Tiles of
@@ -322,16 +279,6 @@ constexpr int PRUNE_BAR_BYTES = 256;                         // pfull[2] pempty[
 // setmaxnreg targets. Launch allocation is 65536 / threads (96 for 640 threads, 168 for 384).
 constexpr int PROD_REGS = PRUNE_T == 1 ? 32 : 56;  // inc can only take what dec released (CTA pool): (launch-PROD)*128 >= (COMPUTE-launch)*32*PRUNE_WARPS
 constexpr int COMPUTE_REGS = PRUNE_T == 1 ? 112 : 224;
-
-// What the producer warpgroup stages for the compute warps, in program order (built on the host).
-enum ItemKind : int32_t {
-    ITEM_P = 0,     // fragment-ordered P image of internal edge `a`            -> P ring (TMA bulk copy)
-    ITEM_LEAF = 1,  // leaf message of leaf `a`: gathered rows of its P^T table  -> M ring (cp.async gather)
-    ITEM_POP = 2    // parked partial of stack level `a`                         -> M ring (TMA bulk copy)
-};
-struct Item {
-    int32_t kind, a;
-};
 
 struct PruneParams {
     const Op* ops;

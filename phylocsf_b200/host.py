@@ -11,6 +11,7 @@ from . import _native as N
 HOST_SYMBOLS = [
     "pcsf_paramset_load", "pcsf_paramset_free", "pcsf_paramset_n_leaves", "pcsf_paramset_leaf_label",
     "pcsf_paramset_tree", "pcsf_paramset_qdiag", "pcsf_paramset_install", "pcsf_qdiag_reversible", "pcsf_omega_q", "pcsf_omega_score",
+    "pcsf_host_tree_program",
 ]
 
 
@@ -34,6 +35,7 @@ def _lib():
         L.pcsf_qdiag_reversible.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_char_p, ctypes.c_int]
         L.pcsf_omega_q.argtypes = [vp, vp, vp, ctypes.c_char_p, ctypes.c_int]
         L.pcsf_omega_score.argtypes = [vp, ctypes.c_int64, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]
+        L.pcsf_host_tree_program.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp]
         L._host_ready = True
     return L
 
@@ -117,3 +119,18 @@ def omega_score(ctx, region_off, codes, omega_H1=0.2, sigma_H1=0.01):
     ctx._check(rc, ok_numeric=True)
     ctx.nregions = R
     return score, diag, st
+
+
+def tree_program(n_leaves, children, level=0, keep=True):
+    """pcsf_host_tree_program: (ops int32 [n_ops, 4], subtabs int32 [n_tabs, 5], (n_tab2, n_tab3, n_tab4, max_levels)).
+    Host logic only - works without a GPU."""
+    L = _lib()
+    ch = np.ascontiguousarray(children, dtype=np.int32).reshape(-1)
+    ops = np.zeros((4 * n_leaves + 8, 4), dtype=np.int32)
+    tabs = np.zeros((n_leaves + 1, 5), dtype=np.int32)
+    info = np.zeros(4, dtype=np.int32)
+    n = L.pcsf_host_tree_program(n_leaves, N.ptr(ch), level, 1 if keep else 0, N.ptr(ops), ops.shape[0], N.ptr(tabs), tabs.shape[0],
+                                 N.ptr(info))
+    if n < 0:
+        raise HostError("pcsf_host_tree_program failed (%d)" % n)
+    return ops[:n].copy(), tabs[: int(info[:3].sum())].copy(), tuple(int(x) for x in info)
